@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) here.
+
+TEST INFRASTRUCTURE ONLY (see oracle/README.md).  Run in the build container:
+
+    python oracle/gen_golden.py            # all cases
+    python oracle/gen_golden.py g1 e2      # selected cases
+
+The reference cannot travel to the GPU box, so the vectors are committed as small fixtures.
+Each fixture stores the inputs, rapt.params overrides, the reference trajectory (all rows) and
+the per-solver-call counters (nfcn, nstep, naccpt, nrejct) = scipy iwork[16:20]
+(scipy 1.18.1 `_dop`, numpy 2.3.5).
+"""
+import os, sys, time, json
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+import warnings
+warnings.filterwarnings("ignore", category=SyntaxWarning)
+import refshim
+from rapt_b200 import synth
+
+rapt = refshim.load_reference()
+from rapt import fields as rf, utils as ru
+GOLD = os.path.join(ROOT, "tests", "golden")
+Re, e, m_pr, m_el, c = rapt.Re, rapt.e, rapt.m_pr, rapt.m_el, rapt.c
+
+
+def save(name, **arrs):
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print(f"  wrote {name}.npz ({os.path.getsize(path)/1024:.1f} KiB)")
+
+
+def take_log():
+    L = np.array(refshim.SOLVER_LOG, dtype=np.int64).reshape(-1, 4)
+    refshim.SOLVER_LOG.clear()
+    return L
+
+
+def run_particle(pos, vel, mass, charge, field, delta, t0=0.0, **par):
+    refshim.reset_params(rapt, **par)
+    refshim.SOLVER_LOG.clear()
+    p = rapt.Particle(pos=tuple(pos), vel=tuple(vel), t0=t0, mass=mass, charge=charge, field=field)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        p.advance(delta)
+    return p, take_log()
+
+
+def run_gc(pos, v, pa, mass, charge, field, delta, eom="TaoChanBrizardEOM", t0=0.0, **par):
+    refshim.reset_params(rapt, **par)
+    refshim.SOLVER_LOG.clear()
+    g = rapt.GuidingCenter(pos=tuple(pos), v=v, pa=pa, t0=t0, mass=mass, charge=charge, field=field)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        g.advance(delta, eom=eom)
+    return g, take_log()
+
+
+def parjson(**par):
+    return np.array(json.dumps(par))
+
+
+# ----------------------------------------------------------------------------- cases
+def case_g1():
+    """README.md:33-52."""
+    v = ru.speedfromKE(1e6, m_pr, 'ev'); pa = 30 * np.pi / 180
+    pos = (6 * Re, 0, 0); vel = (0, -v * np.sin(pa), v * np.cos(pa))
+    p, L = run_particle(pos, vel, m_pr, e, rf.EarthDipole(), 10, cyclotronresolution=20)
+    save("g1_readme", pos=np.array(pos, float), vel=np.array(vel), mass=m_pr, charge=e, delta=10.0,
+         params=parjson(cyclotronresolution=20), traj=p.trajectory, counters=L, tcur=p.tcur)
+
+
+def case_g1b():
+    v = ru.speedfromKE(1e6, m_pr, 'ev')
+    pos = (3.1 * Re, 2.3 * Re, 0.7 * Re)
+    vel = (v * 0.31, -v * 0.52, v * np.sqrt(1 - 0.31 ** 2 - 0.52 ** 2))
+    p, L = run_particle(pos, vel, m_pr, e, rf.EarthDipole(), 5, cyclotronresolution=20)
+    save("g1b_generic", pos=np.array(pos), vel=np.array(vel), mass=m_pr, charge=e, delta=5.0,
+         params=parjson(cyclotronresolution=20), traj=p.trajectory, counters=L, tcur=p.tcur)
+    # second advance() call on the same object (dt recomputed from the current state)
+    refshim.SOLVER_LOG.clear()
+    p.advance(1.0)
+    save("g1b_second_call", pos=np.array(pos), vel=np.array(vel), mass=m_pr, charge=e,
+         delta1=5.0, delta2=1.0, params=parjson(cyclotronresolution=20), traj=p.trajectory,
+         counters=take_log(), tcur=p.tcur)
+
+
+def case_pfields():
+    """Particle.advance in every other analytic field model (+ enforce equatorial)."""
+    out = {}
+    # VarEarthDipole: static=False -> gm recomputed per RHS (Particle.py:290-291)
+    v = ru.speedfromKE(5e5, m_el, 'ev')
+    pos = (3.7 * Re, -1.1 * Re, 0.4 * Re); vel = (0.3 * v, 0.5 * v, v * np.sqrt(1 - .09 - .25))
+    p, L = run_particle(pos, vel, m_el, -e, rf.VarEarthDipole(amp=0.1, period=10), 0.02, t0=1.5,
+                        cyclotronresolution=20)
+    save("p_vardipole", pos=np.array(pos), vel=np.array(vel), mass=m_el, charge=-e, delta=0.02, t0=1.5,
+         fieldprm=np.array([0.1, 10.0]), params=parjson(cyclotronresolution=20),
+         traj=p.trajectory, counters=L, tcur=p.tcur)
+    # UniformCrossedEB: E != 0, static False
+    pos = (0.3, -0.2, 0.1); vel = (1.0e5, 2.0e4, 1.0e4)
+    p, L = run_particle(pos, vel, m_pr, e, rf.UniformCrossedEB(Ey=2.0, Bz=1e-4), 0.01)
+    save("p_crossedeb", pos=np.array(pos), vel=np.array(vel), mass=m_pr, charge=e, delta=0.01,
+         fieldprm=np.array([2.0, 1e-4]), params=parjson(), traj=p.trajectory, counters=L, tcur=p.tcur)
+    # UniformBz
+    p, L = run_particle(pos, vel, m_pr, e, rf.UniformBz(Bz=2e-4), 0.005)
+    save("p_uniformbz", pos=np.array(pos), vel=np.array(vel), mass=m_pr, charge=e, delta=0.005,
+         fieldprm=np.array([2e-4]), params=parjson(), traj=p.trajectory, counters=L, tcur=p.tcur)
+    # Parabolic: the notebook's reference Particle, tolerances 1e-12 (crosses |z| = 1: quirk Q6)
+    pos = (5, -5, 0.9); vel = (-0.1, 0.1, 0)
+    p, L = run_particle(pos, vel, 1, 1, rf.Parabolic(), 60, solvertolerances=(1e-12, 1e-12))
+    save("p_parabolic", pos=np.array(pos, float), vel=np.array(vel, float), mass=1.0, charge=1.0, delta=60.0,
+         fieldprm=np.array([10.0, 1.0, 0.2]), params=parjson(solvertolerances=(1e-12, 1e-12)),
+         traj=p.trajectory, counters=L, tcur=p.tcur)
+    # enforce equatorial
+    v = ru.speedfromKE(2e6, m_pr, 'ev')
+    pos = (4 * Re, 0.5 * Re, 0.0); vel = (0.6 * v, -0.8 * v, 0.0)
+    kw = {"enforce equatorial": True, "cyclotronresolution": 15}
+    p, L = run_particle(pos, vel, m_pr, e, rf.EarthDipole(), 3, **kw)
+    save("p_equatorial", pos=np.array(pos), vel=np.array(vel), mass=m_pr, charge=e, delta=3.0,
+         params=parjson(**kw), traj=p.trajectory, counters=L, tcur=p.tcur)
+    # user-defined field from examples/Creating new fields.ipynb cell 10 (NVRTC path)
+    class ChargedDipole(rf._Field):
+        def __init__(self, B0=1, Q=1):
+            rf._Field.__init__(self)
+            self.B0 = B0; self.Q = Q; self._k = 8.9875517873681764e9; self.static = False
+        def B(self, tpos):
+            t, x, y, z = tpos
+            return self.B0 * np.array([3*x*z, 3*y*z, (2*z*z - x*x - y*y)]) / pow(x*x+y*y+z*z, 5.0/2.0)
+        def E(self, tpos):
+            t, x, y, z = tpos
+            return self._k*self.Q * np.array([x, y, z]) / pow(x*x+y*y+z*z, 3.0/2.0)
+    refshim.reset_params(rapt)
+    p = rapt.Particle([5, 0, 0], [0, 1, 0], t0=0, mass=m_pr, charge=e, field=ChargedDipole(Q=1e-6))
+    p.setke(1)
+    pos0 = p.trajectory[0, 1:4].copy(); mom0 = p.trajectory[0, 4:].copy()
+    gm = np.sqrt(m_pr ** 2 + mom0 @ mom0 / c ** 2)
+    refshim.SOLVER_LOG.clear()
+    cp, cr = p.cycper(), p.cycrad()
+    p.advance(4e-4)
+    save("p_chargeddipole", pos=pos0, vel=mom0 / gm, mom=mom0, mass=m_pr, charge=e, delta=4e-4,
+         fieldprm=np.array([1.0, 1e-6, 8.9875517873681764e9]), params=parjson(),
+         traj=p.trajectory, counters=take_log(), tcur=p.tcur, cycper=cp, cycrad=cr)
+
+
+def bounce_setup(g):
+    """Intermediate values of GuidingCenter.bounceperiod (GuidingCenter.py:593-606)."""
+    from rapt.fieldline import Fieldline
+    tpos, ppar = g.trajectory[-1, 0:4], g.trajectory[-1, 4]
+    Bmag = g.field.magB(tpos)
+    gamma = np.sqrt(1 + 2*g.mu*Bmag/(g.mass*c*c) + (ppar/(g.mass*c))**2)
+    if gamma - 1 < 1e-6:
+        p = np.sqrt(2*g.mass*g.mu*Bmag + ppar**2); v = p/g.mass; Bm = (p**2)/(2*g.mass*g.mu)
+    else:
+        p = g.mass*c*np.sqrt((gamma+1)*(gamma-1)); Bm = p**2/((p-ppar)*(p+ppar))*Bmag; v = p/g.mass/gamma
+    fl = Fieldline(tpos, g.field, Bmax=Bm)
+    ds = fl.ds
+    fl.trace()
+    return dict(bs_gamma=gamma, bs_Bm=Bm, bs_v=v, bs_ds=ds, bs_curvature=g.field.curvature(tpos),
+                bs_curve=fl.curve.copy(), bs_B=fl.getB(),
+                bs_halfpath=rapt.flutils.halfbouncepath(tpos, g.field, Bm),
+                bs_period=g.bounceperiod())
+
+
+def case_g2():
+    """GuidingCenter notebook cell 5, advance(20); + bounce-period set-up (G4)."""
+    refshim.reset_params(rapt)
+    f = rf.DoubleDipole()
+    v = ru.speedfromKE(1e5, m_el)
+    pos = (0, -10 * Re, 0)
+    g0 = rapt.GuidingCenter(pos=pos, v=v, pa=80, mass=m_el, charge=-e, field=f)
+    bs = bounce_setup(g0)
+    g, L = run_gc(pos, v, 80, m_el, -e, f, 20)
+    save("g2_gc_doubledipole", pos=np.array(pos, float), v=v, pa=80.0, mass=m_el, charge=-e, delta=20.0,
+         params=parjson(), traj=g.trajectory, counters=L, tcur=g.tcur, mu=g.mu, **bs)
+
+
+def case_gcfields():
+    # EarthDipole, 1 MeV e-, L=5, pa 60 (bounce period 0.3642159344345973)
+    refshim.reset_params(rapt)
+    f = rf.EarthDipole()
+    v = ru.speedfromKE(1e6, m_el)
+    pos = (5 * Re, 0, 0)
+    g0 = rapt.GuidingCenter(pos=pos, v=v, pa=60, mass=m_el, charge=-e, field=f)
+    bs = bounce_setup(g0)
+    g, L = run_gc(pos, v, 60, m_el, -e, f, 3)
+    save("gc_earthdipole", pos=np.array(pos, float), v=v, pa=60.0, mass=m_el, charge=-e, delta=3.0,
+         params=parjson(), traj=g.trajectory, counters=L, tcur=g.tcur, mu=g.mu, **bs)
+    # generic IC, three EOMs, fixed GCtimestep
+    pos = (4.2 * Re, -2.9 * Re, 0.6 * Re)
+    for eom in ("TaoChanBrizardEOM", "BrizardChanEOM", "NorthropTellerEOM"):
+        g, L = run_gc(pos, v, 55, m_el, -e, rf.DoubleDipole(), 8, eom=eom, GCtimestep=0.1)
+        save("gc_eom_" + eom[:-3].lower(), pos=np.array(pos), v=v, pa=55.0, mass=m_el, charge=-e, delta=8.0,
+             params=parjson(GCtimestep=0.1), eom=np.array(eom), traj=g.trajectory, counters=L,
+             tcur=g.tcur, mu=g.mu)
+    # pa = 90 (Q9: vpar = 0 exactly) with bounce-period dt -> equatorial special case
+    refshim.reset_params(rapt)
+    pos = (-7.8 * Re, 0, 0)
+    vp = ru.speedfromKE(1e5, m_pr)
+    g0 = rapt.GuidingCenter(pos=pos, v=vp, pa=90, mass=m_pr, charge=e, field=rf.DoubleDipole())
+    bs = bounce_setup(g0)
+    g, L = run_gc(pos, vp, 90, m_pr, e, rf.DoubleDipole(), 100, solvertolerances=(1e-6, 1e-6),
+                  bounceresolution=20)
+    save("gc_pa90_equatorial", pos=np.array(pos, float), v=vp, pa=90.0, mass=m_pr, charge=e, delta=100.0,
+         params=parjson(solvertolerances=(1e-6, 1e-6), bounceresolution=20), traj=g.trajectory,
+         counters=L, tcur=g.tcur, mu=g.mu, **bs)
+    # VarEarthDipole (static False: dbdt path, 15 B evaluations per RHS)
+    pos = (4.5 * Re, 1.2 * Re, -0.3 * Re)
+    g, L = run_gc(pos, v, 50, m_el, -e, rf.VarEarthDipole(0.1, 10), 2, t0=0.7, GCtimestep=0.05)
+    save("gc_vardipole", pos=np.array(pos), v=v, pa=50.0, mass=m_el, charge=-e, delta=2.0, t0=0.7,
+         fieldprm=np.array([0.1, 10.0]), params=parjson(GCtimestep=0.05), traj=g.trajectory,
+         counters=L, tcur=g.tcur, mu=g.mu)
+    # UniformCrossedEB: pure E x B drift
+    g, L = run_gc((0.3, -0.2, 0.1), 1.0e5, 70, m_pr, e, rf.UniformCrossedEB(Ey=2.0, Bz=1e-4), 0.05,
+                  GCtimestep=0.005)
+    save("gc_crossedeb", pos=np.array((0.3, -0.2, 0.1)), v=1.0e5, pa=70.0, mass=m_pr, charge=e, delta=0.05,
+         fieldprm=np.array([2.0, 1e-4]), params=parjson(GCtimestep=0.005), traj=g.trajectory,
+         counters=L, tcur=g.tcur, mu=g.mu)
+    # enforce equatorial
+    kw = {"enforce equatorial": True, "GCtimestep": 0.5}
+    g, L = run_gc((6 * Re, 1 * Re, 0.0), v, 90, m_el, -e, rf.DoubleDipole(), 20, **kw)
+    save("gc_equatorial_enforced", pos=np.array((6 * Re, 1 * Re, 0.0)), v=v, pa=90.0, mass=m_el, charge=-e,
+         delta=20.0, params=parjson(**kw), traj=g.trajectory, counters=L, tcur=g.tcur, mu=g.mu)
+
+
+def adaptive_dump(a):
+    modes, nrows, rows = [], [], []
+    for seg in a.trajlist:
+        is_p = seg.trajectory.shape[1] == 7
+        modes.append(0 if is_p else 1)
+        nrows.append(seg.trajectory.shape[0])
+        r = np.zeros((seg.trajectory.shape[0], 8))
+        r[:, :seg.trajectory.shape[1]] = seg.trajectory
+        if not is_p:
+            r[:, 5] = seg.mu
+        rows.append(r)
+    return dict(seg_mode=np.array(modes), seg_nrows=np.array(nrows), rows=np.vstack(rows),
+                seg_tcur=np.array([s.tcur for s in a.trajlist]))
+
+
+def run_adaptive(pos, vel, mass, charge, field, delta, **par):
+    import io, contextlib
+    refshim.reset_params(rapt, **par)
+    refshim.SOLVER_LOG.clear()
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = rapt.Adaptive(tuple(pos), tuple(vel), 0, mass=mass, charge=charge, field=field)
+        a.advance(delta)
+    return a, take_log(), buf.getvalue()
+
+
+SPEISER = dict(solvertolerances=(1e-12, 1e-12), epss=0.02, Ptimestep=0.1, GCtimestep=1)
+
+
+def case_g3():
+    a, L, txt = run_adaptive((5, -5, 0.9), (-0.1, 0.1, 0), 1, 1, rf.Parabolic(), 300, **SPEISER)
+    print(txt)
+    save("g3_speiser", pos=np.array((5, -5, 0.9)), vel=np.array((-0.1, 0.1, 0.0)), mass=1.0, charge=1.0,
+         delta=300.0, params=parjson(**SPEISER), counters=L, stdout=np.array(txt), **adaptive_dump(a))
+
+
+def case_e4():
+    n = 6
+    ic = synth.config4_speiser(n)
+    for i in range(1, n):
+        pos = (ic["x"][i], ic["y"][i], ic["z"][i]); vel = (ic["vx"][i], ic["vy"][i], ic["vz"][i])
+        a, L, txt = run_adaptive(pos, vel, 1, 1, rf.Parabolic(), 150, **SPEISER)
+        save(f"e4_speiser_{i}", index=i, pos=np.array(pos), vel=np.array(vel), mass=1.0, charge=1.0, delta=150.0,
+             params=parjson(**SPEISER), counters=L, stdout=np.array(txt), **adaptive_dump(a))
+
+
+def case_adaptive_dipole():
+    """Adaptive in EarthDipole: adiabatic from the start -> begins as GuidingCenter
+    (Adaptive.py:98-102), dt from the bounce period."""
+    v = ru.speedfromKE(1e4, m_pr)
+    pos = (4 * Re, 0.3 * Re, 0.2 * Re); vel = (0.2 * v, 0.5 * v, v * np.sqrt(1 - 0.04 - 0.25))
+    a, L, txt = run_adaptive(pos, vel, m_pr, e, rf.EarthDipole(), 30)
+    save("adaptive_dipole", pos=np.array(pos), vel=np.array(vel), mass=m_pr, charge=e, delta=30.0,
+         params=parjson(), counters=L, stdout=np.array(txt), **adaptive_dump(a))
+
+
+def case_e2():
+    """First 32 protons of config 2, advance(1.0): rows, totals, final state."""
+    n = 32
+    ic = synth.config2_protons(n)
+    fin, nrows, tot, tcur = [], [], [], []
+    trajs = {}
+    f = rf.EarthDipole()
+    for i in range(n):
+        pos = (ic["x"][i], ic["y"][i], ic["z"][i]); vel = (ic["vx"][i], ic["vy"][i], ic["vz"][i])
+        p, L = run_particle(pos, vel, m_pr, e, f, 1.0, cyclotronresolution=20)
+        fin.append(p.trajectory[-1]); nrows.append(p.trajectory.shape[0]); tot.append(L.sum(0)); tcur.append(p.tcur)
+        if i < 4:
+            trajs[f"traj{i}"] = p.trajectory; trajs[f"counters{i}"] = L
+    save("e2_config2_first32", n=n, seed=20260201, delta=1.0, params=parjson(cyclotronresolution=20),
+         final=np.array(fin), nrows=np.array(nrows), totals=np.array(tot), tcur=np.array(tcur), **trajs)
+
+
+def case_e3():
+    """First 16 electrons of config 3 (GC, DoubleDipole): GCtimestep=0.1 for 10 s, and the
+    reference's bounce periods (dt parity)."""
+    n = 16
+    ic = synth.config3_electrons(n)
+    f = rf.DoubleDipole()
+    fin, nrows, tot, mu, bp = [], [], [], [], []
+    for i in range(n):
+        pos = (ic["x"][i], ic["y"][i], ic["z"][i])
+        g, L = run_gc(pos, ic["v"][i], ic["pa"][i], m_el, -e, f, 10.0, GCtimestep=0.1)
+        fin.append(g.trajectory[-1]); nrows.append(g.trajectory.shape[0]); tot.append(L.sum(0)); mu.append(g.mu)
+        refshim.reset_params(rapt)
+        g0 = rapt.GuidingCenter(pos=pos, v=ic["v"][i], pa=ic["pa"][i], mass=m_el, charge=-e, field=f)
+        bp.append(g0.bounceperiod())
+    save("e3_config3_first16", n=n, seed=20260301, delta=10.0, params=parjson(GCtimestep=0.1),
+         final=np.array(fin), nrows=np.array(nrows), totals=np.array(tot), mu=np.array(mu),
+         bounceperiod=np.array(bp))
+
+
+def case_e5():
+    n = 16
+    ic = synth.config5_belt(n)
+    f = rf.VarEarthDipole(0.1, 10)
+    fin, nrows, tot, mu = [], [], [], []
+    for i in range(n):
+        pos = (ic["x"][i], ic["y"][i], ic["z"][i])
+        g, L = run_gc(pos, ic["v"][i], ic["pa"][i], m_el, -e, f, 2.0, GCtimestep=0.05)
+        fin.append(g.trajectory[-1]); nrows.append(g.trajectory.shape[0]); tot.append(L.sum(0)); mu.append(g.mu)
+    save("e5_config5_first16", n=n, seed=20260501, delta=2.0, params=parjson(GCtimestep=0.05),
+         final=np.array(fin), nrows=np.array(nrows), totals=np.array(tot), mu=np.array(mu))
+
+
+def case_units():
+    """Field operators and utils helpers at seeded points (fields.py:76-280, utils.py:29-433)."""
+    rng = np.random.default_rng(7)
+    flds = {
+        "earthdipole": (rf.EarthDipole(), Re), "doubledipole": (rf.DoubleDipole(), Re),
+        "uniformbz": (rf.UniformBz(2e-4), 1.0), "crossedeb": (rf.UniformCrossedEB(2.0, 1e-4), 1.0),
+        "vardipole": (rf.VarEarthDipole(0.1, 10), Re), "parabolic": (rf.Parabolic(), 1.0),
+    }
+    out = {}
+    for name, (f, scale) in flds.items():
+        npt = 12
+        if name == "parabolic":
+            pts = np.column_stack([rng.uniform(0, 5, npt), rng.uniform(-6, 6, npt), rng.uniform(-6, 6, npt),
+                                   rng.uniform(-1.6, 1.6, npt)])
+        else:
+            pts = np.column_stack([rng.uniform(0, 20, npt), rng.uniform(-7, 7, npt) * scale,
+                                   rng.uniform(-7, 7, npt) * scale, rng.uniform(-3, 3, npt) * scale])
+        rec = {k: [] for k in ("B", "E", "unitb", "magB", "gradB", "jacobianB", "curlb", "curvature",
+                               "dBdt", "dbdt", "lengthscale", "timescale")}
+        for tp in pts:
+            rec["B"].append(f.B(tp)); rec["E"].append(np.asarray(f.E(tp), float)); rec["unitb"].append(f.unitb(tp))
+            rec["magB"].append(f.magB(tp)); rec["gradB"].append(f.gradB(tp)); rec["jacobianB"].append(f.jacobianB(tp))
+            rec["curlb"].append(f.curlb(tp)); rec["curvature"].append(f.curvature(tp))
+            rec["dBdt"].append(float(f.dBdt(tp))); rec["dbdt"].append(np.zeros(3) + f.dbdt(tp))
+            with np.errstate(divide="ignore"):
+                rec["lengthscale"].append(f.lengthscale(tp))
+                ts = f.timescale(tp)
+            rec["timescale"].append(np.nan if ts is None else ts)
+        out[name + "_pts"] = pts
+        for k, v in rec.items():
+            out[f"{name}_{k}"] = np.array(v, dtype=float)
+    # utils helpers in DoubleDipole
+    f = rf.DoubleDipole()
+    npt = 12
+    pos = np.column_stack([rng.uniform(-8, 6, npt), rng.uniform(-8, 8, npt), rng.uniform(-2, 2, npt)]) * Re
+    spd = [ru.speedfromKE(k, m_pr) for k in 10 ** rng.uniform(4, 6.5, npt)]
+    dirs = rng.normal(size=(npt, 3)); dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    vel = dirs * np.array(spd)[:, None]
+    u = {k: [] for k in ("cycper", "cycrad", "gc_R", "gc_vp", "gc_v", "mu", "fp_pos", "fp_vel", "cycper2", "cycrad2")}
+    for i in range(npt):
+        t = 0.0
+        u["cycper"].append(ru.cyclotron_period(t, pos[i], vel[i], f, m_pr, e))
+        u["cycrad"].append(ru.cyclotron_radius(t, pos[i], vel[i], f, m_pr, e))
+        R, vp, vv = ru.guidingcenter(t, pos[i], vel[i], f, m_pr, e)
+        u["gc_R"].append(R); u["gc_vp"].append(vp); u["gc_v"].append(vv)
+        u["mu"].append(ru.magnetic_moment(t, R, vp, vv, f, m_pr))
+        pp, vv2 = ru.GCtoFP(t, R, vp, vv, f, m_pr, e, 0)
+        u["fp_pos"].append(pp); u["fp_vel"].append(vv2)
+        u["cycper2"].append(ru.cyclotron_period2(t, R, vv, f, m_pr, e))
+        u["cycrad2"].append(ru.cyclotron_radius2(t, R, vp, vv, f, m_pr, e))
+    out["utils_pos"] = pos; out["utils_vel"] = vel
+    for k, v in u.items():
+        out["utils_" + k] = np.array(v, dtype=float)
+    out["getperp_in"] = np.array([[0, 1, 2.], [1, 0, 2.], [1, 2, 0.], [1, 2, 3.], [-2, 0.5, 1e-3]])
+    out["getperp_out"] = np.array([np.asarray(ru.getperp(v), float) for v in out["getperp_in"]])
+    kes = np.array([1.0, 1e3, 1e5, 1e6, 1e7, 5e8])
+    out["speed_ke"] = kes
+    out["speed_pr"] = np.array([ru.speedfromKE(k, m_pr) for k in kes])
+    out["speed_el"] = np.array([ru.speedfromKE(k, m_el) for k in kes])
+    # rkf.py on a small test ODE
+    from rapt.rkf import rkf
+    T, X = rkf(lambda x, t: np.array([x[1], -x[0] * (1 + 4 * np.sin(t) ** 2)]), 0.0, 6.0,
+               np.array([1.0, 0.0]), 1e-6, 0.5, 1e-6)
+    out["rkf_T"] = T; out["rkf_X"] = X
+    save("units", **out)
+
+
+CASES = {
+    "g1": case_g1, "g1b": case_g1b, "pfields": case_pfields, "g2": case_g2, "gcfields": case_gcfields,
+    "g3": case_g3, "e4": case_e4, "adip": case_adaptive_dipole, "e2": case_e2, "e3": case_e3,
+    "e5": case_e5, "units": case_units,
+}
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    sel = sys.argv[1:] or list(CASES)
+    for k in sel:
+        t = time.time()
+        print(f"[{k}]")
+        CASES[k]()
+        print(f"  {time.time()-t:.1f} s")
+    with open(os.path.join(GOLD, "VERSIONS.txt"), "w") as fh:
+        import scipy
+        fh.write(f"numpy {np.__version__}\nscipy {scipy.__version__}\npython {sys.version.split()[0]}\n"
+                 "reference mkozturk/rapt at /root/reference (unmodified; shims in oracle/refshim.py)\n")
