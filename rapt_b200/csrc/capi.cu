@@ -1,0 +1,534 @@
+// capi.cu -- the extern "C" boundary of librapt_b200.so (include/rapt_b200.h).
+// Host-side plumbing only: argument checks, device buffers, H2D/D2H copies, work ordering, launches.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <atomic>
+#include <mutex>
+#include "../../include/rapt_b200.h"
+#include "rapt_launch.h"
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+
+static_assert(sizeof(rapt_field_t) == sizeof(rapt::FieldP), "FieldP layout");
+static_assert(sizeof(rapt_params_t) == sizeof(rapt::ParamsP), "ParamsP layout");
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+int g_device = -1, g_sms = 0;
+int *g_queue = nullptr;          // device work counters (ring of 64 ints so async calls do not collide)
+int g_queue_slot = 0;
+
+// scratch for the longest-first work ordering (grown on demand, reused across calls)
+struct SortScratch {
+    double *key_in = nullptr, *key_out = nullptr;
+    int *idx_in = nullptr, *idx_out = nullptr;
+    void *tmp = nullptr;
+    size_t n = 0, tmp_bytes = 0;
+} g_sort;
+
+#define FLAVOUR(strict, fn, ...) ((strict) ? rapt_strict::fn(__VA_ARGS__) : rapt_fast::fn(__VA_ARGS__))
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? RAPT_E_NODEVICE : RAPT_E_CUDA, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int ensure_init()
+{
+    if (g_device >= 0) return RAPT_OK;
+    return rapt_b200_init(0);
+}
+
+int *next_queue(cudaStream_t s)
+{
+    int *q = g_queue + (g_queue_slot++ & 63);
+    cudaMemsetAsync(q, 0, sizeof(int), s);
+    return q;
+}
+
+// RAII device buffer for the host-pointer entry points
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t b) { bytes = b; return b ? cudaMalloc(&p, b) : cudaSuccess; }
+    template <class T> T *as() { return static_cast<T *>(p); }
+};
+
+cudaError_t up(DevBuf &d, const void *h, size_t bytes, cudaStream_t s)
+{
+    cudaError_t e = d.alloc(bytes);
+    if (e != cudaSuccess || !bytes) return e;
+    return cudaMemcpyAsync(d.p, h, bytes, cudaMemcpyHostToDevice, s);
+}
+cudaError_t down(void *h, DevBuf &d, size_t bytes, cudaStream_t s)
+{
+    if (!h || !bytes) return cudaSuccess;
+    return cudaMemcpyAsync(h, d.p, bytes, cudaMemcpyDeviceToHost, s);
+}
+
+void fill_common(rapt::AdvArgs &a, const rapt_field_t *f, const rapt_params_t *p)
+{
+    memset(&a, 0, sizeof a);
+    memcpy(&a.f, f, sizeof a.f);
+    memcpy(&a.p, p, sizeof a.p);
+}
+
+
+// Longest-first schedule: sort particle indices by dt/delta ascending (fewest-rows last), so the lanes
+// that run dry at the end of the kernel are finishing the SHORTEST particles (SURVEY.md hard part H4).
+cudaError_t build_order(rapt::AdvArgs &a, bool strict, cudaStream_t s)
+{
+    const size_t n = (size_t)a.nwork;
+    cudaError_t e;
+    if (g_sort.n < n) {
+        cudaFree(g_sort.key_in); cudaFree(g_sort.key_out); cudaFree(g_sort.idx_in); cudaFree(g_sort.idx_out);
+        if ((e = cudaMalloc(&g_sort.key_in, n * sizeof(double))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&g_sort.key_out, n * sizeof(double))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&g_sort.idx_in, n * sizeof(int))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&g_sort.idx_out, n * sizeof(int))) != cudaSuccess) return e;
+        g_sort.n = n;
+    }
+    if ((e = FLAVOUR(strict, launch_particle_dt, a, g_sort.key_in, g_sort.idx_in, s)) != cudaSuccess) return e;
+    g_launches++;
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, g_sort.key_in, g_sort.key_out, g_sort.idx_in, g_sort.idx_out, (int)n, 0, 64, s);
+    if (need > g_sort.tmp_bytes) {
+        cudaFree(g_sort.tmp);
+        if ((e = cudaMalloc(&g_sort.tmp, need)) != cudaSuccess) return e;
+        g_sort.tmp_bytes = need;
+    }
+    e = cub::DeviceRadixSort::SortPairs(g_sort.tmp, need, g_sort.key_in, g_sort.key_out, g_sort.idx_in, g_sort.idx_out, (int)n, 0, 64, s);
+    g_launches += 1;
+    a.order = g_sort.idx_out;
+    return e;
+}
+
+int grid_for(long long n, int blocks_per_sm)
+{
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    long long want = (n + 127) / 128;
+    return (int)std::min<long long>((long long)g_sms * blocks_per_sm, want);
+}
+
+// register-resident DFMA chains: 8 independent accumulators per thread, 2 flops per DFMA
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 12345.678) out[0] = s;   // never true; keeps the chains alive
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *rapt_b200_last_error(void) { return g_err.c_str(); }
+const char *rapt_b200_version(void) { return "rapt_b200 0.1 (sm_100a)"; }
+int64_t rapt_b200_launch_count(void) { return g_launches.load(); }
+
+int rapt_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int rapt_b200_init(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(RAPT_E_NODEVICE, "no CUDA device available (%s); librapt_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(RAPT_E_ARG, "device %d out of range [0,%d)", device, n);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (g_device != device) {
+        g_queue = nullptr;
+        CK(cudaMalloc(&g_queue, 64 * sizeof(int)));
+        CK(cudaMemset(g_queue, 0, 64 * sizeof(int)));
+    }
+    g_device = device;
+    g_sms = prop.multiProcessorCount;
+    return RAPT_OK;
+}
+
+
+int rapt_b200_fp64_peak(int iters, double *tflops, double *sm_clock_mhz)
+{
+    if (int rc = ensure_init()) return rc;
+    if (iters <= 0 || !tflops) return fail(RAPT_E_ARG, "fp64_peak: bad argument");
+    double *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double)));
+    const int blocks = g_sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    k_fp64_peak<<<blocks, threads>>>(d, iters / 8 + 1, 0.999999, 1e-9);        // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(e0));
+        k_fp64_peak<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+        g_launches++;
+    }
+    CK(cudaGetLastError());
+    double flops = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (sm_clock_mhz) {
+        int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g_device);
+        *sm_clock_mhz = khz / 1000.0;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return RAPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Particle.advance
+// ------------------------------------------------------------------------------------------------
+int rapt_b200_particle_advance_dev(const rapt_field_t *f, const rapt_params_t *p, int64_t n,
+                                   double *t, double *x, double *y, double *z, double *px, double *py, double *pz,
+                                   const double *mass, const double *charge, double delta,
+                                   int64_t store_every, int64_t max_rows, double *rows,
+                                   int32_t *nrows, int32_t *nstored, int32_t *counters, int32_t *status,
+                                   double *tcur, double *dt_out, void *stream)
+{
+    if (int rc = ensure_init()) return rc;
+    if (!f || !p || n < 0 || !t || !x || !y || !z || !px || !py || !pz || !mass || !charge || !nstored || !counters ||
+        !status || !tcur)
+        return fail(RAPT_E_ARG, "particle_advance: null argument");
+    if (f->kind == RAPT_FIELD_USER) return fail(RAPT_E_UNSUPPORTED, "user fields go through the NVRTC module");
+    if (f->kind < 0 || f->kind > 5) return fail(RAPT_E_ARG, "unknown field kind %d", f->kind);
+    if (n == 0) return RAPT_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    rapt::AdvArgs a;
+    fill_common(a, f, p);
+    a.nwork = n; a.order = nullptr; a.queue = next_queue(s);
+    a.t = t; a.s1 = x; a.s2 = y; a.s3 = z; a.s4 = px; a.s5 = py; a.s6 = pz;
+    a.mass = mass; a.charge = charge; a.delta = delta;
+    a.store_every = rows ? store_every : 0; a.max_rows = rows ? max_rows : 0; a.rows = rows;
+    a.nstored = nstored; a.nrows = nrows; a.counters = counters; a.status = status; a.tcur = tcur; a.dt_out = dt_out;
+    const bool strict = p->arith == 1;
+    const int grid = grid_for(n, FLAVOUR(strict, particle_blocks_per_sm));
+    if (p->sort_by_work && n > (long long)grid * 128) CK(build_order(a, strict, s));
+    CK(FLAVOUR(strict, launch_particle, a, grid, s));
+    g_launches++;
+    return RAPT_OK;
+}
+
+int rapt_b200_particle_advance(const rapt_field_t *f, const rapt_params_t *p, int64_t n,
+                               double *t, double *x, double *y, double *z, double *px, double *py, double *pz,
+                               const double *mass, const double *charge, double delta,
+                               int64_t store_every, int64_t max_rows, double *rows,
+                               int32_t *nrows, int32_t *nstored, int32_t *counters, int32_t *status,
+                               double *tcur, double *dt_out)
+{
+    if (int rc = ensure_init()) return rc;
+    if (n < 0) return fail(RAPT_E_ARG, "n < 0");
+    if (n == 0) return RAPT_OK;
+    if (!t || !x || !y || !z || !px || !py || !pz || !mass || !charge)
+        return fail(RAPT_E_ARG, "particle_advance: null state pointer");
+    cudaStream_t s = 0;
+    const size_t nb = (size_t)n * sizeof(double);
+    DevBuf dt_, dx, dy, dz, dpx, dpy, dpz, dm, dq, drows, dnrows, dnst, dcnt, dst, dtcur, ddt;
+    CK(up(dt_, t, nb, s)); CK(up(dx, x, nb, s)); CK(up(dy, y, nb, s)); CK(up(dz, z, nb, s));
+    CK(up(dpx, px, nb, s)); CK(up(dpy, py, nb, s)); CK(up(dpz, pz, nb, s));
+    CK(up(dm, mass, nb, s)); CK(up(dq, charge, nb, s));
+    const bool want_rows = rows && store_every > 0 && max_rows > 0;
+    const size_t rb = want_rows ? (size_t)n * (size_t)max_rows * 8 * sizeof(double) : 0;
+    CK(drows.alloc(rb));
+    CK(dnrows.alloc(n * sizeof(int))); CK(dnst.alloc(n * sizeof(int))); CK(dcnt.alloc(n * 4 * sizeof(int)));
+    CK(dst.alloc(n * sizeof(int))); CK(dtcur.alloc(nb)); CK(ddt.alloc(nb));
+    int rc = rapt_b200_particle_advance_dev(f, p, n, dt_.as<double>(), dx.as<double>(), dy.as<double>(), dz.as<double>(),
+                                            dpx.as<double>(), dpy.as<double>(), dpz.as<double>(), dm.as<double>(),
+                                            dq.as<double>(), delta, store_every, max_rows,
+                                            want_rows ? drows.as<double>() : nullptr, dnrows.as<int>(), dnst.as<int>(),
+                                            dcnt.as<int>(), dst.as<int>(), dtcur.as<double>(), ddt.as<double>(), s);
+    if (rc) return rc;
+    CK(down(t, dt_, nb, s)); CK(down(x, dx, nb, s)); CK(down(y, dy, nb, s)); CK(down(z, dz, nb, s));
+    CK(down(px, dpx, nb, s)); CK(down(py, dpy, nb, s)); CK(down(pz, dpz, nb, s));
+    CK(down(nrows, dnrows, n * sizeof(int), s)); CK(down(nstored, dnst, n * sizeof(int), s));
+    CK(down(counters, dcnt, n * 4 * sizeof(int), s)); CK(down(status, dst, n * sizeof(int), s));
+    CK(down(tcur, dtcur, nb, s)); CK(down(dt_out, ddt, nb, s));
+    if (want_rows) CK(down(rows, drows, rb, s));
+    CK(cudaStreamSynchronize(s));
+    return RAPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GuidingCenter.advance
+// ------------------------------------------------------------------------------------------------
+int rapt_b200_gc_advance_dev(const rapt_field_t *f, const rapt_params_t *p, int eom, int64_t n,
+                             double *t, double *x, double *y, double *z, double *ppar,
+                             const double *mu, const double *v, const double *mass, const double *charge,
+                             const double *dt, double delta,
+                             int64_t store_every, int64_t max_rows, double *rows,
+                             int32_t *nrows, int32_t *nstored, int32_t *counters, int32_t *status, double *tcur,
+                             void *stream)
+{
+    if (int rc = ensure_init()) return rc;
+    if (!f || !p || n < 0 || !t || !x || !y || !z || !ppar || !mu || !v || !mass || !charge || !dt || !nstored ||
+        !counters || !status || !tcur)
+        return fail(RAPT_E_ARG, "gc_advance: null argument");
+    if (f->kind == RAPT_FIELD_USER) return fail(RAPT_E_UNSUPPORTED, "user fields go through the NVRTC module");
+    if (f->kind < 0 || f->kind > 5) return fail(RAPT_E_ARG, "unknown field kind %d", f->kind);
+    if (eom < 0 || eom > 2) return fail(RAPT_E_ARG, "unknown eom %d", eom);
+    if (n == 0) return RAPT_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    rapt::AdvArgs a;
+    fill_common(a, f, p);
+    a.nwork = n; a.order = nullptr; a.queue = next_queue(s);
+    a.t = t; a.s1 = x; a.s2 = y; a.s3 = z; a.s4 = ppar;
+    a.mass = mass; a.charge = charge; a.mu = mu; a.v = v; a.dtin = dt; a.delta = delta; a.eom = eom;
+    a.store_every = rows ? store_every : 0; a.max_rows = rows ? max_rows : 0; a.rows = rows;
+    a.nstored = nstored; a.nrows = nrows; a.counters = counters; a.status = status; a.tcur = tcur;
+    const bool strict = p->arith == 1;
+    const int grid = grid_for(n, FLAVOUR(strict, gc_blocks_per_sm));
+    CK(FLAVOUR(strict, launch_gc, a, grid, s));
+    g_launches++;
+    return RAPT_OK;
+}
+
+int rapt_b200_gc_advance(const rapt_field_t *f, const rapt_params_t *p, int eom, int64_t n,
+                         double *t, double *x, double *y, double *z, double *ppar,
+                         const double *mu, const double *v, const double *mass, const double *charge,
+                         const double *dt, double delta,
+                         int64_t store_every, int64_t max_rows, double *rows,
+                         int32_t *nrows, int32_t *nstored, int32_t *counters, int32_t *status, double *tcur)
+{
+    if (int rc = ensure_init()) return rc;
+    if (n < 0) return fail(RAPT_E_ARG, "n < 0");
+    if (n == 0) return RAPT_OK;
+    if (!t || !x || !y || !z || !ppar || !mu || !v || !mass || !charge || !dt)
+        return fail(RAPT_E_ARG, "gc_advance: null state pointer");
+    cudaStream_t s = 0;
+    const size_t nb = (size_t)n * sizeof(double);
+    DevBuf dt_, dx, dy, dz, dpp, dmu, dv, dm, dq, ddt, drows, dnrows, dnst, dcnt, dst, dtcur;
+    CK(up(dt_, t, nb, s)); CK(up(dx, x, nb, s)); CK(up(dy, y, nb, s)); CK(up(dz, z, nb, s)); CK(up(dpp, ppar, nb, s));
+    CK(up(dmu, mu, nb, s)); CK(up(dv, v, nb, s)); CK(up(dm, mass, nb, s)); CK(up(dq, charge, nb, s)); CK(up(ddt, dt, nb, s));
+    const bool want_rows = rows && store_every > 0 && max_rows > 0;
+    const size_t rb = want_rows ? (size_t)n * (size_t)max_rows * 8 * sizeof(double) : 0;
+    CK(drows.alloc(rb));
+    CK(dnrows.alloc(n * sizeof(int))); CK(dnst.alloc(n * sizeof(int))); CK(dcnt.alloc(n * 4 * sizeof(int)));
+    CK(dst.alloc(n * sizeof(int))); CK(dtcur.alloc(nb));
+    int rc = rapt_b200_gc_advance_dev(f, p, eom, n, dt_.as<double>(), dx.as<double>(), dy.as<double>(), dz.as<double>(),
+                                      dpp.as<double>(), dmu.as<double>(), dv.as<double>(), dm.as<double>(), dq.as<double>(),
+                                      ddt.as<double>(), delta, store_every, max_rows,
+                                      want_rows ? drows.as<double>() : nullptr, dnrows.as<int>(), dnst.as<int>(),
+                                      dcnt.as<int>(), dst.as<int>(), dtcur.as<double>(), s);
+    if (rc) return rc;
+    CK(down(t, dt_, nb, s)); CK(down(x, dx, nb, s)); CK(down(y, dy, nb, s)); CK(down(z, dz, nb, s)); CK(down(ppar, dpp, nb, s));
+    CK(down(nrows, dnrows, n * sizeof(int), s)); CK(down(nstored, dnst, n * sizeof(int), s));
+    CK(down(counters, dcnt, n * 4 * sizeof(int), s)); CK(down(status, dst, n * sizeof(int), s));
+    CK(down(tcur, dtcur, nb, s));
+    if (want_rows) CK(down(rows, drows, rb, s));
+    CK(cudaStreamSynchronize(s));
+    return RAPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small per-call kernels (host pointers)
+// ------------------------------------------------------------------------------------------------
+static int check_field(const rapt_field_t *f)
+{
+    if (!f) return fail(RAPT_E_ARG, "null field");
+    if (f->kind == RAPT_FIELD_USER) return fail(RAPT_E_UNSUPPORTED, "user fields go through the NVRTC module");
+    if (f->kind < 0 || f->kind > 5) return fail(RAPT_E_ARG, "unknown field kind %d", f->kind);
+    return RAPT_OK;
+}
+
+int rapt_b200_field_ops(const rapt_field_t *f, int arith, int64_t npt, const double *tpos,
+                        double *B, double *E, double *unitb, double *magB, double *gradB, double *jacobianB,
+                        double *curlb, double *curvature, double *dBdt, double *dbdt,
+                        double *lengthscale, double *timescale)
+{
+    if (int rc = ensure_init()) return rc;
+    if (int rc = check_field(f)) return rc;
+    if (npt < 0 || (npt > 0 && !tpos)) return fail(RAPT_E_ARG, "field_ops: bad argument");
+    if (npt == 0) return RAPT_OK;
+    cudaStream_t s = 0;
+    DevBuf dpos, o[12];
+    CK(up(dpos, tpos, npt * 4 * sizeof(double), s));
+    double *host[12] = {B, E, unitb, magB, gradB, jacobianB, curlb, curvature, dBdt, dbdt, lengthscale, timescale};
+    const int width[12] = {3, 3, 3, 1, 3, 9, 3, 1, 1, 3, 1, 1};
+    for (int k = 0; k < 12; k++) if (host[k]) CK(o[k].alloc(npt * width[k] * sizeof(double)));
+    rapt::OpsArgs a;
+    memset(&a, 0, sizeof a);
+    memcpy(&a.f, f, sizeof a.f);
+    a.n = npt; a.tpos = dpos.as<double>();
+    a.B = o[0].as<double>(); a.E = o[1].as<double>(); a.unitb = o[2].as<double>(); a.magB = o[3].as<double>();
+    a.gradB = o[4].as<double>(); a.jac = o[5].as<double>(); a.curlb = o[6].as<double>(); a.curv = o[7].as<double>();
+    a.dBdt = o[8].as<double>(); a.dbdt = o[9].as<double>(); a.lscale = o[10].as<double>(); a.tscale = o[11].as<double>();
+    CK(FLAVOUR(arith == 1, launch_field_ops, &a, s));
+    g_launches++;
+    for (int k = 0; k < 12; k++) if (host[k]) CK(down(host[k], o[k], npt * width[k] * sizeof(double), s));
+    CK(cudaStreamSynchronize(s));
+    return RAPT_OK;
+}
+
+int rapt_b200_gc_construct(const rapt_field_t *f, int arith, int64_t n, const double *t0, const double *x,
+                           const double *y, const double *z, const double *v, const double *pa_deg,
+                           const double *mass, double *ppar, double *mu)
+{
+    if (int rc = ensure_init()) return rc;
+    if (int rc = check_field(f)) return rc;
+    if (n < 0 || (n > 0 && (!t0 || !x || !y || !z || !v || !pa_deg || !mass || !ppar || !mu))) return fail(RAPT_E_ARG, "gc_construct: bad argument");
+    if (n == 0) return RAPT_OK;
+    cudaStream_t s = 0;
+    const size_t nb = n * sizeof(double);
+    DevBuf in[7], o0, o1;
+    const double *h[7] = {t0, x, y, z, v, pa_deg, mass};
+    for (int k = 0; k < 7; k++) CK(up(in[k], h[k], nb, s));
+    CK(o0.alloc(nb)); CK(o1.alloc(nb));
+    rapt::MiscArgs a;
+    memset(&a, 0, sizeof a);
+    memcpy(&a.f, f, sizeof a.f);
+    a.n = n; a.op = 0;
+    a.a0 = in[0].as<double>(); a.a1 = in[1].as<double>(); a.a2 = in[2].as<double>(); a.a3 = in[3].as<double>();
+    a.a4 = in[4].as<double>(); a.a5 = in[5].as<double>(); a.a6 = in[6].as<double>();
+    a.o0 = o0.as<double>(); a.o1 = o1.as<double>();
+    CK(FLAVOUR(arith == 1, launch_misc, &a, s));
+    g_launches++;
+    CK(down(ppar, o0, nb, s)); CK(down(mu, o1, nb, s));
+    CK(cudaStreamSynchronize(s));
+    return RAPT_OK;
+}
+
+int rapt_b200_switch_p2g(const rapt_field_t *f, int arith, int64_t n, const double *prow7, const double *mass,
+                         const double *charge, double *grow5, double *mu, double *v, int32_t *status)
+{
+    if (int rc = ensure_init()) return rc;
+    if (int rc = check_field(f)) return rc;
+    if (n < 0 || (n > 0 && (!prow7 || !mass || !charge || !grow5 || !mu || !v || !status))) return fail(RAPT_E_ARG, "switch_p2g: bad argument");
+    if (n == 0) return RAPT_OK;
+    cudaStream_t s = 0;
+    const size_t nb = n * sizeof(double);
+    DevBuf dp, dm, dq, og, omu, ov, ost;
+    CK(up(dp, prow7, 7 * nb, s)); CK(up(dm, mass, nb, s)); CK(up(dq, charge, nb, s));
+    CK(og.alloc(5 * nb)); CK(omu.alloc(nb)); CK(ov.alloc(nb)); CK(ost.alloc(n * sizeof(int)));
+    rapt::MiscArgs a;
+    memset(&a, 0, sizeof a);
+    memcpy(&a.f, f, sizeof a.f);
+    a.n = n; a.op = 1;
+    a.a0 = dp.as<double>(); a.a1 = dm.as<double>(); a.a2 = dq.as<double>();
+    a.o0 = og.as<double>(); a.o1 = omu.as<double>(); a.o2 = ov.as<double>(); a.io = ost.as<int>();
+    CK(FLAVOUR(arith == 1, launch_misc, &a, s));
+    g_launches++;
+    CK(down(grow5, og, 5 * nb, s)); CK(down(mu, omu, nb, s)); CK(down(v, ov, nb, s)); CK(down(status, ost, n * sizeof(int), s));
+    CK(cudaStreamSynchronize(s));
+    return RAPT_OK;
+}
+
+int rapt_b200_switch_g2p(const rapt_field_t *f, int arith, int64_t n, const double *grow5, const double *mu,
+                         const double *mass, const double *charge, double t_eval, double *prow7)
+{
+    if (int rc = ensure_init()) return rc;
+    if (int rc = check_field(f)) return rc;
+    if (n < 0 || (n > 0 && (!grow5 || !mu || !mass || !charge || !prow7))) return fail(RAPT_E_ARG, "switch_g2p: bad argument");
+    if (n == 0) return RAPT_OK;
+    cudaStream_t s = 0;
+    const size_t nb = n * sizeof(double);
+    DevBuf dg, dmu, dm, dq, op;
+    CK(up(dg, grow5, 5 * nb, s)); CK(up(dmu, mu, nb, s)); CK(up(dm, mass, nb, s)); CK(up(dq, charge, nb, s));
+    CK(op.alloc(7 * nb));
+    rapt::MiscArgs a;
+    memset(&a, 0, sizeof a);
+    memcpy(&a.f, f, sizeof a.f);
+    a.n = n; a.op = 2; a.t_eval = t_eval;
+    a.a0 = dg.as<double>(); a.a1 = dmu.as<double>(); a.a2 = dm.as<double>(); a.a3 = dq.as<double>();
+    a.o0 = op.as<double>();
+    CK(FLAVOUR(arith == 1, launch_misc, &a, s));
+    g_launches++;
+    CK(down(prow7, op, 7 * nb, s));
+    CK(cudaStreamSynchronize(s));
+    return RAPT_OK;
+}
+
+int rapt_b200_isadiabatic(const rapt_field_t *f, const rapt_params_t *p, int mode, int64_t n, const double *rows,
+                          int64_t row_stride, const double *mu, const double *mass, const double *charge, int32_t *out)
+{
+    if (int rc = ensure_init()) return rc;
+    if (int rc = check_field(f)) return rc;
+    if (!p || n < 0 || (n > 0 && (!rows || !mass || !charge || !out || (mode == 1 && !mu)))) return fail(RAPT_E_ARG, "isadiabatic: bad argument");
+    if (row_stride < (mode == 0 ? 7 : 5)) return fail(RAPT_E_ARG, "isadiabatic: row_stride too small");
+    if (n == 0) return RAPT_OK;
+    cudaStream_t s = 0;
+    const size_t nb = n * sizeof(double);
+    DevBuf dr, dmu, dm, dq, oo;
+    CK(up(dr, rows, row_stride * nb, s)); if (mu) CK(up(dmu, mu, nb, s));
+    CK(up(dm, mass, nb, s)); CK(up(dq, charge, nb, s)); CK(oo.alloc(n * sizeof(int)));
+    rapt::MiscArgs a;
+    memset(&a, 0, sizeof a);
+    memcpy(&a.f, f, sizeof a.f); memcpy(&a.p, p, sizeof a.p);
+    a.n = n; a.op = 3; a.mode = mode; a.stride = row_stride;
+    a.a0 = dr.as<double>(); a.a1 = dmu.as<double>(); a.a2 = dm.as<double>(); a.a3 = dq.as<double>(); a.io = oo.as<int>();
+    CK(FLAVOUR(p->arith == 1, launch_misc, &a, s));
+    g_launches++;
+    CK(down(out, oo, n * sizeof(int), s));
+    CK(cudaStreamSynchronize(s));
+    return RAPT_OK;
+}
+
+int rapt_b200_bounce_setup(const rapt_field_t *f, int arith, double fieldlineresolution, int64_t n,
+                           const double *t, const double *x, const double *y, const double *z, const double *ppar,
+                           const double *mu, const double *mass,
+                           double *Bm, double *v, double *ds, int32_t *npts, int64_t max_pts, double *curve)
+{
+    if (int rc = ensure_init()) return rc;
+    if (int rc = check_field(f)) return rc;
+    if (n < 0 || max_pts < 3 || (n > 0 && (!t || !x || !y || !z || !ppar || !mu || !mass || !Bm || !v || !ds || !npts || !curve)))
+        return fail(RAPT_E_ARG, "bounce_setup: bad argument");
+    if (n == 0) return RAPT_OK;
+    cudaStream_t s = 0;
+    const size_t nb = n * sizeof(double);
+    DevBuf in[7], oBm, ov, ods, onp, ocv, scr;
+    const double *h[7] = {t, x, y, z, ppar, mu, mass};
+    for (int k = 0; k < 7; k++) CK(up(in[k], h[k], nb, s));
+    CK(oBm.alloc(nb)); CK(ov.alloc(nb)); CK(ods.alloc(nb)); CK(onp.alloc(n * sizeof(int)));
+    CK(ocv.alloc((size_t)n * max_pts * 5 * sizeof(double))); CK(scr.alloc((size_t)n * max_pts * 4 * sizeof(double)));
+    rapt::BounceArgs a;
+    memset(&a, 0, sizeof a);
+    memcpy(&a.f, f, sizeof a.f);
+    a.flres = fieldlineresolution; a.n = n; a.max_pts = max_pts;
+    a.t = in[0].as<double>(); a.x = in[1].as<double>(); a.y = in[2].as<double>(); a.z = in[3].as<double>();
+    a.ppar = in[4].as<double>(); a.mu = in[5].as<double>(); a.mass = in[6].as<double>();
+    a.Bm = oBm.as<double>(); a.v = ov.as<double>(); a.ds = ods.as<double>(); a.npts = onp.as<int>();
+    a.curve = ocv.as<double>(); a.scratch = scr.as<double>();
+    CK(FLAVOUR(arith == 1, launch_bounce, &a, s));
+    g_launches++;
+    CK(down(Bm, oBm, nb, s)); CK(down(v, ov, nb, s)); CK(down(ds, ods, nb, s)); CK(down(npts, onp, n * sizeof(int), s));
+    CK(down(curve, ocv, (size_t)n * max_pts * 5 * sizeof(double), s));
+    CK(cudaStreamSynchronize(s));
+    return RAPT_OK;
+}
+
+}  // extern "C"

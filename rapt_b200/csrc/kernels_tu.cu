@@ -1,0 +1,130 @@
+// kernels_tu.cu -- one translation unit per (arithmetic flavour, kernel family); see Makefile.
+//   -DRAPT_STRICT=0|1 -DRAPT_NS=rapt_fast|rapt_strict -DRAPT_TU_PARTICLE | -DRAPT_TU_GC | -DRAPT_TU_AUX
+#include <cuda_runtime.h>
+#include "rapt_launch.h"
+
+#ifdef RAPT_TU_PARTICLE
+#include "rapt_particle.cuh"
+namespace RAPT_NS {
+template <int KIND> static cudaError_t go_particle(const rapt::AdvArgs &a, int grid, cudaStream_t s)
+{
+    k_particle_dop853<Field<KIND>><<<grid, 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_particle(const rapt::AdvArgs &a, int grid, cudaStream_t s)
+{
+    switch (a.f.kind) {
+    case 0: return go_particle<0>(a, grid, s);
+    case 1: return go_particle<1>(a, grid, s);
+    case 2: return go_particle<2>(a, grid, s);
+    case 3: return go_particle<3>(a, grid, s);
+    case 4: return go_particle<4>(a, grid, s);
+    case 5: return go_particle<5>(a, grid, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+int particle_blocks_per_sm()
+{
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_particle_dop853<Field<0>>, 128, 0);
+    return nb;
+}
+}  // namespace RAPT_NS
+#endif
+
+#ifdef RAPT_TU_GC
+#include "rapt_gc.cuh"
+namespace RAPT_NS {
+template <int KIND> static cudaError_t go_gc(const rapt::AdvArgs &a, int grid, cudaStream_t s)
+{
+    k_gc_dopri5<Field<KIND>><<<grid, 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_gc(const rapt::AdvArgs &a, int grid, cudaStream_t s)
+{
+    switch (a.f.kind) {
+    case 0: return go_gc<0>(a, grid, s);
+    case 1: return go_gc<1>(a, grid, s);
+    case 2: return go_gc<2>(a, grid, s);
+    case 3: return go_gc<3>(a, grid, s);
+    case 4: return go_gc<4>(a, grid, s);
+    case 5: return go_gc<5>(a, grid, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+int gc_blocks_per_sm()
+{
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gc_dopri5<Field<1>>, 128, 0);
+    return nb;
+}
+}  // namespace RAPT_NS
+#endif
+
+#ifdef RAPT_TU_AUX
+#include "rapt_aux.cuh"
+namespace RAPT_NS {
+// per-particle output step of Particle.advance (Particle.py:282): the work-ordering key (small dt = many rows)
+template <class F>
+__global__ void k_particle_dt(const rapt::AdvArgs a, double *key, int *idx)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= a.nwork) return;
+    double mass = a.mass[i], q = a.charge[i], px = a.s4[i], py = a.s5[i], pz = a.s6[i];
+    double gm = sqrt(mass * mass + dot3(px, py, pz, px, py, pz) / (RAPT_C_LIGHT * RAPT_C_LIGHT));
+    double vx = px / gm, vy = py / gm, vz = pz / gm;
+    double gamma = 1.0 / sqrt(1 - dot3(vx, vy, vz, vx, vy, vz) / (RAPT_C_LIGHT * RAPT_C_LIGHT));
+    double Bm = F::magB(a.f, a.t[i], a.s1[i], a.s2[i], a.s3[i]);
+    double dt = 2 * RAPT_PI * gamma * mass / Bm / fabs(q) / a.p.cyclotronresolution;
+    double delta = a.delta_arr ? a.delta_arr[i] : a.delta;
+    key[i] = dt / delta;            // ~ 1 / (number of output rows)
+    idx[i] = (int)i;
+}
+#define RAPT_KIND_SWITCH(CALL)                         \
+    switch (kind) {                                    \
+    case 0: CALL(0); break; case 1: CALL(1); break;    \
+    case 2: CALL(2); break; case 3: CALL(3); break;    \
+    case 4: CALL(4); break; case 5: CALL(5); break;    \
+    default: return cudaErrorInvalidValue;             \
+    }
+cudaError_t launch_particle_dt(const rapt::AdvArgs &a, double *key, int *idx, cudaStream_t s)
+{
+    const int kind = a.f.kind;
+    const int grid = (int)((a.nwork + 255) / 256);
+#define CALL(K) k_particle_dt<Field<K>><<<grid, 256, 0, s>>>(a, key, idx)
+    RAPT_KIND_SWITCH(CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+cudaError_t launch_field_ops(const void *args, cudaStream_t s)
+{
+    const OpsArgs &a = *static_cast<const OpsArgs *>(args);
+    const int kind = a.f.kind;
+    const int grid = (int)((a.n + 127) / 128);
+#define CALL(K) k_field_ops<Field<K>><<<grid, 128, 0, s>>>(a)
+    RAPT_KIND_SWITCH(CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+cudaError_t launch_misc(const void *args, cudaStream_t s)
+{
+    const MiscArgs &a = *static_cast<const MiscArgs *>(args);
+    const int kind = a.f.kind;
+    const int grid = (int)((a.n + 127) / 128);
+#define CALL(K) k_misc<Field<K>><<<grid, 128, 0, s>>>(a)
+    RAPT_KIND_SWITCH(CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+cudaError_t launch_bounce(const void *args, cudaStream_t s)
+{
+    const BounceArgs &a = *static_cast<const BounceArgs *>(args);
+    const int kind = a.f.kind;
+    const int grid = (int)((a.n + 127) / 128);
+#define CALL(K) k_bounce_setup<Field<K>><<<grid, 128, 0, s>>>(a)
+    RAPT_KIND_SWITCH(CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+}  // namespace RAPT_NS
+#endif

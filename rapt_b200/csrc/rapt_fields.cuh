@@ -1,0 +1,245 @@
+// rapt_fields.cuh -- analytic field models as inlined device functions + the finite-difference
+// operator layer of rapt/fields.py:_Field.  Compiled by nvcc (built-ins) and by NVRTC (user
+// snippets), so no host headers here.
+//
+// Two arithmetic flavours, selected at compile time:
+//   RAPT_STRICT=1 (built with -fmad=false): mirrors the CPU reference's unfused fp64 operation
+//                 order (including numpy's fused 3-vector dot), for parity runs;
+//   RAPT_STRICT=0 : FMA contraction allowed, pow(r2,2.5) -> rsqrt chain, reciprocal multiplies.
+#pragma once
+
+#ifndef RAPT_STRICT
+#define RAPT_STRICT 0
+#endif
+#ifndef RAPT_NS
+#define RAPT_NS rapt_fast
+#endif
+
+#define RAPT_C_LIGHT 299792458.0           /* rapt/__init__.py:8  */
+#define RAPT_EARTH_B0 3.07e-5              /* rapt/__init__.py:9  */
+#define RAPT_EARTH_RE 6378137.0            /* rapt/__init__.py:10 */
+#define RAPT_PI 3.141592653589793
+
+#define RAPT_DEV __device__ __forceinline__
+
+#include "rapt_types.h"
+
+namespace RAPT_NS {
+
+using rapt::FieldP;
+
+// np.dot on 3-vectors as executed by the reference's numpy: fma(a2,b2, fma(a1,b1, a0*b0))
+RAPT_DEV double dot3(double ax, double ay, double az, double bx, double by, double bz)
+{
+    return fma(az, bz, fma(ay, by, ax * bx));
+}
+
+RAPT_DEV double sgn(double z) { return z > 0 ? 1.0 : (z < 0 ? -1.0 : 0.0); }
+
+#ifdef RAPT_USER_FIELD
+// supplied by the NVRTC-compiled user snippet
+__device__ void rapt_user_B(double t, double x, double y, double z, const double *prm, double *B);
+#if RAPT_USER_HAS_E
+__device__ void rapt_user_E(double t, double x, double y, double z, const double *prm, double *E);
+#endif
+#endif
+
+// ------------------------------------------------------------------------------------------
+// Field models.  KIND is a compile-time constant so every kernel contains exactly one model.
+// ------------------------------------------------------------------------------------------
+template <int KIND> struct Field {
+    static constexpr bool HAS_E =
+#ifdef RAPT_USER_FIELD
+        (KIND == 100) ? (RAPT_USER_HAS_E != 0) :
+#endif
+        (KIND == 3);
+    static constexpr bool TIME_DEP = (KIND == 4) || (KIND == 100);
+    static constexpr bool UNIFORM = (KIND == 2) || (KIND == 3);
+
+    static RAPT_DEV void B(const FieldP &f, double t, double x, double y, double z,
+                           double &bx, double &by, double &bz)
+    {
+        if (KIND == 0) {                    // EarthDipole, fields.py:315-317
+            double r2 = x * x + y * y + z * z;
+#if RAPT_STRICT
+            double s = f.prm[0] / pow(r2, 2.5);
+            bx = s * (x * z); by = s * (y * z); bz = s * (z * z - r2 / 3);
+#else
+            double ir = rsqrt(r2), ir2 = ir * ir;
+            double s = f.prm[0] * (ir2 * ir2 * ir);
+            bx = s * (x * z); by = s * (y * z); bz = s * (z * z - r2 * (1.0 / 3.0));
+#endif
+        } else if (KIND == 1) {             // DoubleDipole, fields.py:358-362
+            double x2 = x - f.prm[1], k = f.prm[2];
+#if RAPT_STRICT
+            double p1 = pow(x * x + y * y + z * z, 5.0 / 2.0);
+            double a0 = 3 * x * z / p1, a1 = 3 * y * z / p1, a2 = (2 * z * z - x * x - y * y) / p1;
+            double p2 = pow(x2 * x2 + y * y + z * z, 5.0 / 2.0);
+            double b0 = k * (3 * x2 * z) / p2, b1 = k * (3 * y * z) / p2, b2 = k * (2 * z * z - x2 * x2 - y * y) / p2;
+            bx = f.prm[0] * (a0 + b0); by = f.prm[0] * (a1 + b1); bz = f.prm[0] * (a2 + b2);
+#else
+            double yz2 = y * y + z * z, zz2 = 2 * z * z - y * y;
+            double r1 = rsqrt(x * x + yz2), r2_ = rsqrt(x2 * x2 + yz2);
+            double q1 = r1 * r1, q2 = r2_ * r2_;
+            double w1 = q1 * q1 * r1, w2 = k * (q2 * q2 * r2_);
+            double tz = 3 * z;
+            bx = f.prm[0] * (tz * (x * w1 + x2 * w2));
+            by = f.prm[0] * (tz * y * (w1 + w2));
+            bz = f.prm[0] * ((zz2 - x * x) * w1 + (zz2 - x2 * x2) * w2);
+#endif
+        } else if (KIND == 2 || KIND == 3) { // UniformBz / UniformCrossedEB, fields.py:390
+            bx = 0; by = 0; bz = f.prm[0];
+        } else if (KIND == 4) {             // VarEarthDipole, fields.py:469-470
+            double s = -RAPT_EARTH_B0 * (RAPT_EARTH_RE * RAPT_EARTH_RE * RAPT_EARTH_RE) *
+                       (1 + f.prm[0] * sin(2 * RAPT_PI * t / f.prm[1]));
+#if RAPT_STRICT
+            double p = pow(x * x + y * y + z * z, 5.0 / 2.0);
+            bx = s * (3 * x * z) / p; by = s * (3 * y * z) / p; bz = s * (2 * z * z - x * x - y * y) / p;
+#else
+            double ir = rsqrt(x * x + y * y + z * z), ir2 = ir * ir;
+            double w = s * (ir2 * ir2 * ir);
+            bx = w * (3 * x * z); by = w * (3 * y * z); bz = w * (2 * z * z - x * x - y * y);
+#endif
+        } else if (KIND == 5) {             // Parabolic, fields.py:506-511 (quirk Q6: module B0 outside |z|<=1)
+            if (fabs(z) <= 1.0) bx = f.prm[0] * z / f.prm[2];
+            else bx = sgn(z) * RAPT_EARTH_B0;
+            by = 0; bz = f.prm[1];
+        }
+#ifdef RAPT_USER_FIELD
+        else if (KIND == 100) {
+            double o[3];
+            rapt_user_B(t, x, y, z, f.prm, o);
+            bx = o[0]; by = o[1]; bz = o[2];
+        }
+#endif
+        else { bx = by = bz = 0; }
+    }
+
+    static RAPT_DEV void E(const FieldP &f, double t, double x, double y, double z,
+                           double &ex, double &ey, double &ez)
+    {
+        ex = 0; ey = 0; ez = 0;             // fields.py:59-74
+        if (KIND == 3) ey = f.prm[1];       // fields.py:427
+#if defined(RAPT_USER_FIELD) && RAPT_USER_HAS_E
+        if (KIND == 100) {
+            double o[3];
+            rapt_user_E(t, x, y, z, f.prm, o);
+            ex = o[0]; ey = o[1]; ez = o[2];
+        }
+#endif
+    }
+
+    // fields.py:108-109
+    static RAPT_DEV double magB(const FieldP &f, double t, double x, double y, double z)
+    {
+        double bx, by, bz; B(f, t, x, y, z, bx, by, bz);
+        return sqrt(dot3(bx, by, bz, bx, by, bz));
+    }
+    // fields.py:90-91
+    static RAPT_DEV void unitb(const FieldP &f, double t, double x, double y, double z,
+                               double &ux, double &uy, double &uz)
+    {
+        double bx, by, bz; B(f, t, x, y, z, bx, by, bz);
+#if RAPT_STRICT
+        double m = sqrt(dot3(bx, by, bz, bx, by, bz));
+        ux = bx / m; uy = by / m; uz = bz / m;
+#else
+        double im = rsqrt(dot3(bx, by, bz, bx, by, bz));
+        ux = bx * im; uy = by * im; uz = bz * im;
+#endif
+    }
+    // fields.py:125-131 : central differences with the nominal 2*d (perturb-then-round as the reference)
+    static RAPT_DEV void gradB(const FieldP &f, double t, double x, double y, double z,
+                               double &gx, double &gy, double &gz)
+    {
+        if (UNIFORM) { gx = gy = gz = 0; return; }      // exact: identical field values subtract to 0
+        double d = f.gradstep;
+#if RAPT_STRICT
+        gx = (magB(f, t, x + d, y, z) - magB(f, t, x - d, y, z)) / (2 * d);
+        gy = (magB(f, t, x, y + d, z) - magB(f, t, x, y - d, z)) / (2 * d);
+        gz = (magB(f, t, x, y, z + d) - magB(f, t, x, y, z - d)) / (2 * d);
+#else
+        double i2d = 1.0 / (2 * d);
+        gx = (magB(f, t, x + d, y, z) - magB(f, t, x - d, y, z)) * i2d;
+        gy = (magB(f, t, x, y + d, z) - magB(f, t, x, y - d, z)) * i2d;
+        gz = (magB(f, t, x, y, z + d) - magB(f, t, x, y, z - d)) * i2d;
+#endif
+    }
+    // fields.py:191-200 with _M1 (fields.py:33-36); strict mode keeps the summation order the
+    // reference's BLAS uses for np.dot(_M1, beta)
+    static RAPT_DEV void curlb(const FieldP &f, double t, double x, double y, double z,
+                               double &cx, double &cy, double &cz)
+    {
+        if (UNIFORM) { cx = cy = cz = 0; return; }
+        double d = f.gradstep;
+        double pxx, pxy, pxz, mxx, mxy, mxz, pyx, pyy, pyz, myx, myy, myz, pzx, pzy, pzz, mzx, mzy, mzz;
+        unitb(f, t, x + d, y, z, pxx, pxy, pxz); unitb(f, t, x - d, y, z, mxx, mxy, mxz);   // beta[0..2], [3..5]
+        unitb(f, t, x, y + d, z, pyx, pyy, pyz); unitb(f, t, x, y - d, z, myx, myy, myz);   // beta[6..8], [9..11]
+        unitb(f, t, x, y, z + d, pzx, pzy, pzz); unitb(f, t, x, y, z - d, mzx, mzy, mzz);   // beta[12..14], [15..17]
+        (void)pxx; (void)mxx; (void)pyy; (void)myy; (void)pzz; (void)mzz;
+#if RAPT_STRICT
+        cx = ((pyz + (-myz + -pzy)) + mzy) / (2 * d);          // +b8 -b11 -b13 +b16
+        cy = ((-pxz + pzx) + (mxz + -mzx)) / (2 * d);          // -b2 +b5 +b12 -b15
+        cz = ((pxy + myx) + (-mxy + -pyx)) / (2 * d);          // +b1 -b4 -b6 +b9
+#else
+        double i2d = 1.0 / (2 * d);
+        cx = ((pyz - myz) - (pzy - mzy)) * i2d;
+        cy = ((pzx - mzx) - (pxz - mxz)) * i2d;
+        cz = ((pxy - mxy) - (pyx - myx)) * i2d;
+#endif
+    }
+    // fields.py:239-245
+    static RAPT_DEV void dbdt(const FieldP &f, double t, double x, double y, double z,
+                              double &ox, double &oy, double &oz)
+    {
+        double d = f.tstep, ax, ay, az, bx, by, bz;
+        unitb(f, t - d, x, y, z, ax, ay, az);
+        unitb(f, t + d, x, y, z, bx, by, bz);
+        ox = (bx - ax) / d / 2; oy = (by - ay) / d / 2; oz = (bz - az) / d / 2;
+    }
+    // fields.py:217-223
+    static RAPT_DEV double dBdt(const FieldP &f, double t, double x, double y, double z)
+    {
+        double d = f.tstep;
+        return (magB(f, t + d, x, y, z) - magB(f, t - d, x, y, z)) / d / 2;
+    }
+    // fields.py:148-153 : J[i][j] = dB_i/dx_j
+    static RAPT_DEV void jacobianB(const FieldP &f, double t, double x, double y, double z, double J[9])
+    {
+        double d = f.gradstep, ax, ay, az, bx, by, bz;
+        B(f, t, x + d, y, z, ax, ay, az); B(f, t, x - d, y, z, bx, by, bz);
+        J[0] = (ax - bx) / (2 * d); J[3] = (ay - by) / (2 * d); J[6] = (az - bz) / (2 * d);
+        B(f, t, x, y + d, z, ax, ay, az); B(f, t, x, y - d, z, bx, by, bz);
+        J[1] = (ax - bx) / (2 * d); J[4] = (ay - by) / (2 * d); J[7] = (az - bz) / (2 * d);
+        B(f, t, x, y, z + d, ax, ay, az); B(f, t, x, y, z - d, bx, by, bz);
+        J[2] = (ax - bx) / (2 * d); J[5] = (ay - by) / (2 * d); J[8] = (az - bz) / (2 * d);
+    }
+    // fields.py:261
+    static RAPT_DEV double lengthscale(const FieldP &f, double t, double x, double y, double z)
+    {
+        double J[9], m = 0;
+        jacobianB(f, t, x, y, z, J);
+#pragma unroll
+        for (int i = 0; i < 9; i++) m = fmax(m, fabs(J[i]));
+        return magB(f, t, x, y, z) / m;
+    }
+    // fields.py:277-280
+    static RAPT_DEV double timescale(const FieldP &f, double t, double x, double y, double z)
+    {
+        return magB(f, t, x, y, z) / fabs(dBdt(f, t, x, y, z));
+    }
+    // fields.py:170-174 (quirk Q7: np.dot(gB, B) with the scalar B is element-wise)
+    static RAPT_DEV double curvature(const FieldP &f, double t, double x, double y, double z)
+    {
+        double bx, by, bz, gx, gy, gz;
+        B(f, t, x, y, z, bx, by, bz);
+        double Bm = sqrt(dot3(bx, by, bz, bx, by, bz));
+        gradB(f, t, x, y, z, gx, gy, gz);
+        double px = gx - ((gx * Bm) / (Bm * Bm)) * bx;
+        double py = gy - ((gy * Bm) / (Bm * Bm)) * by;
+        double pz = gz - ((gz * Bm) / (Bm * Bm)) * bz;
+        return sqrt(dot3(px, py, pz, px, py, pz)) / Bm;
+    }
+};
+
+}  // namespace RAPT_NS

@@ -1,0 +1,366 @@
+// rapt_gc.cuh -- GuidingCenter.advance (GuidingCenter.py:397-458) for an ensemble: one thread per
+// guiding centre, DOPRI5 (scipy "dopri5" as driven at GuidingCenter.py:450-453: fresh call per
+// output row, beta -> 0.04, nsteps 500) with the three selectable equations of motion
+// (GuidingCenter.py:329-395) on the finite-difference operators of rapt/fields.py.
+//
+// Loop shape: the right-hand side (7 field evaluations + normalisations) dwarfs the stage
+// arithmetic, so the flat per-lane loop evaluates exactly ONE right-hand side per iteration and a
+// small state machine (stage) decides what the evaluation is for: the k1 of a fresh particle,
+// HINIT's Euler probe, or stage 2..7 of a step.  Lanes in different stages, rows or particles
+// therefore still execute the expensive code together; only the cheap stage bookkeeping diverges.
+//
+// The reference evaluates curlb (6 x unitb) and gradB (6 x magB) at the SAME six shifted points
+// (fields.py:125-131, 191-200); unitb and magB of one point share B and sqrt(B.B), so evaluating each
+// point once (7 field evaluations per RHS instead of 13) is bit-identical.
+#pragma once
+#include "rapt_fields.cuh"
+#include "dop_const.cuh"
+
+namespace RAPT_NS {
+
+using rapt::ParamsP;
+using rapt::AdvArgs;
+
+// |B| and b at one point
+template <class F>
+RAPT_DEV void mag_and_unit(const FieldP &f, double t, double x, double y, double z,
+                           double &m, double &ux, double &uy, double &uz)
+{
+    double bx, by, bz; F::B(f, t, x, y, z, bx, by, bz);
+    m = sqrt(dot3(bx, by, bz, bx, by, bz));
+#if RAPT_STRICT
+    ux = bx / m; uy = by / m; uz = bz / m;
+#else
+    double im = 1.0 / m;
+    ux = bx * im; uy = by * im; uz = bz * im;
+#endif
+}
+
+// gradB (fields.py:125-131) and curlb (fields.py:191-200) from one pass over the six shifted points
+template <class F>
+RAPT_DEV void grad_and_curl(const FieldP &f, double t, double x, double y, double z,
+                            double (&g)[3], double (&c)[3])
+{
+    if (F::UNIFORM) { g[0] = g[1] = g[2] = 0; c[0] = c[1] = c[2] = 0; return; }
+    const double d = f.gradstep;
+    double mp, mm, pxx, pxy, pxz, mxx, mxy, mxz, pyx, pyy, pyz, myx, myy, myz, pzx, pzy, pzz, mzx, mzy, mzz;
+#if RAPT_STRICT
+    const double den = 2 * d;
+#define RAPT_FD(a, b) (((a) - (b)) / den)
+#else
+    const double i2d = 1.0 / (2 * d);
+#define RAPT_FD(a, b) (((a) - (b)) * i2d)
+#endif
+    mag_and_unit<F>(f, t, x + d, y, z, mp, pxx, pxy, pxz); mag_and_unit<F>(f, t, x - d, y, z, mm, mxx, mxy, mxz);
+    g[0] = RAPT_FD(mp, mm);
+    mag_and_unit<F>(f, t, x, y + d, z, mp, pyx, pyy, pyz); mag_and_unit<F>(f, t, x, y - d, z, mm, myx, myy, myz);
+    g[1] = RAPT_FD(mp, mm);
+    mag_and_unit<F>(f, t, x, y, z + d, mp, pzx, pzy, pzz); mag_and_unit<F>(f, t, x, y, z - d, mm, mzx, mzy, mzz);
+    g[2] = RAPT_FD(mp, mm);
+    (void)pxx; (void)mxx; (void)pyy; (void)myy; (void)pzz; (void)mzz;
+#if RAPT_STRICT
+    // summation order of np.dot(_M1, beta) in the reference's BLAS (see oracle/rapt_oracle.c field_curlb)
+    c[0] = ((pyz + (-myz + -pzy)) + mzy) / den;
+    c[1] = ((-pxz + pzx) + (mxz + -mzx)) / den;
+    c[2] = ((pxy + myx) + (-mxy + -pyx)) / den;
+#else
+    c[0] = ((pyz - myz) - (pzy - mzy)) * i2d;
+    c[1] = ((pzx - mzx) - (pxz - mxz)) * i2d;
+    c[2] = ((pxy - mxy) - (pyx - myx)) * i2d;
+#endif
+#undef RAPT_FD
+}
+
+struct GcConst { double mass, q, mu, v; };
+
+// GuidingCenter._TaoChanBrizardEOM :329-355, _BrizardChanEOM :357-379, _NorthropTellerEOM :381-395
+template <class F>
+RAPT_DEV void gc_rhs(const FieldP &f, const GcConst &c, int eom, int equatorial,
+                     double t, const double (&Y)[4], double (&out)[4])
+{
+    const double m = c.mass, q = c.q, mu = c.mu, ppar = Y[3];
+    double bx, by, bz, gB[3], cb[3];
+    F::B(f, t, Y[0], Y[1], Y[2], bx, by, bz);
+    const double Bmag = sqrt(dot3(bx, by, bz, bx, by, bz));
+    const double ux = bx / Bmag, uy = by / Bmag, uz = bz / Bmag;
+    grad_and_curl<F>(f, t, Y[0], Y[1], Y[2], gB, cb);
+    if (eom == 0) {
+        const double pm = ppar / (m * RAPT_C_LIGHT);
+        const double gamma = sqrt(1 + 2 * mu * Bmag / (m * RAPT_C_LIGHT * RAPT_C_LIGHT) + pm * pm);
+        const double Bsx = bx + ppar * cb[0] / q, Bsy = by + ppar * cb[1] / q, Bsz = bz + ppar * cb[2] / q;
+        const double Bsp = dot3(Bsx, Bsy, Bsz, ux, uy, uz);
+        double ex = 0, ey = 0, ez = 0, dbx = 0, dby = 0, dbz = 0;
+        if (F::HAS_E) F::E(f, t, Y[0], Y[1], Y[2], ex, ey, ez);
+        if (F::TIME_DEP) { if (!f.is_static) F::dbdt(f, t, Y[0], Y[1], Y[2], dbx, dby, dbz); }
+        const double Esx = ex - (ppar * dbx + mu * gB[0] / gamma) / q;
+        const double Esy = ey - (ppar * dby + mu * gB[1] / gamma) / q;
+        const double Esz = ez - (ppar * dbz + mu * gB[2] / gamma) / q;
+        const double cx = Esy * uz - Esz * uy, cy = Esz * ux - Esx * uz, cz = Esx * uy - Esy * ux;
+        const double gmm = gamma * m;
+        out[0] = (ppar * Bsx / gmm + cx) / Bsp;
+        out[1] = (ppar * Bsy / gmm + cy) / Bsp;
+        out[2] = (ppar * Bsz / gmm + cz) / Bsp;
+        out[3] = q * dot3(Esx, Esy, Esz, Bsx, Bsy, Bsz) / Bsp;
+    } else if (eom == 1) {
+        const double vc = c.v / RAPT_C_LIGHT;
+        const double gamma = 1.0 / sqrt(1 - vc * vc);
+        const double Bsx = bx + ppar * cb[0] / q, Bsy = by + ppar * cb[1] / q, Bsz = bz + ppar * cb[2] / q;
+        const double Bsp = dot3(Bsx, Bsy, Bsz, ux, uy, uz);
+        const double cx = uy * gB[2] - uz * gB[1], cy = uz * gB[0] - ux * gB[2], cz = ux * gB[1] - uy * gB[0];
+        const double gmm = gamma * m, qg = q * gamma;
+        out[0] = (ppar * Bsx / gmm + mu * cx / qg) / Bsp;
+        out[1] = (ppar * Bsy / gmm + mu * cy / qg) / Bsp;
+        out[2] = (ppar * Bsz / gmm + mu * cz / qg) / Bsp;
+        out[3] = -mu * dot3(Bsx, Bsy, Bsz, gB[0], gB[1], gB[2]) / (gamma * Bsp);
+    } else {
+        const double vc = c.v / RAPT_C_LIGHT;
+        const double gamma = 1.0 / sqrt(1 - vc * vc);
+        const double gm = gamma * m;
+        const double cx = uy * gB[2] - uz * gB[1], cy = uz * gB[0] - ux * gB[2], cz = ux * gB[1] - uy * gB[0];
+        const double s = (gm * (c.v * c.v) + ppar * ppar / gm) / (2 * q * (Bmag * Bmag));
+        out[0] = s * cx + ppar * ux / gm;
+        out[1] = s * cy + ppar * uy / gm;
+        out[2] = s * cz + ppar * uz / gm;
+        out[3] = -mu * dot3(ux, uy, uz, gB[0], gB[1], gB[2]) / gamma;
+    }
+    if (equatorial) { out[2] = 0; out[3] = 0; }
+}
+
+// utils.cyclotron_radius2 (utils.py:183-187) given |B|
+RAPT_DEV double cycrad2(double Bmag, double vpar, double v, double mass, double q)
+{
+    double vc = v / RAPT_C_LIGHT;
+    double gamma = 1.0 / sqrt(1 - vc * vc);
+    double vperp = sqrt((v - vpar) * (v + vpar));
+    return gamma * mass * vperp / (fabs(q) * Bmag);
+}
+
+// GuidingCenter.isadiabatic :323-327 with cycrad :517-529 and cycper :531-541 (quirk Q10 kept)
+template <class F>
+RAPT_DEV bool gc_isadiabatic(const FieldP &f, const ParamsP &p, double t, const double (&y)[4],
+                             double mu, double mass, double q)
+{
+    const double pp = y[3];
+    const double Bmag = F::magB(f, t, y[0], y[1], y[2]);
+    const double pmc = pp / mass / RAPT_C_LIGHT;
+    const double gamma = sqrt(1 + 2 * mu * Bmag / (mass * RAPT_C_LIGHT * RAPT_C_LIGHT) + pmc * pmc);
+    double vp, v;
+    if (gamma - 1 < 1e-6) { vp = pp / mass; v = sqrt(2 * mu * Bmag / mass + vp * vp); }
+    else { vp = pp / mass / gamma; v = RAPT_C_LIGHT * sqrt(1 - 1 / (gamma * gamma)); }
+    const double rho = cycrad2(Bmag, vp, v, mass, q);
+    bool sp = rho / F::lengthscale(f, t, y[0], y[1], y[2]) < p.epss;
+    if (f.is_static || !sp) return sp;
+    const double g2 = sqrt(1 + 2 * mu * Bmag / (mass * RAPT_C_LIGHT * RAPT_C_LIGHT) + pp * pp);
+    double v2;
+    if (g2 - 1 < 1e-6) { double vq = pp / mass; v2 = sqrt(2 * mu * Bmag / mass + vq * vq); }
+    else v2 = RAPT_C_LIGHT * sqrt(1 - 1 / (g2 * g2));
+    const double vc = v2 / RAPT_C_LIGHT;
+    const double per = 2 * RAPT_PI * (1.0 / sqrt(1 - vc * vc)) * mass / Bmag / fabs(q);
+    return per / F::timescale(f, t, y[0], y[1], y[2]) < p.epst;
+}
+
+enum { S_FETCH = 0, S_K1, S_HINIT, S_2, S_3, S_4, S_5, S_6, S_7 };
+
+template <class F>
+__global__ void __launch_bounds__(128, 2) k_gc_dopri5(const AdvArgs a)
+{
+    const double rtol = a.p.rtol, atol = a.p.atol;
+    const int eqf = a.p.enforce_equatorial, eom = a.eom;
+    const double beta = 0.04, safe = 0.9, fac1 = 0.2, fac2 = 10.0, uround = 2.3e-16;
+    const double expo1 = 0.2 - beta * 0.75, facc1 = 1.0 / fac1, facc2 = 1.0 / fac2;
+
+    double y[4], k1[4], k2[4], k3[4], k4[4], k5[4], k6[4], y1[4], yin[4], kout[4];
+    double x = 0, h = 0, xend = 0, tstop = 0, dt = 0, facold = 1e-4, hmax = 0, tin = 0, dnf = 0;
+    GcConst gc = {0, 0, 0, 0};
+    int pid = -1, stage = S_FETCH;
+    int nstep = 0, naccpt = 0, nrejct = 0, ncalls = 0, nstep_row = 0, naccpt_row = 0;
+    int rowidx = 0, nst = 0, st = RAPT_ST_OK;
+    bool last = false, reject = false;
+    double *myrows = nullptr;
+
+    for (;;) {
+        if (stage == S_FETCH) {
+            if (pid >= 0) {      // write back the finished guiding centre
+                a.t[pid] = x; a.s1[pid] = y[0]; a.s2[pid] = y[1]; a.s3[pid] = y[2]; a.s4[pid] = y[3];
+                int *c = a.counters + 4 * (long long)pid;
+                int nf = 2 * ncalls + 6 * nstep;                 // as scipy counts: SURVEY.md §3.1
+                if (a.append) { c[0] += nf; c[1] += nstep; c[2] += naccpt; c[3] += nrejct; }
+                else { c[0] = nf; c[1] = nstep; c[2] = naccpt; c[3] = nrejct; }
+                a.status[pid] = st;
+                a.tcur[pid] = x;                                 // GuidingCenter.py:456
+                if (a.nrows) a.nrows[pid] = rowidx + 1;
+                a.nstored[pid] = nst;
+            }
+            int w = atomicAdd(a.queue, 1);
+            if (w >= a.nwork) break;
+            pid = a.order ? a.order[w] : w;
+            x = a.t[pid];
+            y[0] = a.s1[pid]; y[1] = a.s2[pid]; y[2] = a.s3[pid]; y[3] = a.s4[pid];
+            gc.mass = a.mass[pid]; gc.q = a.charge[pid]; gc.mu = a.mu[pid]; gc.v = a.v[pid];
+            dt = a.dtin[pid];
+            double delta = a.delta_arr ? a.delta_arr[pid] : a.delta;
+            tstop = x + delta;                                   // GuidingCenter.py:452
+            nstep = naccpt = nrejct = ncalls = 0; rowidx = 0; st = RAPT_ST_OK;
+            myrows = a.rows ? a.rows + (size_t)pid * (size_t)a.max_rows * 8 : nullptr;
+            if (a.append) nst = a.nstored[pid];
+            else {
+                nst = 0;
+                if (myrows && a.store_every > 0 && a.max_rows > 0) {
+                    double2 *r = reinterpret_cast<double2 *>(myrows);
+                    r[0] = make_double2(x, y[0]); r[1] = make_double2(y[1], y[2]);
+                    r[2] = make_double2(y[3], gc.mu); r[3] = make_double2(0.0, 0.0);
+                    nst = 1;
+                }
+            }
+            if (!(x < tstop)) { stage = S_FETCH; continue; }     // delta <= 0
+            tin = x;
+#pragma unroll
+            for (int i = 0; i < 4; i++) yin[i] = y[i];
+            stage = S_K1;
+        }
+
+        gc_rhs<F>(a.f, gc, eom, eqf, tin, yin, kout);
+
+        bool row_start = false, begin_step = false;
+        switch (stage) {
+        case S_K1:
+#pragma unroll
+            for (int i = 0; i < 4; i++) k1[i] = kout[i];
+            row_start = true;
+            break;
+        case S_HINIT: {
+            double der2 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                double sk = atol + rtol * fabs(y[i]);
+                der2 += ((kout[i] - k1[i]) / sk) * ((kout[i] - k1[i]) / sk);
+            }
+            der2 = sqrt(der2) / h;
+            double der12 = fmax(fabs(der2), sqrt(dnf));
+            double h1 = (der12 <= 1e-15) ? fmax(1e-6, fabs(h) * 1e-3) : pow(0.01 / der12, 1.0 / 5.0);
+            h = fmin(fmin(100 * fabs(h), h1), hmax);
+            facold = 1e-4; last = false; reject = false; nstep_row = 0; naccpt_row = 0;
+            ncalls++;
+            begin_step = true;
+            break; }
+        case S_2:
+#pragma unroll
+            for (int i = 0; i < 4; i++) { k2[i] = kout[i]; yin[i] = y[i] + h * (T5(A3_1) * k1[i] + T5(A3_2) * k2[i]); }
+            tin = x + T5(C3) * h; stage = S_3;
+            break;
+        case S_3:
+#pragma unroll
+            for (int i = 0; i < 4; i++) { k3[i] = kout[i]; yin[i] = y[i] + h * (T5(A4_1) * k1[i] + T5(A4_2) * k2[i] + T5(A4_3) * k3[i]); }
+            tin = x + T5(C4) * h; stage = S_4;
+            break;
+        case S_4:
+#pragma unroll
+            for (int i = 0; i < 4; i++) { k4[i] = kout[i]; yin[i] = y[i] + h * (T5(A5_1) * k1[i] + T5(A5_2) * k2[i] + T5(A5_3) * k3[i] + T5(A5_4) * k4[i]); }
+            tin = x + T5(C5) * h; stage = S_5;
+            break;
+        case S_5:
+#pragma unroll
+            for (int i = 0; i < 4; i++) { k5[i] = kout[i]; yin[i] = y[i] + h * (T5(A6_1) * k1[i] + T5(A6_2) * k2[i] + T5(A6_3) * k3[i] + T5(A6_4) * k4[i] + T5(A6_5) * k5[i]); }
+            tin = x + h; stage = S_6;
+            break;
+        case S_6:
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                k6[i] = kout[i];
+                y1[i] = y[i] + h * (T5(A7_1) * k1[i] + T5(A7_3) * k3[i] + T5(A7_4) * k4[i] + T5(A7_5) * k5[i] + T5(A7_6) * k6[i]);
+                yin[i] = y1[i];
+            }
+            tin = x + h; stage = S_7;
+            break;
+        case S_7: {
+            double err = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                k2[i] = kout[i];
+                double e = (T5(E1) * k1[i] + T5(E3) * k3[i] + T5(E4) * k4[i] + T5(E5) * k5[i] + T5(E6) * k6[i] + T5(E7) * k2[i]) * h;
+                double sk = atol + rtol * fmax(fabs(y[i]), fabs(y1[i]));
+                err += (e / sk) * (e / sk);
+            }
+            err = sqrt(err / 4);
+            double fac11 = pow(err, expo1);
+            double fac = fac11 / pow(facold, beta);
+            fac = fmax(facc2, fmin(facc1, fac / safe));
+            double hnew = h / fac;
+            if (err <= 1.0) {
+                facold = fmax(err, 1e-4);
+                naccpt++; naccpt_row++;
+#pragma unroll
+                for (int i = 0; i < 4; i++) { k1[i] = k2[i]; y[i] = y1[i]; }
+                x = x + h;
+                if (last) {
+                    // ---- output row complete (GuidingCenter.py:453-458)
+                    rowidx++;
+                    if (myrows && a.store_every > 0 && (rowidx % a.store_every) == 0 && nst < a.max_rows) {
+                        double2 *r = reinterpret_cast<double2 *>(myrows + (size_t)nst * 8);
+                        double tag = a.segtag ? (double)a.segtag[pid] : (double)nstep;
+                        r[0] = make_double2(x, y[0]); r[1] = make_double2(y[1], y[2]);
+                        r[2] = make_double2(y[3], gc.mu); r[3] = make_double2(0.0, tag);
+                        nst++;
+                    }
+                    if (a.p.check_adiabaticity) {
+                        if (!gc_isadiabatic<F>(a.f, a.p, x, y, gc.mu, gc.mass, gc.q)) st = RAPT_ST_NONADIABATIC;
+                    }
+                    if (st == RAPT_ST_OK && x < tstop) row_start = true;
+                    else stage = S_FETCH;
+                } else {
+                    if (fabs(hnew) > hmax) hnew = hmax;
+                    if (reject) hnew = fmin(fabs(hnew), fabs(h));
+                    reject = false;
+                    h = hnew;
+                    begin_step = true;
+                }
+            } else {
+                hnew = h / fmin(facc1, fac11 / safe);
+                reject = true;
+                if (naccpt_row >= 1) nrejct++;
+                last = false;
+                h = hnew;
+                begin_step = true;
+            }
+            break; }
+        default: break;
+        }
+
+        if (row_start) {
+            // new output row = new solver call: HINIT part 1
+            xend = x + dt;                                       // GuidingCenter.py:453
+            hmax = fabs(xend - x);
+            double dny = 0;
+            dnf = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                double sk = atol + rtol * fabs(y[i]);
+                dnf += (k1[i] / sk) * (k1[i] / sk);
+                dny += (y[i] / sk) * (y[i] / sk);
+            }
+            h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
+            h = fmin(h, hmax);
+#pragma unroll
+            for (int i = 0; i < 4; i++) yin[i] = y[i] + h * k1[i];
+            tin = x + h;
+            stage = S_HINIT;
+        }
+        if (begin_step) {
+            if (nstep_row > 500) st = RAPT_ST_NMAX;
+            else if (0.1 * fabs(h) <= fabs(x) * uround) st = RAPT_ST_HSMALL;
+            if (st != RAPT_ST_OK) {
+                rowidx++;                                         // the failed row is still appended
+                stage = S_FETCH;
+                continue;
+            }
+            if ((x + 1.01 * h - xend) > 0.0) { h = xend - x; last = true; }
+            nstep_row++; nstep++;
+#pragma unroll
+            for (int i = 0; i < 4; i++) yin[i] = y[i] + h * T5(A2_1) * k1[i];
+            tin = x + T5(C2) * h;
+            stage = S_2;
+        }
+    }
+}
+
+}  // namespace RAPT_NS

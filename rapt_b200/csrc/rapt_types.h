@@ -1,0 +1,86 @@
+// rapt_types.h -- POD argument blocks shared by the host C-ABI layer, both arithmetic flavours of
+// the kernels and the NVRTC-compiled user-field kernels.  Layouts of FieldP / ParamsP mirror
+// rapt_field_t / rapt_params_t in include/rapt_b200.h (static_asserts in capi.cu).
+#pragma once
+
+namespace rapt {
+
+struct FieldP {
+    int kind, is_static, user_id, nprm;
+    double prm[16];
+    double gradstep, tstep;
+};
+
+struct ParamsP {
+    double rtol, atol, cyclotronresolution, epss, epst;
+    int enforce_equatorial, check_adiabaticity, dop853_reject_rule, arith, sort_by_work;
+    int reserved[3];
+};
+
+// one advance launch (Particle or GuidingCenter)
+struct AdvArgs {
+    FieldP f;
+    ParamsP p;
+    long long nwork;              // number of work items
+    const int *order;             // work item -> particle id (NULL: identity)
+    int *queue;                   // global work counter (zeroed before launch)
+    // state, structure of arrays (Particle: t,x,y,z,px,py,pz ; GuidingCenter: t,X,Y,Z,ppar)
+    double *t, *s1, *s2, *s3, *s4, *s5, *s6;
+    const double *mass, *charge;
+    const double *mu, *v, *dtin;  // guiding centre only
+    double delta;
+    const double *delta_arr;      // per-particle duration (adaptive), or NULL
+    long long store_every, max_rows;
+    double *rows;                 // [n][max_rows][8] or NULL
+    int *nstored, *nrows, *counters, *status;
+    double *tcur, *dt_out;
+    const int *segtag;            // adaptive: column-7 tag per particle, or NULL
+    int append;                   // adaptive: rows appended after nstored[pid]; counters accumulated
+    int eom;                      // guiding centre only
+};
+
+// batched _Field operators
+struct OpsArgs {
+    FieldP f;
+    long long n;
+    const double *tpos;
+    double *B, *E, *unitb, *magB, *gradB, *jac, *curlb, *curv, *dBdt, *dbdt, *lscale, *tscale;
+};
+
+// small per-call kernels: 0 gc_construct, 1 p2g, 2 g2p, 3 isadiabatic
+struct MiscArgs {
+    FieldP f;
+    ParamsP p;
+    long long n;
+    int op;                   // 0 gc_construct, 1 p2g, 2 g2p, 3 isadiabatic
+    int mode;
+    long long stride;
+    double t_eval;
+    const double *a0, *a1, *a2, *a3, *a4, *a5, *a6;
+    double *o0, *o1, *o2;
+    int *io;
+};
+
+// bounce-period set-up
+struct BounceArgs {
+    FieldP f;
+    double flres;
+    long long n, max_pts;
+    const double *t, *x, *y, *z, *ppar, *mu, *mass;
+    double *Bm, *v, *ds;
+    int *npts;
+    double *curve;            // [n][max_pts][5] : s, x, y, z, |B|
+    double *scratch;          // [n][max_pts][4] : backward half before reversal
+};
+
+}  // namespace rapt
+
+#ifndef RAPT_ST_OK   /* same values as include/rapt_b200.h (not visible to NVRTC) */
+#define RAPT_ST_OK 1
+#define RAPT_ST_ADIABATIC 2
+#define RAPT_ST_NONADIABATIC 3
+#define RAPT_ST_NMAX (-2)
+#define RAPT_ST_HSMALL (-3)
+#define RAPT_ST_GCITER (-5)
+#define RAPT_ST_ROWCAP (-10)
+#endif
