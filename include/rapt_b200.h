@@ -166,7 +166,8 @@ int rapt_b200_gc_advance_dev(const rapt_field_t *f, const rapt_params_t *p, int 
  * RKF45 until |B| > Bm.  Outputs per particle: Bm, v, ds, npts and the curve
  * curve[(i*max_pts + k)*5 + c], c = s, x, y, z, |B| ordered as Fieldline.curve.  npts > max_pts means the
  * buffer was too small (retry).  The quadrature over the curve (scipy interp1d/brentq/quad in the
- * reference, flutils.py:295-314) is done by the caller.  HOST pointers. */
+ * reference, flutils.py:295-314) is done by the caller.  With mu == NULL the call is a plain
+ * Fieldline(tpos, field, Bmax=Bm).trace(): Bm[] is then an INPUT and ppar, mass, v may be NULL.  HOST pointers. */
 int rapt_b200_bounce_setup(const rapt_field_t *f, int arith, double fieldlineresolution, int64_t n,
                            const double *t, const double *x, const double *y, const double *z, const double *ppar,
                            const double *mu, const double *mass,

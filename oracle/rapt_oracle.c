@@ -113,6 +113,8 @@ static void field_E(const ofield_t *f, const double tp[4], double E[3])
 
 /* np.dot on 3-vectors as executed by the container's numpy (OpenBLAS 0.3.30 ddot): a fused chain
  * fma(a2,b2, fma(a1,b1, a0*b0)) -- determined by exhaustive comparison, see DESIGN.md. */
+/* Python/numpy scalar `x**2` is libm pow(x, 2.0) (0.52 ulp, not always == x*x): mirrored for bit parity */
+static double sq(double x) { return pow(x, 2.0); }
 static double dot3(const double a[3], const double b[3]) { return fma(a[2], b[2], fma(a[1], b[1], a[0] * b[0])); }
 static void cross3(const double a[3], const double b[3], double o[3])
 {
@@ -161,7 +163,7 @@ static double field_curvature(const ofield_t *f, const double tp[4])
     field_B(f, tp, Bv);
     double B = sqrt(dot3(Bv, Bv));
     field_gradB(f, tp, gB);
-    for (int i = 0; i < 3; i++) gp[i] = gB[i] - ((gB[i] * B) / (B * B)) * Bv[i];
+    for (int i = 0; i < 3; i++) gp[i] = gB[i] - ((gB[i] * B) / sq(B)) * Bv[i];
     return sqrt(dot3(gp, gp)) / B;
 }
 /* fields.py:191-200 with _M1 (fields.py:33-36): beta = [b(+x) b(-x) b(+y) b(-y) b(+z) b(-z)] */
@@ -423,7 +425,7 @@ static double cyclotron_period(const ofield_t *f, double t, const double pos[3],
 static double cyclotron_period2(const ofield_t *f, double t, const double pos[3], double speed,
                                 double mass, double charge)
 {
-    double gamma = 1.0 / sqrt(1 - (speed / C_LIGHT) * (speed / C_LIGHT));
+    double gamma = 1.0 / sqrt(1 - sq(speed / C_LIGHT));
     double tp[4] = { t, pos[0], pos[1], pos[2] };
     double B = field_magB(f, tp);
     return 2 * M_PI * gamma * mass / B / fabs(charge);
@@ -438,14 +440,14 @@ static double cyclotron_radius(const ofield_t *f, double t, const double pos[3],
     field_B(f, tp, B);
     double Bmag = sqrt(dot3(B, B));
     double vpar = dot3(vel, B) / Bmag;
-    double vperp = sqrt(vsq - vpar * vpar);
+    double vperp = sqrt(vsq - sq(vpar));
     return gamma * mass * vperp / (fabs(charge) * Bmag);
 }
 /* utils.py:183-187 */
 static double cyclotron_radius2(const ofield_t *f, double t, const double pos[3], double vpar, double v,
                                 double mass, double charge)
 {
-    double gamma = 1.0 / sqrt(1 - (v / C_LIGHT) * (v / C_LIGHT));
+    double gamma = 1.0 / sqrt(1 - sq(v / C_LIGHT));
     double tp[4] = { t, pos[0], pos[1], pos[2] }, B[3];
     field_B(f, tp, B);
     double Bmag = sqrt(dot3(B, B));
@@ -455,10 +457,10 @@ static double cyclotron_radius2(const ofield_t *f, double t, const double pos[3]
 /* utils.py:214-216 */
 static double magnetic_moment(const ofield_t *f, double t, const double pos[3], double vpar, double v, double mass)
 {
-    double gamma = 1.0 / sqrt(1 - (v / C_LIGHT) * (v / C_LIGHT));
+    double gamma = 1.0 / sqrt(1 - sq(v / C_LIGHT));
     double tp[4] = { t, pos[0], pos[1], pos[2] };
     double Bmag = field_magB(f, tp);
-    return gamma * gamma * mass * (v - vpar) * (v + vpar) / (2 * Bmag);
+    return sq(gamma) * mass * (v - vpar) * (v + vpar) / (2 * Bmag);
 }
 /* utils.py:298-303 */
 static void gyrovector(const ofield_t *f, double t, const double r[3], const double v[3], double mass,
@@ -503,7 +505,7 @@ static void getperp(const double v[3], double o[3])
     if (v[1] == 0) { o[0] = 0; o[1] = 1; o[2] = 0; return; }
     if (v[2] == 0) { o[0] = 0; o[1] = 0; o[2] = 1; return; }
     double cc = -1.0 * (v[0] + v[1]) / v[2];
-    double nrm = sqrt(2 + cc * cc);
+    double nrm = sqrt(2 + sq(cc));
     o[0] = 1 / nrm; o[1] = 1 / nrm; o[2] = cc / nrm;
 }
 /* utils.py:422-433 */
@@ -539,7 +541,7 @@ static void particle_eom(double t, const double *Y, double *out, void *vctx)
     pctx_t *c = (pctx_t *)vctx;
     double tp[4] = { t, Y[0], Y[1], Y[2] }, E[3], B[3], cr[3];
     if (!c->f->is_static)
-        c->gm = sqrt(c->mass * c->mass + dot3(Y + 3, Y + 3) / (C_LIGHT * C_LIGHT));
+        c->gm = sqrt(sq(c->mass) + dot3(Y + 3, Y + 3) / (C_LIGHT * C_LIGHT));
     double gm = c->gm;
     out[0] = Y[3] / gm; out[1] = Y[4] / gm; out[2] = Y[5] / gm;
     field_E(c->f, tp, E); field_B(c->f, tp, B);
@@ -552,7 +554,7 @@ static void particle_eom(double t, const double *Y, double *out, void *vctx)
 static int particle_isadiabatic(const ofield_t *f, const oparams_t *p, const double row[7], double mass, double charge)
 {
     const double *mom = row + 4;
-    double gm = sqrt(mass * mass + dot3(mom, mom) / (C_LIGHT * C_LIGHT));
+    double gm = sqrt(sq(mass) + dot3(mom, mom) / (C_LIGHT * C_LIGHT));
     double v[3] = { mom[0] / gm, mom[1] / gm, mom[2] / gm };
     double tp[4] = { row[0], row[1], row[2], row[3] };
     int sp = cyclotron_radius(f, row[0], row + 1, v, mass, charge) / field_lengthscale(f, tp) < p->epss;
@@ -576,7 +578,7 @@ static int particle_advance_one(const ofield_t *f, const oparams_t *p, double st
     double t0 = state[0];
     const double *mom = state + 4;
     pctx_t ctx = { f, p, mass, charge, 0 };
-    ctx.gm = sqrt(mass * mass + dot3(mom, mom) / (C_LIGHT * C_LIGHT));             /* :274 */
+    ctx.gm = sqrt(sq(mass) + dot3(mom, mom) / (C_LIGHT * C_LIGHT));             /* :274 */
     double vel[3] = { mom[0] / ctx.gm, mom[1] / ctx.gm, mom[2] / ctx.gm };           /* :275 */
     double dt = cyclotron_period(f, t0, state + 1, vel, mass, charge) / p->cyclotronresolution;  /* :282 */
     if (dt_out) *dt_out = dt;
@@ -623,7 +625,7 @@ static void gc_eom(double t, const double *Y, double *out, void *vctx)
     double Bmag = sqrt(dot3(B, B));
     for (int i = 0; i < 3; i++) ub[i] = B[i] / Bmag;
     if (c->eom == EOM_TAOCHANBRIZARD) {            /* GuidingCenter.py:336-355 */
-        double gamma = sqrt(1 + 2 * mu * Bmag / (m * C_LIGHT * C_LIGHT) + (ppar / (m * C_LIGHT)) * (ppar / (m * C_LIGHT)));
+        double gamma = sqrt(1 + 2 * mu * Bmag / (m * C_LIGHT * C_LIGHT) + sq(ppar / (m * C_LIGHT)));
         double E[3], dbdt[3], Es[3];
         field_curlb(f, tp, cb);
         for (int i = 0; i < 3; i++) Bs[i] = B[i] + ppar * cb[i] / q;
@@ -636,7 +638,7 @@ static void gc_eom(double t, const double *Y, double *out, void *vctx)
         for (int i = 0; i < 3; i++) out[i] = (ppar * Bs[i] / (gamma * m) + cr[i]) / Bsp;
         out[3] = q * dot3(Es, Bs) / Bsp;
     } else if (c->eom == EOM_BRIZARDCHAN) {        /* GuidingCenter.py:364-379 */
-        double gamma = 1.0 / sqrt(1 - (c->v / C_LIGHT) * (c->v / C_LIGHT));
+        double gamma = 1.0 / sqrt(1 - sq(c->v / C_LIGHT));
         field_gradB(f, tp, gB);
         field_curlb(f, tp, cb);
         for (int i = 0; i < 3; i++) Bs[i] = B[i] + ppar * cb[i] / q;
@@ -645,11 +647,11 @@ static void gc_eom(double t, const double *Y, double *out, void *vctx)
         for (int i = 0; i < 3; i++) out[i] = (ppar * Bs[i] / (gamma * m) + mu * cr[i] / (q * gamma)) / Bsp;
         out[3] = -mu * dot3(Bs, gB) / (gamma * Bsp);
     } else {                                       /* GuidingCenter.py:382-395 */
-        double gamma = 1.0 / sqrt(1 - (c->v / C_LIGHT) * (c->v / C_LIGHT));
+        double gamma = 1.0 / sqrt(1 - sq(c->v / C_LIGHT));
         double gm = gamma * m;
         field_gradB(f, tp, gB);
         cross3(ub, gB, cr);
-        double s = (gm * (c->v * c->v) + ppar * ppar / gm) / (2 * q * (Bmag * Bmag));
+        double s = (gm * sq(c->v) + sq(ppar) / gm) / (2 * q * sq(Bmag));
         for (int i = 0; i < 3; i++) out[i] = s * cr[i] + ppar * ub[i] / gm;
         out[3] = -mu * dot3(ub, gB) / gamma;
     }
@@ -661,9 +663,9 @@ static double gc_cycrad(const ofield_t *f, const double row[5], double mu, doubl
 {
     double tp[4] = { row[0], row[1], row[2], row[3] }, pp = row[4], vp, v;
     double Bmag = field_magB(f, tp);
-    double gamma = sqrt(1 + 2 * mu * Bmag / (mass * C_LIGHT * C_LIGHT) + (pp / mass / C_LIGHT) * (pp / mass / C_LIGHT));
-    if (gamma - 1 < 1e-6) { vp = pp / mass; v = sqrt(2 * mu * Bmag / mass + vp * vp); }
-    else { vp = pp / mass / gamma; v = C_LIGHT * sqrt(1 - 1 / (gamma * gamma)); }
+    double gamma = sqrt(1 + 2 * mu * Bmag / (mass * C_LIGHT * C_LIGHT) + sq(pp / mass / C_LIGHT));
+    if (gamma - 1 < 1e-6) { vp = pp / mass; v = sqrt(2 * mu * Bmag / mass + sq(vp)); }
+    else { vp = pp / mass / gamma; v = C_LIGHT * sqrt(1 - 1 / sq(gamma)); }
     return cyclotron_radius2(f, row[0], row + 1, vp, v, mass, charge);
 }
 /* GuidingCenter.py:531-541 (quirk Q10: pp**2 without /(mc)) */
@@ -671,9 +673,9 @@ static double gc_cycper(const ofield_t *f, const double row[5], double mu, doubl
 {
     double tp[4] = { row[0], row[1], row[2], row[3] }, pp = row[4], v;
     double Bmag = field_magB(f, tp);
-    double gamma = sqrt(1 + 2 * mu * Bmag / (mass * C_LIGHT * C_LIGHT) + pp * pp);
-    if (gamma - 1 < 1e-6) { double vp = pp / mass; v = sqrt(2 * mu * Bmag / mass + vp * vp); }
-    else v = C_LIGHT * sqrt(1 - 1 / (gamma * gamma));
+    double gamma = sqrt(1 + 2 * mu * Bmag / (mass * C_LIGHT * C_LIGHT) + sq(pp));
+    if (gamma - 1 < 1e-6) { double vp = pp / mass; v = sqrt(2 * mu * Bmag / mass + sq(vp)); }
+    else v = C_LIGHT * sqrt(1 - 1 / sq(gamma));
     return cyclotron_period2(f, row[0], row + 1, v, mass, charge);
 }
 /* GuidingCenter.py:323-327 */
@@ -724,7 +726,7 @@ static int gc_advance_one(const ofield_t *f, const oparams_t *p, int eom, double
 static void gc_construct(const ofield_t *f, double t0, const double pos[3], double v, double pa_deg, int use_pa,
                          double ppar_in, double mass, double *ppar, double *mu)
 {
-    double gamma = 1 / sqrt(1 - (v / C_LIGHT) * (v / C_LIGHT));
+    double gamma = 1 / sqrt(1 - sq(v / C_LIGHT));
     double pp = ppar_in;
     if (use_pa) {
         double vpar = (pa_deg == 90) ? 0.0 : v * cos(pa_deg * M_PI / 180);
@@ -739,10 +741,10 @@ static int switch_P2G(const ofield_t *f, const double prow[7], double mass, doub
                       double grow[5], double *mu, double *v)
 {
     const double *mom = prow + 4;
-    double gm = sqrt(mass * mass + dot3(mom, mom) / (C_LIGHT * C_LIGHT));
+    double gm = sqrt(sq(mass) + dot3(mom, mom) / (C_LIGHT * C_LIGHT));
     double vel[3] = { mom[0] / gm, mom[1] / gm, mom[2] / gm }, R[3], vp, spd;
     if (guidingcenter(f, prow[0], prow + 1, vel, mass, charge, R, &vp, &spd)) return ST_GCITER;
-    double gamma = 1 / sqrt(1 - (spd / C_LIGHT) * (spd / C_LIGHT));
+    double gamma = 1 / sqrt(1 - sq(spd / C_LIGHT));
     double pp;
     gc_construct(f, prow[0], R, spd, 0, 0, mass * gamma * vp, mass, &pp, mu);
     grow[0] = prow[0]; grow[1] = R[0]; grow[2] = R[1]; grow[3] = R[2]; grow[4] = pp;
@@ -756,8 +758,8 @@ static void switch_G2P(const ofield_t *f, const double grow[5], double mu, doubl
 {
     double tp[4] = { grow[0], grow[1], grow[2], grow[3] };
     double B = field_magB(f, tp), v, pos[3], vel[3];
-    double gammasq = 1 + 2 * mu * B / (mass * C_LIGHT * C_LIGHT) + (grow[4] / mass / C_LIGHT) * (grow[4] / mass / C_LIGHT);
-    if (sqrt(gammasq) - 1 < 1e-6) v = sqrt(2 * mu * B / mass + (grow[4] / mass) * (grow[4] / mass));
+    double gammasq = 1 + 2 * mu * B / (mass * C_LIGHT * C_LIGHT) + sq(grow[4] / mass / C_LIGHT);
+    if (sqrt(gammasq) - 1 < 1e-6) v = sqrt(2 * mu * B / mass + sq(grow[4] / mass));
     else v = C_LIGHT * sqrt(1 - 1 / gammasq);
     double vpar = grow[4] / mass / sqrt(gammasq);
     GCtoFP(f, t_eval, grow + 1, vpar, v, mass, charge, 0.0, pos, vel);
@@ -874,13 +876,13 @@ void oracle_gc_mirror(const ofield_t *f, const double state[5], double mu, doubl
 {
     double tp[4] = { state[0], state[1], state[2], state[3] }, ppar = state[4];
     double Bmag = field_magB(f, tp);
-    double gamma = sqrt(1 + 2 * mu * Bmag / (mass * C_LIGHT * C_LIGHT) + (ppar / (mass * C_LIGHT)) * (ppar / (mass * C_LIGHT)));
+    double gamma = sqrt(1 + 2 * mu * Bmag / (mass * C_LIGHT * C_LIGHT) + sq(ppar / (mass * C_LIGHT)));
     if (gamma - 1 < 1e-6) {
-        double p = sqrt(2 * mass * mu * Bmag + ppar * ppar);
-        *v = p / mass; *Bm = (p * p) / (2 * mass * mu);
+        double p = sqrt(2 * mass * mu * Bmag + sq(ppar));
+        *v = p / mass; *Bm = sq(p) / (2 * mass * mu);
     } else {
         double p = mass * C_LIGHT * sqrt((gamma + 1) * (gamma - 1));
-        *Bm = p * p / ((p - ppar) * (p + ppar)) * Bmag;
+        *Bm = sq(p) / ((p - ppar) * (p + ppar)) * Bmag;
         *v = p / mass / gamma;
     }
 }
@@ -1084,3 +1086,35 @@ int oracle_particle_isadiabatic(const ofield_t *f, const oparams_t *p, const dou
 { return particle_isadiabatic(f, p, row, mass, charge); }
 int oracle_gc_isadiabatic(const ofield_t *f, const oparams_t *p, const double row[5], double mu, double mass, double charge)
 { return gc_isadiabatic(f, p, row, mu, mass, charge); }
+
+/* right-hand sides exposed for unit tests */
+void oracle_gc_rhs(const ofield_t *f, const oparams_t *p, int eom, double mass, double charge, double mu, double v,
+                   double t, const double *Y, double *out)
+{
+    gctx_t ctx = { f, p, mass, charge, mu, v, eom };
+    gc_eom(t, Y, out, &ctx);
+}
+void oracle_particle_rhs(const ofield_t *f, const oparams_t *p, double mass, double charge, double gm,
+                         double t, const double *Y, double *out)
+{
+    pctx_t ctx = { f, p, mass, charge, gm };
+    particle_eom(t, Y, out, &ctx);
+}
+
+/* debug: one dopri5 call on the GC equations with every RHS call logged (t, Y[4], out[4]) */
+static double *g_log; static long g_nlog, g_caplog;
+static void gc_eom_logged(double t, const double *Y, double *out, void *vctx)
+{
+    gc_eom(t, Y, out, vctx);
+    if (g_nlog < g_caplog) { double *r = g_log + 9 * g_nlog; r[0] = t; memcpy(r + 1, Y, 32); memcpy(r + 5, out, 32); }
+    g_nlog++;
+}
+long oracle_gc_debug_row(const ofield_t *f, const oparams_t *p, int eom, double mass, double charge, double mu, double v,
+                         double x0, double *y, double xend, double *log, long cap)
+{
+    gctx_t ctx = { f, p, mass, charge, mu, v, eom };
+    g_log = log; g_nlog = 0; g_caplog = cap;
+    double x = x0;
+    dopri5(4, gc_eom_logged, &ctx, &x, y, xend, p->rtol, p->atol, NULL);
+    return g_nlog;
+}

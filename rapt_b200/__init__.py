@@ -43,4 +43,10 @@ params = {
     "dop853_reject_rule": 0,    # 0: scipy 1.18.1 `_dop`; 1: Hairer's Fortran (scipy 1.3.1)
 }
 
-from . import fields, engine          # noqa: E402
+from . import utils, fields, engine          # noqa: E402
+from .Particle import Particle               # noqa: E402
+from .GuidingCenter import GuidingCenter     # noqa: E402
+from .Adaptive import Adaptive               # noqa: E402
+from .BounceCenter import BounceCenter       # noqa: E402
+from .fieldline import Fieldline             # noqa: E402
+from .ensemble import ParticleEnsemble, GuidingCenterEnsemble, AdaptiveEnsemble   # noqa: E402

@@ -505,15 +505,17 @@ int rapt_b200_bounce_setup(const rapt_field_t *f, int arith, double fieldlineres
 {
     if (int rc = ensure_init()) return rc;
     if (int rc = check_field(f)) return rc;
-    if (n < 0 || max_pts < 3 || (n > 0 && (!t || !x || !y || !z || !ppar || !mu || !mass || !Bm || !v || !ds || !npts || !curve)))
+    if (n < 0 || max_pts < 3 || (n > 0 && (!t || !x || !y || !z || !Bm || !ds || !npts || !curve)))
         return fail(RAPT_E_ARG, "bounce_setup: bad argument");
+    if (mu && (!ppar || !mass || !v)) return fail(RAPT_E_ARG, "bounce_setup: ppar, mass, v required with mu");
     if (n == 0) return RAPT_OK;
     cudaStream_t s = 0;
     const size_t nb = n * sizeof(double);
     DevBuf in[7], oBm, ov, ods, onp, ocv, scr;
     const double *h[7] = {t, x, y, z, ppar, mu, mass};
-    for (int k = 0; k < 7; k++) CK(up(in[k], h[k], nb, s));
-    CK(oBm.alloc(nb)); CK(ov.alloc(nb)); CK(ods.alloc(nb)); CK(onp.alloc(n * sizeof(int)));
+    for (int k = 0; k < 7; k++) if (h[k]) CK(up(in[k], h[k], nb, s));
+    if (mu) CK(oBm.alloc(nb)); else CK(up(oBm, Bm, nb, s));      // mu == NULL: Bm is an input
+    CK(ov.alloc(nb)); CK(ods.alloc(nb)); CK(onp.alloc(n * sizeof(int)));
     CK(ocv.alloc((size_t)n * max_pts * 5 * sizeof(double))); CK(scr.alloc((size_t)n * max_pts * 4 * sizeof(double)));
     rapt::BounceArgs a;
     memset(&a, 0, sizeof a);
@@ -525,9 +527,142 @@ int rapt_b200_bounce_setup(const rapt_field_t *f, int arith, double fieldlineres
     a.curve = ocv.as<double>(); a.scratch = scr.as<double>();
     CK(FLAVOUR(arith == 1, launch_bounce, &a, s));
     g_launches++;
-    CK(down(Bm, oBm, nb, s)); CK(down(v, ov, nb, s)); CK(down(ds, ods, nb, s)); CK(down(npts, onp, n * sizeof(int), s));
+    CK(down(Bm, oBm, nb, s)); if (v) CK(down(v, ov, nb, s)); CK(down(ds, ods, nb, s)); CK(down(npts, onp, n * sizeof(int), s));
     CK(down(curve, ocv, (size_t)n * max_pts * 5 * sizeof(double), s));
     CK(cudaStreamSynchronize(s));
+    return RAPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adaptive.__init__ + Adaptive.advance for an ensemble: epochs of
+//   [particle kernel over the particle-mode list | guiding-centre kernel over the GC-mode list]
+//   -> switch + compaction kernel
+// until no tracer has t < delta.  The two advance kernels of an epoch are independent and run on two
+// streams.
+// ------------------------------------------------------------------------------------------------
+int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, int64_t n,
+                               const double *x, const double *y, const double *z,
+                               const double *vx, const double *vy, const double *vz,
+                               const double *t0, const double *mass, const double *charge,
+                               double gc_dt, double delta, int64_t store_every, int64_t max_rows, double *rows,
+                               int32_t *nstored, int32_t *nseg, int32_t *mode_out, double *fin,
+                               int32_t *counters, int32_t *status, int32_t *epochs_out)
+{
+    if (int rc = ensure_init()) return rc;
+    if (int rc = check_field(f)) return rc;
+    if (!p || n < 0 || (n > 0 && (!x || !y || !z || !vx || !vy || !vz || !t0 || !mass || !charge)))
+        return fail(RAPT_E_ARG, "adaptive_advance: null argument");
+    if (!(gc_dt > 0)) return fail(RAPT_E_ARG, "adaptive_advance: gc_dt (params['GCtimestep']) must be > 0 for ensembles");
+    if (n == 0) { if (epochs_out) *epochs_out = 0; return RAPT_OK; }
+    const bool strict = p->arith == 1;
+    const bool want_rows = rows && max_rows > 0;
+    const size_t nb = (size_t)n * sizeof(double), ni = (size_t)n * sizeof(int);
+    cudaStream_t s0 = 0, s1 = nullptr, s2 = nullptr;
+    CK(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t a, b; ~StreamGuard() { cudaStreamDestroy(a); cudaStreamDestroy(b); } } guard{s1, s2};
+    DevBuf in[9];
+    const double *h[9] = {x, y, z, vx, vy, vz, t0, mass, charge};
+    for (int k = 0; k < 9; k++) CK(up(in[k], h[k], nb, s0));
+    DevBuf ps[7], gs[7], dmode, dst, dnseg, dtag, dnst, dtvar, drem, dtcur, drows, dlp, dlg, dcounts, dcnt, ddtg, ddtp;
+    for (int k = 0; k < 7; k++) { CK(ps[k].alloc(nb)); CK(gs[k].alloc(nb)); CK(cudaMemsetAsync(gs[k].p, 0, nb, s0)); CK(cudaMemsetAsync(ps[k].p, 0, nb, s0)); }
+    CK(dmode.alloc(ni)); CK(dst.alloc(ni)); CK(dnseg.alloc(ni)); CK(dtag.alloc(ni)); CK(dnst.alloc(ni));
+    CK(dtvar.alloc(nb)); CK(drem.alloc(nb)); CK(dtcur.alloc(nb));
+    CK(drows.alloc(want_rows ? (size_t)n * max_rows * 8 * sizeof(double) : 0));
+    CK(dlp.alloc(ni)); CK(dlg.alloc(ni)); CK(dcounts.alloc(2 * sizeof(int))); CK(dcnt.alloc(4 * ni));
+    CK(ddtg.alloc(nb)); CK(ddtp.alloc(nb));
+    CK(cudaMemsetAsync(dcnt.p, 0, 4 * ni, s0)); CK(cudaMemsetAsync(dcounts.p, 0, 2 * sizeof(int), s0));
+    {   // per-tracer GC output step (uniform: params["GCtimestep"])
+        std::vector<double> hd((size_t)n, gc_dt);
+        CK(cudaMemcpyAsync(ddtg.p, hd.data(), nb, cudaMemcpyHostToDevice, s0));
+        CK(cudaStreamSynchronize(s0));
+    }
+    rapt::AdaptArgs sw;
+    memset(&sw, 0, sizeof sw);
+    memcpy(&sw.f, f, sizeof sw.f); memcpy(&sw.p, p, sizeof sw.p);
+    sw.n = n; sw.delta = delta;
+    sw.x0 = in[0].as<double>(); sw.y0 = in[1].as<double>(); sw.z0 = in[2].as<double>();
+    sw.vx0 = in[3].as<double>(); sw.vy0 = in[4].as<double>(); sw.vz0 = in[5].as<double>(); sw.t0 = in[6].as<double>();
+    sw.mass = in[7].as<double>(); sw.charge = in[8].as<double>();
+    sw.pt = ps[0].as<double>(); sw.px = ps[1].as<double>(); sw.py = ps[2].as<double>(); sw.pz = ps[3].as<double>();
+    sw.ppx = ps[4].as<double>(); sw.ppy = ps[5].as<double>(); sw.ppz = ps[6].as<double>();
+    sw.gt = gs[0].as<double>(); sw.gx = gs[1].as<double>(); sw.gy = gs[2].as<double>(); sw.gz = gs[3].as<double>();
+    sw.gpp = gs[4].as<double>(); sw.mu = gs[5].as<double>(); sw.v = gs[6].as<double>();
+    sw.mode = dmode.as<int>(); sw.status = dst.as<int>(); sw.nseg = dnseg.as<int>(); sw.segtag = dtag.as<int>();
+    sw.nstored = dnst.as<int>(); sw.tvar = dtvar.as<double>(); sw.rem = drem.as<double>(); sw.tcur = dtcur.as<double>();
+    sw.max_rows = want_rows ? max_rows : 0; sw.rows = want_rows ? drows.as<double>() : nullptr;
+    sw.listP = dlp.as<int>(); sw.listG = dlg.as<int>(); sw.counts = dcounts.as<int>();
+    sw.first = 1;
+    CK(FLAVOUR(strict, launch_adaptive_switch, &sw, s0));
+    g_launches++;
+    sw.first = 0;
+
+    rapt_params_t pc = *p;
+    pc.check_adiabaticity = 1;
+    const int gp = grid_for(1 << 30, FLAVOUR(strict, particle_blocks_per_sm));
+    const int gg = grid_for(1 << 30, FLAVOUR(strict, gc_blocks_per_sm));
+    int epochs = 0;
+    for (;; epochs++) {
+        int cnt[2] = {0, 0};
+        CK(cudaMemcpyAsync(cnt, dcounts.p, sizeof cnt, cudaMemcpyDeviceToHost, s0));
+        CK(cudaStreamSynchronize(s0));
+        if (cnt[0] == 0 && cnt[1] == 0) break;
+        if (epochs > 100000) return fail(RAPT_E_CUDA, "adaptive_advance: epoch limit");
+        CK(cudaMemsetAsync(dcounts.p, 0, 2 * sizeof(int), s0));
+        CK(cudaStreamSynchronize(s0));
+        if (cnt[0] > 0) {
+            rapt::AdvArgs a;
+            fill_common(a, f, &pc);
+            a.nwork = cnt[0]; a.order = sw.listP; a.queue = next_queue(s1);
+            a.t = sw.pt; a.s1 = sw.px; a.s2 = sw.py; a.s3 = sw.pz; a.s4 = sw.ppx; a.s5 = sw.ppy; a.s6 = sw.ppz;
+            a.mass = sw.mass; a.charge = sw.charge; a.delta = 0; a.delta_arr = sw.rem;
+            a.store_every = want_rows ? std::max<int64_t>(store_every, 1) : 0; a.max_rows = sw.max_rows; a.rows = sw.rows;
+            a.nstored = sw.nstored; a.nrows = nullptr; a.counters = dcnt.as<int>(); a.status = sw.status;
+            a.tcur = sw.tcur; a.dt_out = ddtp.as<double>(); a.segtag = sw.segtag; a.append = 1;
+            CK(FLAVOUR(strict, launch_particle, a, std::min(gp, (cnt[0] + 127) / 128), s1));
+            g_launches++;
+        }
+        if (cnt[1] > 0) {
+            rapt::AdvArgs a;
+            fill_common(a, f, &pc);
+            a.nwork = cnt[1]; a.order = sw.listG; a.queue = next_queue(s2);
+            a.t = sw.gt; a.s1 = sw.gx; a.s2 = sw.gy; a.s3 = sw.gz; a.s4 = sw.gpp;
+            a.mass = sw.mass; a.charge = sw.charge; a.mu = sw.mu; a.v = sw.v; a.dtin = ddtg.as<double>();
+            a.delta = 0; a.delta_arr = sw.rem; a.eom = RAPT_EOM_TAOCHANBRIZARD;
+            a.store_every = want_rows ? std::max<int64_t>(store_every, 1) : 0; a.max_rows = sw.max_rows; a.rows = sw.rows;
+            a.nstored = sw.nstored; a.nrows = nullptr; a.counters = dcnt.as<int>(); a.status = sw.status;
+            a.tcur = sw.tcur; a.segtag = sw.segtag; a.append = 1;
+            CK(FLAVOUR(strict, launch_gc, a, std::min(gg, (cnt[1] + 127) / 128), s2));
+            g_launches++;
+        }
+        CK(cudaStreamSynchronize(s1)); CK(cudaStreamSynchronize(s2));
+        CK(FLAVOUR(strict, launch_adaptive_switch, &sw, s0));
+        g_launches++;
+    }
+    if (epochs_out) *epochs_out = epochs;
+    // results
+    std::vector<int> hmode((size_t)n);
+    CK(cudaMemcpyAsync(hmode.data(), dmode.p, ni, cudaMemcpyDeviceToHost, s0));
+    CK(down(nstored, dnst, ni, s0)); CK(down(nseg, dnseg, ni, s0)); CK(down(status, dst, ni, s0));
+    CK(down(counters, dcnt, 4 * ni, s0));
+    if (want_rows) CK(down(rows, drows, (size_t)n * max_rows * 8 * sizeof(double), s0));
+    std::vector<double> hp[7], hg[7];
+    if (fin) {
+        for (int k = 0; k < 7; k++) {
+            hp[k].resize(n); hg[k].resize(n);
+            CK(cudaMemcpyAsync(hp[k].data(), ps[k].p, nb, cudaMemcpyDeviceToHost, s0));
+            CK(cudaMemcpyAsync(hg[k].data(), gs[k].p, nb, cudaMemcpyDeviceToHost, s0));
+        }
+    }
+    CK(cudaStreamSynchronize(s0));
+    for (int64_t i = 0; i < n; i++) {
+        if (mode_out) mode_out[i] = hmode[i];
+        if (fin) {
+            double *o = fin + 8 * i;
+            if (hmode[i] == 0) { for (int k = 0; k < 7; k++) o[k] = hp[k][i]; o[7] = 0; }
+            else { for (int k = 0; k < 5; k++) o[k] = hg[k][i]; o[5] = hg[5][i]; o[6] = hg[6][i]; o[7] = 1; }
+        }
+    }
     return RAPT_OK;
 }
 

@@ -116,6 +116,16 @@ cudaError_t launch_misc(const void *args, cudaStream_t s)
 #undef CALL
     return cudaGetLastError();
 }
+cudaError_t launch_adaptive_switch(const void *args, cudaStream_t s)
+{
+    const AdaptArgs &a = *static_cast<const AdaptArgs *>(args);
+    const int kind = a.f.kind;
+    const int grid = (int)((a.n + 255) / 256);
+#define CALL(K) k_adaptive_switch<Field<K>><<<grid, 256, 0, s>>>(a)
+    RAPT_KIND_SWITCH(CALL)
+#undef CALL
+    return cudaGetLastError();
+}
 cudaError_t launch_bounce(const void *args, cudaStream_t s)
 {
     const BounceArgs &a = *static_cast<const BounceArgs *>(args);

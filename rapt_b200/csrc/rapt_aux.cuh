@@ -12,6 +12,7 @@ namespace RAPT_NS {
 using rapt::OpsArgs;
 using rapt::MiscArgs;
 using rapt::BounceArgs;
+using rapt::AdaptArgs;
 
 // utils.magnetic_moment, utils.py:214-216
 template <class F>
@@ -269,20 +270,23 @@ __global__ void __launch_bounds__(128) k_bounce_setup(const BounceArgs a)
 {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    const double t = a.t[i], x = a.x[i], y = a.y[i], z = a.z[i], ppar = a.ppar[i], mu = a.mu[i], mass = a.mass[i];
-    // GuidingCenter.bounceperiod :595-605
-    const double Bmag = F::magB(a.f, t, x, y, z);
-    const double pmc = ppar / (mass * RAPT_C_LIGHT);
-    const double gamma = sqrt(1 + 2 * mu * Bmag / (mass * RAPT_C_LIGHT * RAPT_C_LIGHT) + pmc * pmc);
-    double Bm, v;
-    if (gamma - 1 < 1e-6) {
-        double p = sqrt(2 * mass * mu * Bmag + ppar * ppar);
-        v = p / mass; Bm = (p * p) / (2 * mass * mu);
-    } else {
-        double p = mass * RAPT_C_LIGHT * sqrt((gamma + 1) * (gamma - 1));
-        Bm = p * p / ((p - ppar) * (p + ppar)) * Bmag;
-        v = p / mass / gamma;
-    }
+    const double t = a.t[i], x = a.x[i], y = a.y[i], z = a.z[i];
+    double Bm, v = 0;
+    if (a.mu) {
+        // GuidingCenter.bounceperiod :595-605
+        const double ppar = a.ppar[i], mu = a.mu[i], mass = a.mass[i];
+        const double Bmag = F::magB(a.f, t, x, y, z);
+        const double pmc = ppar / (mass * RAPT_C_LIGHT);
+        const double gamma = sqrt(1 + 2 * mu * Bmag / (mass * RAPT_C_LIGHT * RAPT_C_LIGHT) + pmc * pmc);
+        if (gamma - 1 < 1e-6) {
+            double p = sqrt(2 * mass * mu * Bmag + ppar * ppar);
+            v = p / mass; Bm = (p * p) / (2 * mass * mu);
+        } else {
+            double p = mass * RAPT_C_LIGHT * sqrt((gamma + 1) * (gamma - 1));
+            Bm = p * p / ((p - ppar) * (p + ppar)) * Bmag;
+            v = p / mass / gamma;
+        }
+    } else Bm = a.Bm[i];                                     // Fieldline(tpos, field, Bmax=Bm)
     const double ds = 1 / F::curvature(a.f, t, x, y, z) / a.flres;      // fieldline.py:31-35
     a.Bm[i] = Bm; a.v[i] = v; a.ds[i] = ds;
 
@@ -328,6 +332,111 @@ __global__ void __launch_bounds__(128) k_bounce_setup(const BounceArgs a)
         o[4] = F::magB(a.f, t, o[1], o[2], o[3]);        // Fieldline.getB, fieldline.py:123-127
     }
     a.npts[i] = (int)n;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Adaptive epochs.  k_adaptive_switch runs between the per-mode advance kernels:
+//   first == 1 : Adaptive.__init__ (Adaptive.py:96-104) -- build the Particle, test isadiabatic(),
+//                start as GuidingCenter if adiabatic;
+//   first == 0 : consume the status the advance kernels left (Adiabatic / NonAdiabatic raised after a
+//                completed row, Particle.py:308-309, GuidingCenter.py:457-458), apply the
+//                Particle->GuidingCenter or GuidingCenter->Particle transform (Adaptive.py:208-221),
+//                open the new segment (its first row is always stored) and update Adaptive.advance's
+//                loop variable t = current.tcur (Adaptive.py:222).
+// Then every tracer that still has t < delta is appended to the work list of its mode: warp ballot ->
+// per-warp counts -> block-level scan in shared memory -> one atomicAdd per block and mode.  The next
+// epoch's kernels therefore see tracers regrouped by mode, finished ones dropped.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256) k_adaptive_switch(const AdaptArgs a)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int want = -1;                                       // -1 idle/finished, 0 particle list, 1 GC list
+    if (i < a.n) {
+        const double mass = a.mass[i], q = a.charge[i];
+        int mode, st, nseg;
+        bool newseg = false;
+        double prow[7], grow[5], mu = 0, v = 0;
+        if (a.first) {
+            // Particle.__init__ :106-108
+            const double vx = a.vx0[i], vy = a.vy0[i], vz = a.vz0[i];
+            const double gamma = 1 / sqrt(1 - dot3(vx, vy, vz, vx, vy, vz) / (RAPT_C_LIGHT * RAPT_C_LIGHT));
+            prow[0] = a.t0[i]; prow[1] = a.x0[i]; prow[2] = a.y0[i]; prow[3] = a.z0[i];
+            prow[4] = mass * gamma * vx; prow[5] = mass * gamma * vy; prow[6] = mass * gamma * vz;
+            const double yy[6] = {prow[1], prow[2], prow[3], prow[4], prow[5], prow[6]};
+            st = RAPT_ST_OK; nseg = 1; newseg = true;
+            a.nstored[i] = 0; a.tvar[i] = 0; a.tcur[i] = prow[0];
+            if (particle_isadiabatic<F>(a.f, a.p, prow[0], yy, mass, q)) {
+                int rc = switch_p2g<F>(a.f, prow, mass, q, grow, mu, v);
+                mode = 1;
+                if (rc) st = rc;
+            } else mode = 0;
+        } else {
+            mode = a.mode[i]; st = a.status[i]; nseg = a.nseg[i];
+            if (st == RAPT_ST_ADIABATIC && mode == 0) {          // Adaptive.py:215-221
+                prow[0] = a.pt[i]; prow[1] = a.px[i]; prow[2] = a.py[i]; prow[3] = a.pz[i];
+                prow[4] = a.ppx[i]; prow[5] = a.ppy[i]; prow[6] = a.ppz[i];
+                int rc = switch_p2g<F>(a.f, prow, mass, q, grow, mu, v);
+                mode = 1; nseg++; newseg = true;
+                st = rc ? rc : RAPT_ST_OK;
+                a.tcur[i] = grow[0];                               // GuidingCenter.__init__: tcur = t0
+            } else if (st == RAPT_ST_NONADIABATIC && mode == 1) {  // Adaptive.py:208-214
+                grow[0] = a.gt[i]; grow[1] = a.gx[i]; grow[2] = a.gy[i]; grow[3] = a.gz[i]; grow[4] = a.gpp[i];
+                switch_g2p<F>(a.f, grow, a.mu[i], mass, q, 0.0 /* Particle().tcur, quirk Q12 */, prow);
+                mode = 0; nseg++; newseg = true;
+                st = RAPT_ST_OK;
+                a.tcur[i] = prow[0];                               // Particle.__init__: tcur = t0
+            }
+        }
+        if (newseg && st == RAPT_ST_OK) {
+            const int tag = 2 * (nseg - 1) + mode;
+            a.segtag[i] = tag;
+            int nst = a.nstored[i];
+            if (mode == 0) {
+                a.pt[i] = prow[0]; a.px[i] = prow[1]; a.py[i] = prow[2]; a.pz[i] = prow[3];
+                a.ppx[i] = prow[4]; a.ppy[i] = prow[5]; a.ppz[i] = prow[6];
+                if (a.rows && nst < a.max_rows) {
+                    double *r = a.rows + ((size_t)i * a.max_rows + nst) * 8;
+                    for (int k = 0; k < 7; k++) r[k] = prow[k];
+                    r[7] = (double)tag;
+                    a.nstored[i] = nst + 1;
+                }
+            } else {
+                a.gt[i] = grow[0]; a.gx[i] = grow[1]; a.gy[i] = grow[2]; a.gz[i] = grow[3]; a.gpp[i] = grow[4];
+                a.mu[i] = mu; a.v[i] = v;
+                if (a.rows && nst < a.max_rows) {
+                    double *r = a.rows + ((size_t)i * a.max_rows + nst) * 8;
+                    for (int k = 0; k < 5; k++) r[k] = grow[k];
+                    r[5] = mu; r[6] = 0; r[7] = (double)tag;
+                    a.nstored[i] = nst + 1;
+                }
+            }
+        }
+        a.mode[i] = mode; a.nseg[i] = nseg; a.status[i] = st;
+        // Adaptive.py:205,222 : t = current.tcur ; loop while t < delta (absolute tcur vs duration, quirk Q14)
+        double tv = a.first ? 0.0 : a.tcur[i];
+        a.tvar[i] = tv;
+        a.rem[i] = a.delta - tv;
+        if (st == RAPT_ST_OK && tv < a.delta) want = mode;
+    }
+    // ---- regroup by mode: ballot + shared-memory scan + one atomic per block and mode
+    __shared__ int wcount[2][8];
+    __shared__ int wbase[2][8];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned mP = __ballot_sync(0xffffffffu, want == 0), mG = __ballot_sync(0xffffffffu, want == 1);
+    if (lane == 0) { wcount[0][warp] = __popc(mP); wcount[1][warp] = __popc(mG); }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        int tot = 0;
+        for (int w = 0; w < 8; w++) { wbase[threadIdx.x][w] = tot; tot += wcount[threadIdx.x][w]; }
+        int base = tot ? atomicAdd(a.counts + threadIdx.x, tot) : 0;
+        for (int w = 0; w < 8; w++) wbase[threadIdx.x][w] += base;
+    }
+    __syncthreads();
+    const unsigned below = (1u << lane) - 1;
+    if (want == 0) a.listP[wbase[0][warp] + __popc(mP & below)] = (int)i;
+    if (want == 1) a.listG[wbase[1][warp] + __popc(mG & below)] = (int)i;
 }
 
 }  // namespace RAPT_NS

@@ -31,7 +31,7 @@ RAPT_DEV void mag_and_unit(const FieldP &f, double t, double x, double y, double
 #if RAPT_STRICT
     ux = bx / m; uy = by / m; uz = bz / m;
 #else
-    double im = 1.0 / m;
+    double im = fast_rcp(m);
     ux = bx * im; uy = by * im; uz = bz * im;
 #endif
 }

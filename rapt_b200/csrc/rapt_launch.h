@@ -13,6 +13,7 @@
     cudaError_t launch_field_ops(const void *args, cudaStream_t s);                       \
     cudaError_t launch_misc(const void *args, cudaStream_t s);                            \
     cudaError_t launch_bounce(const void *args, cudaStream_t s);                          \
+    cudaError_t launch_adaptive_switch(const void *args, cudaStream_t s);                 \
     }
 RAPT_DECLARE_FLAVOUR(rapt_fast)
 RAPT_DECLARE_FLAVOUR(rapt_strict)

@@ -37,7 +37,7 @@ RAPT_DEV void particle_rhs(const FieldP &f, double q, double mass, double &gm, d
     if (!f.is_static) {
         gm = sqrt(mass * mass + dot3(Y[3], Y[4], Y[5], Y[3], Y[4], Y[5]) / (RAPT_C_LIGHT * RAPT_C_LIGHT));
 #if !RAPT_STRICT
-        igm = 1.0 / gm;
+        igm = fast_rcp(gm);
 #endif
     }
     F::B(f, t, Y[0], Y[1], Y[2], bx, by, bz);
@@ -85,16 +85,16 @@ RAPT_DEV bool particle_isadiabatic(const FieldP &f, const ParamsP &p, double t, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// The kernel.  Flat per-lane loop, ONE right-hand-side evaluation per iteration; a small state
-// machine says what the evaluation is for (k1 of a fresh particle, HINIT's Euler probe, stage 2..12,
-// or the FSAL evaluation after an accepted step).  Two reasons for this shape:
-//   * the hot loop body stays ~20 KB of SASS, inside the 32 KB L1.5 instruction cache (the fully
-//     unrolled 12-stage step was 53 KB and stalled on instruction fetch, profiles/r1_particle_v1),
-//   * lanes in different stages / rows / particles still run the field evaluation together.
-// All k-vectors are indexed statically inside their case so they live in registers.
+// The kernel.  Flat per-lane loop whose body is exactly ONE step attempt, so lanes that sit in
+// different rows / particles still execute the stage arithmetic and field evaluations together.
+// Inside the body the 13 right-hand-side evaluations (HINIT's Euler probe for lanes that start a row,
+// stages 2..12, the FSAL evaluation for lanes that accepted) go through ONE copy of the field code in
+// a warp-uniform, non-unrolled stage loop: the hot loop is ~25 KB of SASS and stays inside the 32 KB
+// L1.5 instruction cache.  (v1 inlined 13 copies, 53 KB, and stalled on instruction fetch; v2 ran one
+// evaluation per iteration with a per-lane stage and serialised the stage arithmetic across lanes --
+// profiles/r1_particle_history.md.)  All k-vectors are indexed statically inside their case so they
+// live in registers.
 // ---------------------------------------------------------------------------------------------
-enum { PS_FETCH = 0, PS_K1, PS_HINIT, PS_2, PS_3, PS_4, PS_5, PS_6, PS_7, PS_8, PS_9, PS_10, PS_11, PS_12, PS_FSAL };
-
 #if RAPT_STRICT
 #define RAPT_POW(x, e) pow((x), (e))
 #else
@@ -102,10 +102,10 @@ enum { PS_FETCH = 0, PS_K1, PS_HINIT, PS_2, PS_3, PS_4, PS_5, PS_6, PS_7, PS_8, 
 #define RAPT_POW(x, e) exp((e) * log(x))
 #endif
 
-#define D8_NEXT(NEXTSTAGE, CC, EXPR)                                                \
+#define D8_PREP(CC, EXPR)                                                           \
     {                                                                               \
         _Pragma("unroll") for (int i = 0; i < 6; i++) yin[i] = y[i] + h * (EXPR);   \
-        tin = x + (CC) * h; stage = NEXTSTAGE;                                      \
+        tin = x + (CC) * h;                                                         \
     }
 #define D8_SAVE(K) { _Pragma("unroll") for (int i = 0; i < 6; i++) K[i] = kout[i]; }
 
@@ -119,31 +119,33 @@ __global__ void __launch_bounds__(128, 2) k_particle_dop853(const AdvArgs a)
     const double pf0 = pow(1e-4, beta);          // facold^beta at the first step of every row
 
     double y[6], k1[6], k2[6], k3[6], k4[6], k5[6], k6[6], k7[6], k8[6], k9[6], k10[6], yin[6], kout[6];
-    double x = 0, h = 0, xend = 0, label = 0, tstop = 0, dt = 0, facold = 1e-4, hmax = 0, tin = 0, dnf = 0;
+    double x = 0, h = 0, xend = 0, label = 0, tstop = 0, dt = 0, facold = 1e-4, hmax = 0, tin = 0, dnf = 0, hnew = 0;
     double mass = 0, q = 0, gm = 1, igm = 1;
-    int pid = -1, stage = PS_FETCH;
+    int pid = -1;
     int nstep = 0, naccpt = 0, nrejct = 0, ncalls = 0, nstep_row = 0, naccpt_row = 0;
     int rowidx = 0, nst = 0, st = ST_OK;
-    bool last = false, reject = false;
+    bool last = false, reject = false, need_row = false, have = false;
     double *myrows = nullptr;
 #if !RAPT_STRICT
     double isk[6];
 #endif
 
     for (;;) {
-        if (stage == PS_FETCH) {
-            if (pid >= 0) {      // write back the finished particle
-                a.t[pid] = label; a.s1[pid] = y[0]; a.s2[pid] = y[1]; a.s3[pid] = y[2];
-                a.s4[pid] = y[3]; a.s5[pid] = y[4]; a.s6[pid] = y[5];
-                int *c = a.counters + 4 * (long long)pid;
-                int nf = 2 * ncalls + 11 * nstep + naccpt;       // as scipy counts: SURVEY.md §3.1
-                if (a.append) { c[0] += nf; c[1] += nstep; c[2] += naccpt; c[3] += nrejct; }
-                else { c[0] = nf; c[1] = nstep; c[2] = naccpt; c[3] = nrejct; }
-                a.status[pid] = st;
-                a.tcur[pid] = x + dt;                            // Particle.py:306
-                if (a.nrows) a.nrows[pid] = rowidx + 1;
-                a.nstored[pid] = nst;
-            }
+        // ---- (A) particle finished?  write it back and fetch the next one
+        if (have && need_row && !(st == ST_OK && x < tstop)) {
+            a.t[pid] = label; a.s1[pid] = y[0]; a.s2[pid] = y[1]; a.s3[pid] = y[2];
+            a.s4[pid] = y[3]; a.s5[pid] = y[4]; a.s6[pid] = y[5];
+            int *c = a.counters + 4 * (long long)pid;
+            int nf = 2 * ncalls + 11 * nstep + naccpt;       // as scipy counts: SURVEY.md §3.1
+            if (a.append) { c[0] += nf; c[1] += nstep; c[2] += naccpt; c[3] += nrejct; }
+            else { c[0] = nf; c[1] = nstep; c[2] = naccpt; c[3] = nrejct; }
+            a.status[pid] = st;
+            a.tcur[pid] = x + dt;                            // Particle.py:306
+            if (a.nrows) a.nrows[pid] = rowidx + 1;
+            a.nstored[pid] = nst;
+            have = false;
+        }
+        if (!have) {
             int w = atomicAdd(a.queue, 1);
             if (w >= a.nwork) break;
             pid = a.order ? a.order[w] : w;
@@ -176,188 +178,205 @@ __global__ void __launch_bounds__(128, 2) k_particle_dop853(const AdvArgs a)
                     nst = 1;
                 }
             }
-            if (!(x < tstop)) { stage = PS_FETCH; continue; }    // delta <= 0: nothing to do
-            tin = x;
-#pragma unroll
-            for (int i = 0; i < 6; i++) yin[i] = y[i];
-            stage = PS_K1;
+            have = true; need_row = true;
+            if (!(x < tstop)) continue;                      // delta <= 0: nothing to do
+            particle_rhs<F>(a.f, q, mass, gm, igm, eqf, x, y, k1);           // k1 = f(x, y)
         }
-
-        particle_rhs<F>(a.f, q, mass, gm, igm, eqf, tin, yin, kout);
-
-        bool row_start = false, begin_step = false;
-        switch (stage) {
-        case PS_K1:
-            D8_SAVE(k1)
-            row_start = true;
-            break;
-        case PS_HINIT: {
-            double der2 = 0;
+        // ---- (B) one step attempt; stage 1 = HINIT for lanes that start an output row
+        bool accepted = false, skip = false;
+#pragma unroll 1
+        for (int s = 1; s <= 13; s++) {
+            bool active = !skip;
+            switch (s) {
+            case 1:
+                active = need_row;
+                if (active) {
+                    // new output row = new solver call: xend, HINIT part 1
+                    xend = x + dt; label = xend;             // Particle.py:305
+                    hmax = fabs(xend - x);
+                    double dny = 0;
+                    dnf = 0;
 #pragma unroll
-            for (int i = 0; i < 6; i++) {
+                    for (int i = 0; i < 6; i++) {
 #if RAPT_STRICT
-                double sk = atol + rtol * fabs(y[i]);
-                der2 += ((kout[i] - k1[i]) / sk) * ((kout[i] - k1[i]) / sk);
+                        double sk = atol + rtol * fabs(y[i]);
+                        dnf += (k1[i] / sk) * (k1[i] / sk);
+                        dny += (y[i] / sk) * (y[i] / sk);
 #else
-                double d_ = (kout[i] - k1[i]) * isk[i];
-                der2 += d_ * d_;
+                        isk[i] = fast_rcp(atol + rtol * fabs(y[i]));
+                        double a_ = k1[i] * isk[i], b_ = y[i] * isk[i];
+                        dnf += a_ * a_; dny += b_ * b_;
 #endif
-            }
-            der2 = sqrt(der2) / h;
-            double der12 = fmax(fabs(der2), sqrt(dnf));
-            // h1 = (0.01/der12)^(1/8) only matters when it is the smallest of the three candidates;
-            // h1 >= hmax  <=>  0.01/der12 >= hmax^8 (monotone), decided without the pow unless close.
-            double h1;
-            if (der12 <= 1e-15) h1 = fmax(1e-6, fabs(h) * 1e-3);
-            else {
-                double tq = 0.01 / der12, hm2 = hmax * hmax, hm4 = hm2 * hm2;
-                if (tq > hm4 * hm4 * 1.000001) h1 = hmax;
-                else h1 = pow(tq, 1.0 / 8.0);
-            }
-            h = fmin(fmin(100 * fabs(h), h1), hmax);
-            facold = 1e-4; last = false; reject = false; nstep_row = 0; naccpt_row = 0;
-            ncalls++;
-            begin_step = true;
-            break; }
-        case PS_2: D8_SAVE(k2) D8_NEXT(PS_3, T8(C3), T8(A3_1) * k1[i] + T8(A3_2) * k2[i]) break;
-        case PS_3: D8_SAVE(k3) D8_NEXT(PS_4, T8(C4), T8(A4_1) * k1[i] + T8(A4_3) * k3[i]) break;
-        case PS_4: D8_SAVE(k4) D8_NEXT(PS_5, T8(C5), T8(A5_1) * k1[i] + T8(A5_3) * k3[i] + T8(A5_4) * k4[i]) break;
-        case PS_5: D8_SAVE(k5) D8_NEXT(PS_6, T8(C6), T8(A6_1) * k1[i] + T8(A6_4) * k4[i] + T8(A6_5) * k5[i]) break;
-        case PS_6: D8_SAVE(k6) D8_NEXT(PS_7, T8(C7), T8(A7_1) * k1[i] + T8(A7_4) * k4[i] + T8(A7_5) * k5[i] + T8(A7_6) * k6[i]) break;
-        case PS_7: D8_SAVE(k7) D8_NEXT(PS_8, T8(C8), T8(A8_1) * k1[i] + T8(A8_4) * k4[i] + T8(A8_5) * k5[i] + T8(A8_6) * k6[i] + T8(A8_7) * k7[i]) break;
-        case PS_8: D8_SAVE(k8) D8_NEXT(PS_9, T8(C9), T8(A9_1) * k1[i] + T8(A9_4) * k4[i] + T8(A9_5) * k5[i] + T8(A9_6) * k6[i] + T8(A9_7) * k7[i] + T8(A9_8) * k8[i]) break;
-        case PS_9: D8_SAVE(k9) D8_NEXT(PS_10, T8(C10), T8(A10_1) * k1[i] + T8(A10_4) * k4[i] + T8(A10_5) * k5[i] + T8(A10_6) * k6[i] + T8(A10_7) * k7[i] + T8(A10_8) * k8[i] + T8(A10_9) * k9[i]) break;
-        case PS_10: D8_SAVE(k10) D8_NEXT(PS_11, T8(C11), T8(A11_1) * k1[i] + T8(A11_4) * k4[i] + T8(A11_5) * k5[i] + T8(A11_6) * k6[i] + T8(A11_7) * k7[i] + T8(A11_8) * k8[i] + T8(A11_9) * k9[i] + T8(A11_10) * k10[i]) break;
-        case PS_11:
-            D8_SAVE(k2)
+                    }
+                    h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
+                    h = fmin(h, hmax);
 #pragma unroll
-            for (int i = 0; i < 6; i++)
-                yin[i] = y[i] + h * (T8(A12_1) * k1[i] + T8(A12_4) * k4[i] + T8(A12_5) * k5[i] + T8(A12_6) * k6[i] + T8(A12_7) * k7[i] + T8(A12_8) * k8[i] + T8(A12_9) * k9[i] + T8(A12_10) * k10[i] + T8(A12_11) * k2[i]);
-            tin = x + h; stage = PS_12;
-            break;
-        case PS_12: {
-            D8_SAVE(k3)
-            double err = 0, err2 = 0;
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-                k4[i] = T8(B1) * k1[i] + T8(B6) * k6[i] + T8(B7) * k7[i] + T8(B8) * k8[i] + T8(B9) * k9[i] + T8(B10) * k10[i] + T8(B11) * k2[i] + T8(B12) * k3[i];
-                k5[i] = y[i] + h * k4[i];
-                double sk = atol + rtol * fmax(fabs(y[i]), fabs(k5[i]));
-                double e3 = k4[i] - T8(BHH1) * k1[i] - T8(BHH2) * k9[i] - T8(BHH3) * k3[i];
-                double e5 = T8(ER1) * k1[i] + T8(ER6) * k6[i] + T8(ER7) * k7[i] + T8(ER8) * k8[i] + T8(ER9) * k9[i] + T8(ER10) * k10[i] + T8(ER11) * k2[i] + T8(ER12) * k3[i];
-#if RAPT_STRICT
-                err2 += (e3 / sk) * (e3 / sk);
-                err += (e5 / sk) * (e5 / sk);
-#else
-                double is_ = 1.0 / sk;
-                e3 *= is_; e5 *= is_;
-                err2 += e3 * e3; err += e5 * e5;
-#endif
-            }
-            double deno = err + 0.01 * err2;
-            if (deno <= 0.0) deno = 1.0;
-            err = fabs(h) * err * sqrt(1.0 / (6 * deno));
-            if (err <= 1.0) {
-                // accepted.  The controller's new step is only consumed when the row continues.
-                if (!last) {
-                    double fac11 = RAPT_POW(err, expo1);
-                    double fac = fac11 / ((facold == 1e-4) ? pf0 : RAPT_POW(facold, beta));
-                    fac = fmax(facc2, fmin(facc1, fac / safe));
-                    double hnew = h / fac;
-                    if (fabs(hnew) > hmax) hnew = hmax;
-                    if (reject) hnew = fmin(fabs(hnew), fabs(h));
-                    dnf = hnew;                              // parked until the FSAL evaluation returns
+                    for (int i = 0; i < 6; i++) yin[i] = y[i] + h * k1[i];
+                    tin = x + h;
                 }
-                facold = fmax(err, 1e-4);
-                naccpt++; naccpt_row++;
+                break;
+            case 2:
+                // step prologue (every lane): failure checks, clip the step to the row end
+                if (nstep_row > 500) st = ST_NMAX;
+                else if (0.1 * fabs(h) <= fabs(x) * uround) st = ST_HSMALL;
+                if (st != ST_OK) {
+                    // the reference's loop ends silently on solver failure (Particle.py:304); the row is still appended
+                    rowidx++; need_row = true; skip = true; active = false;
+                } else {
+                    if ((x + 1.01 * h - xend) > 0.0) { h = xend - x; last = true; }
+                    nstep_row++; nstep++;
+#pragma unroll
+                    for (int i = 0; i < 6; i++) yin[i] = y[i] + h * T8(A2_1) * k1[i];   // Hairer's association (h*a21)*k1
+                    tin = x + T8(C2) * h;
+                }
+                break;
+            case 3: D8_PREP(T8(C3), T8(A3_1) * k1[i] + T8(A3_2) * k2[i]) break;
+            case 4: D8_PREP(T8(C4), T8(A4_1) * k1[i] + T8(A4_3) * k3[i]) break;
+            case 5: D8_PREP(T8(C5), T8(A5_1) * k1[i] + T8(A5_3) * k3[i] + T8(A5_4) * k4[i]) break;
+            case 6: D8_PREP(T8(C6), T8(A6_1) * k1[i] + T8(A6_4) * k4[i] + T8(A6_5) * k5[i]) break;
+            case 7: D8_PREP(T8(C7), T8(A7_1) * k1[i] + T8(A7_4) * k4[i] + T8(A7_5) * k5[i] + T8(A7_6) * k6[i]) break;
+            case 8: D8_PREP(T8(C8), T8(A8_1) * k1[i] + T8(A8_4) * k4[i] + T8(A8_5) * k5[i] + T8(A8_6) * k6[i] + T8(A8_7) * k7[i]) break;
+            case 9: D8_PREP(T8(C9), T8(A9_1) * k1[i] + T8(A9_4) * k4[i] + T8(A9_5) * k5[i] + T8(A9_6) * k6[i] + T8(A9_7) * k7[i] + T8(A9_8) * k8[i]) break;
+            case 10: D8_PREP(T8(C10), T8(A10_1) * k1[i] + T8(A10_4) * k4[i] + T8(A10_5) * k5[i] + T8(A10_6) * k6[i] + T8(A10_7) * k7[i] + T8(A10_8) * k8[i] + T8(A10_9) * k9[i]) break;
+            case 11: D8_PREP(T8(C11), T8(A11_1) * k1[i] + T8(A11_4) * k4[i] + T8(A11_5) * k5[i] + T8(A11_6) * k6[i] + T8(A11_7) * k7[i] + T8(A11_8) * k8[i] + T8(A11_9) * k9[i] + T8(A11_10) * k10[i]) break;
+            case 12:
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+                    yin[i] = y[i] + h * (T8(A12_1) * k1[i] + T8(A12_4) * k4[i] + T8(A12_5) * k5[i] + T8(A12_6) * k6[i] + T8(A12_7) * k7[i] + T8(A12_8) * k8[i] + T8(A12_9) * k9[i] + T8(A12_10) * k10[i] + T8(A12_11) * k2[i]);
+                tin = x + h;
+                break;
+            default:   // 13: FSAL evaluation f(x+h, ynew) for lanes whose step was accepted
+                active = accepted;
 #pragma unroll
                 for (int i = 0; i < 6; i++) yin[i] = k5[i];
-                tin = x + h; stage = PS_FSAL;
-            } else {
-                // rejected: scipy 1.18.1 shrinks by 1/facc1 whatever err is; Hairer uses the controller
-                double hnew;
-                if (a.p.dop853_reject_rule == 1) hnew = h / fmin(facc1, RAPT_POW(err, expo1) / safe);
-                else hnew = h / facc1;
-                reject = true;
-                if (naccpt_row >= 1) nrejct++;
-                last = false;
-                h = hnew;
-                begin_step = true;
+                tin = x + h;
+                break;
             }
-            break; }
-        case PS_FSAL:
-            D8_SAVE(k1)                                      // k1 = f(x+h, ynew)
-#pragma unroll
-            for (int i = 0; i < 6; i++) y[i] = k5[i];
-            x = x + h;
-            if (last) {
-                // ---- output row complete (Particle.py:305-309)
-                rowidx++;
-                if (myrows && a.store_every > 0 && (rowidx % a.store_every) == 0 && nst < a.max_rows) {
-                    double2 *r = reinterpret_cast<double2 *>(myrows + (size_t)nst * 8);
-                    double tag = a.segtag ? (double)a.segtag[pid] : (double)nstep;
-                    r[0] = make_double2(label, y[0]); r[1] = make_double2(y[1], y[2]);
-                    r[2] = make_double2(y[3], y[4]); r[3] = make_double2(y[5], tag);
-                    nst++;
-                }
-                if (a.p.check_adiabaticity) {
-                    if (particle_isadiabatic<F>(a.f, a.p, label, y, mass, q)) st = ST_ADIABATIC;
-                }
-                if (st == ST_OK && x < tstop) row_start = true;
-                else stage = PS_FETCH;
-            } else {
-                h = dnf;
-                reject = false;
-                begin_step = true;
-            }
-            break;
-        default: break;
-        }
 
-        if (row_start) {
-            // new output row = new solver call: xend, HINIT part 1
-            xend = x + dt; label = xend;                     // Particle.py:305
-            hmax = fabs(xend - x);
-            double dny = 0;
-            dnf = 0;
+            if (active) particle_rhs<F>(a.f, q, mass, gm, igm, eqf, tin, yin, kout);
+
+            switch (s) {
+            case 1:
+                if (active) {
+                    double der2 = 0;
 #pragma unroll
-            for (int i = 0; i < 6; i++) {
+                    for (int i = 0; i < 6; i++) {
 #if RAPT_STRICT
-                double sk = atol + rtol * fabs(y[i]);
-                dnf += (k1[i] / sk) * (k1[i] / sk);
-                dny += (y[i] / sk) * (y[i] / sk);
+                        double sk = atol + rtol * fabs(y[i]);
+                        der2 += ((kout[i] - k1[i]) / sk) * ((kout[i] - k1[i]) / sk);
 #else
-                isk[i] = 1.0 / (atol + rtol * fabs(y[i]));
-                double a_ = k1[i] * isk[i], b_ = y[i] * isk[i];
-                dnf += a_ * a_; dny += b_ * b_;
+                        double d_ = (kout[i] - k1[i]) * isk[i];
+                        der2 += d_ * d_;
 #endif
-            }
-            h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
-            h = fmin(h, hmax);
+                    }
+                    der2 = sqrt(der2) / h;
+                    double der12 = fmax(fabs(der2), sqrt(dnf));
+                    // h1 = (0.01/der12)^(1/8) only matters when it is the smallest of the three candidates;
+                    // h1 >= hmax  <=>  0.01/der12 >= hmax^8 (monotone), decided without the pow unless close.
+                    double h1;
+                    if (der12 <= 1e-15) h1 = fmax(1e-6, fabs(h) * 1e-3);
+                    else {
+                        double tq = 0.01 / der12, hm2 = hmax * hmax, hm4 = hm2 * hm2;
+                        if (tq > hm4 * hm4 * 1.000001) h1 = hmax;
+                        else h1 = pow(tq, 1.0 / 8.0);
+                    }
+                    h = fmin(fmin(100 * fabs(h), h1), hmax);
+                    facold = 1e-4; last = false; reject = false; nstep_row = 0; naccpt_row = 0;
+                    ncalls++;
+                    need_row = false;
+                }
+                break;
+            case 2: if (active) D8_SAVE(k2) break;
+            case 3: if (active) D8_SAVE(k3) break;
+            case 4: if (active) D8_SAVE(k4) break;
+            case 5: if (active) D8_SAVE(k5) break;
+            case 6: if (active) D8_SAVE(k6) break;
+            case 7: if (active) D8_SAVE(k7) break;
+            case 8: if (active) D8_SAVE(k8) break;
+            case 9: if (active) D8_SAVE(k9) break;
+            case 10: if (active) D8_SAVE(k10) break;
+            case 11: if (active) D8_SAVE(k2) break;
+            case 12:
+                if (active) {
+                    D8_SAVE(k3)
+                    double err = 0, err2 = 0;
 #pragma unroll
-            for (int i = 0; i < 6; i++) yin[i] = y[i] + h * k1[i];
-            tin = x + h;
-            stage = PS_HINIT;
-        }
-        if (begin_step) {
-            if (nstep_row > 500) st = ST_NMAX;
-            else if (0.1 * fabs(h) <= fabs(x) * uround) st = ST_HSMALL;
-            if (st != ST_OK) {
-                // the reference's loop ends silently on solver failure (Particle.py:304); the row is still appended
-                rowidx++;
-                stage = PS_FETCH;
-                continue;
-            }
-            if ((x + 1.01 * h - xend) > 0.0) { h = xend - x; last = true; }
-            nstep_row++; nstep++;
+                    for (int i = 0; i < 6; i++) {
+                        k4[i] = T8(B1) * k1[i] + T8(B6) * k6[i] + T8(B7) * k7[i] + T8(B8) * k8[i] + T8(B9) * k9[i] + T8(B10) * k10[i] + T8(B11) * k2[i] + T8(B12) * k3[i];
+                        k5[i] = y[i] + h * k4[i];
+                        double sk = atol + rtol * fmax(fabs(y[i]), fabs(k5[i]));
+                        double e3 = k4[i] - T8(BHH1) * k1[i] - T8(BHH2) * k9[i] - T8(BHH3) * k3[i];
+                        double e5 = T8(ER1) * k1[i] + T8(ER6) * k6[i] + T8(ER7) * k7[i] + T8(ER8) * k8[i] + T8(ER9) * k9[i] + T8(ER10) * k10[i] + T8(ER11) * k2[i] + T8(ER12) * k3[i];
+#if RAPT_STRICT
+                        err2 += (e3 / sk) * (e3 / sk);
+                        err += (e5 / sk) * (e5 / sk);
+#else
+                        double is_ = fast_rcp(sk);
+                        e3 *= is_; e5 *= is_;
+                        err2 += e3 * e3; err += e5 * e5;
+#endif
+                    }
+                    double deno = err + 0.01 * err2;
+                    if (deno <= 0.0) deno = 1.0;
+#if RAPT_STRICT
+                    err = fabs(h) * err * sqrt(1.0 / (6 * deno));
+#else
+                    err = fabs(h) * err * fast_rsqrt(6 * deno);
+#endif
+                    if (err <= 1.0) {
+                        // accepted.  The controller's new step is only consumed when the row continues.
+                        if (!last) {
+                            double fac11 = RAPT_POW(err, expo1);
+                            double fac = fac11 / ((facold == 1e-4) ? pf0 : RAPT_POW(facold, beta));
+                            fac = fmax(facc2, fmin(facc1, fac / safe));
+                            hnew = h / fac;
+                            if (fabs(hnew) > hmax) hnew = hmax;
+                            if (reject) hnew = fmin(fabs(hnew), fabs(h));
+                        }
+                        facold = fmax(err, 1e-4);
+                        naccpt++; naccpt_row++;
+                        accepted = true;
+                    } else {
+                        // rejected: scipy 1.18.1 shrinks by 1/facc1 whatever err is; Hairer uses the controller
+                        if (a.p.dop853_reject_rule == 1) h = h / fmin(facc1, RAPT_POW(err, expo1) / safe);
+                        else h = h / facc1;
+                        reject = true;
+                        if (naccpt_row >= 1) nrejct++;
+                        last = false;
+                    }
+                }
+                break;
+            default:
+                if (active) {
+                    D8_SAVE(k1)                              // k1 = f(x+h, ynew)
 #pragma unroll
-            for (int i = 0; i < 6; i++) yin[i] = y[i] + h * T8(A2_1) * k1[i];     // Hairer's association (h*a21)*k1
-            tin = x + T8(C2) * h;
-            stage = PS_2;
+                    for (int i = 0; i < 6; i++) y[i] = k5[i];
+                    x = x + h;
+                    if (last) {
+                        // ---- output row complete (Particle.py:305-309)
+                        rowidx++;
+                        if (myrows && a.store_every > 0 && (rowidx % a.store_every) == 0 && nst < a.max_rows) {
+                            double2 *r = reinterpret_cast<double2 *>(myrows + (size_t)nst * 8);
+                            double tag = a.segtag ? (double)a.segtag[pid] : (double)nstep;
+                            r[0] = make_double2(label, y[0]); r[1] = make_double2(y[1], y[2]);
+                            r[2] = make_double2(y[3], y[4]); r[3] = make_double2(y[5], tag);
+                            nst++;
+                        }
+                        if (a.p.check_adiabaticity) {
+                            if (particle_isadiabatic<F>(a.f, a.p, label, y, mass, q)) st = ST_ADIABATIC;
+                        }
+                        need_row = true;
+                    } else {
+                        h = hnew;
+                        reject = false;
+                    }
+                }
+                break;
+            }
         }
     }
 }
-#undef D8_NEXT
+#undef D8_PREP
 #undef D8_SAVE
 
 }  // namespace RAPT_NS

@@ -66,11 +66,29 @@ struct BounceArgs {
     FieldP f;
     double flres;
     long long n, max_pts;
-    const double *t, *x, *y, *z, *ppar, *mu, *mass;
+    const double *t, *x, *y, *z, *ppar, *mu, *mass;   // mu == NULL: Bm[] is an INPUT (plain Fieldline trace)
     double *Bm, *v, *ds;
     int *npts;
     double *curve;            // [n][max_pts][5] : s, x, y, z, |B|
     double *scratch;          // [n][max_pts][4] : backward half before reversal
+};
+
+// Adaptive: per-tracer state of both modes + the epoch bookkeeping (rapt/Adaptive.py:70-104, 187-222)
+struct AdaptArgs {
+    FieldP f;
+    ParamsP p;
+    long long n;
+    int first;                         // 1: Adaptive.__init__ (initial mode choice), 0: after an epoch
+    double delta;
+    const double *x0, *y0, *z0, *vx0, *vy0, *vz0, *t0;   // constructor arguments (first == 1)
+    const double *mass, *charge;
+    double *pt, *px, *py, *pz, *ppx, *ppy, *ppz;        // Particle-mode state (last row)
+    double *gt, *gx, *gy, *gz, *gpp, *mu, *v;           // GuidingCenter-mode state (last row), mu, speed
+    int *mode, *status, *nseg, *segtag, *nstored;
+    double *tvar, *rem, *tcur;                          // Adaptive.advance's `t`, delta - t, current.tcur
+    long long max_rows;
+    double *rows;
+    int *listP, *listG, *counts;                        // compacted work lists by mode; counts[0..1]
 };
 
 }  // namespace rapt

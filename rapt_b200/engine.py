@@ -180,6 +180,24 @@ def bounce_setup(field, state, mu, mass, fieldlineresolution=None, arith="strict
         max_pts = int(2 ** math.ceil(math.log2(npts.max() + 1)))
 
 
+def fieldline_trace(field, tpos, Bm, fieldlineresolution=None, arith="strict", max_pts=256):
+    """Fieldline(tpos, field, Bmax=Bm).trace() (fieldline.py:13-105) on the device for one start point.
+    Returns dict(curve (k,5): s,x,y,z,|B| ; ds)."""
+    from . import params as gp
+    f = _field_desc(field)
+    flr = float(gp["fieldlineresolution"] if fieldlineresolution is None else fieldlineresolution)
+    tpos = np.asarray(tpos, dtype=np.float64)
+    cols = [np.array([tpos[i]]) for i in range(4)]
+    while True:
+        Bm_a = np.array([float(Bm)]); ds = np.zeros(1); npts = np.zeros(1, np.int32); curve = np.empty((1, max_pts, 5))
+        check(_lib.load().rapt_b200_bounce_setup(C.byref(f), C.c_int(1 if arith in ("strict", 1) else 0), C.c_double(flr),
+                                                 C.c_int64(1), *[ptr(c_) for c_ in cols], None, None, None,
+                                                 ptr(Bm_a), None, ptr(ds), ptr(npts), C.c_int64(max_pts), ptr(curve)))
+        if npts[0] <= max_pts:
+            return dict(curve=curve[0, :npts[0]].copy(), ds=float(ds[0]))
+        max_pts *= 4
+
+
 def halfbouncepath_from_curve(s, b, Bm):
     """flutils.halfbouncepath (flutils.py:274-316) on a traced curve.  The non-equatorial branch uses
     scipy's quadratic spline / brentq / QUADPACK exactly as the reference does (third-party there too)."""

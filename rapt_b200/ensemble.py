@@ -1,0 +1,243 @@
+"""Ensemble entry points: millions of independent tracers per call (no reference counterpart; the
+reference advances one Python object at a time).
+
+Each class mirrors the constructor of its single-tracer namesake with array arguments and exposes
+`advance(delta)`.  State can live on the host (numpy; every `advance` copies in and out through the
+host-pointer C ABI) or on the device (`.cuda()`: torch CUDA tensors updated in place through the
+device-pointer C ABI, no host traffic) -- the latter is what large runs and multi-GPU sharding use.
+"""
+import numpy as np
+
+from . import c, params
+from . import engine
+
+
+def _arr(a, n=None):
+    a = np.asarray(a, dtype=np.float64)
+    if n is not None:
+        a = np.broadcast_to(a, (n,))
+    return np.ascontiguousarray(a).copy()
+
+
+class _DeviceState:
+    """Device-resident columns (torch CUDA float64 tensors) + output scratch."""
+
+    def __init__(self, cols, extras, device):
+        import torch
+        self.device = torch.device(device)
+        self.cols = [torch.as_tensor(np.ascontiguousarray(cc), device=self.device) for cc in cols]
+        self.extras = {k: torch.as_tensor(np.ascontiguousarray(v), device=self.device) for k, v in extras.items()}
+        self.out = engine.alloc_outputs(self.cols[0].numel(), self.device)
+        self.rows = None
+
+
+class ParticleEnsemble:
+    """n full-orbit tracers: Particle(pos, vel, t0, mass, charge, field) with array arguments
+    (reference constructor: rapt/Particle.py:59-109).
+
+    pos, vel: (n,3); t0, mass, charge: scalars or (n,).  `state` is (n,7): t,x,y,z,px,py,pz.
+    """
+
+    def __init__(self, pos, vel, t0=0.0, mass=None, charge=None, field=None):
+        pos = np.asarray(pos, dtype=np.float64).reshape(-1, 3)
+        vel = np.asarray(vel, dtype=np.float64).reshape(-1, 3)
+        n = len(pos)
+        self.n = n
+        self.mass = _arr(mass, n); self.charge = _arr(charge, n)
+        self.field = field
+        mom = engine.particle_momentum(vel, self.mass)               # Particle.py:106-107
+        self.state = np.column_stack([_arr(t0, n), pos, mom])
+        self.tcur = self.state[:, 0].copy()
+        self.dt = np.zeros(n)
+        self.counters = np.zeros((n, 4), dtype=np.int64)             # cumulative (nfcn, nstep, naccpt, nrejct)
+        self.status = np.ones(n, dtype=np.int32)
+        self.nrows = np.ones(n, dtype=np.int64)
+        self.trajectory = None                                       # (n, max_rows, 8) of the last advance()
+        self.nstored = None
+        self.check_adiabaticity = False
+        self._dev = None
+
+    # ---- residency
+    def cuda(self, device="cuda:0"):
+        self._dev = _DeviceState([self.state[:, i] for i in range(7)], dict(mass=self.mass, charge=self.charge), device)
+        return self
+
+    def cpu(self):
+        if self._dev is not None:
+            import torch
+            torch.cuda.synchronize(self._dev.device)
+            self.state = np.column_stack([cc.cpu().numpy() for cc in self._dev.cols])
+            self._pull_outputs()
+            self._dev = None
+        return self
+
+    def _pull_outputs(self):
+        o = self._dev.out
+        self.status = o["status"].cpu().numpy()
+        self.tcur = o["tcur"].cpu().numpy()
+        self.dt = o["dt"].cpu().numpy()
+        self.last_counters = o["counters"].cpu().numpy().astype(np.int64)
+        self.nrows = o["nrows"].cpu().numpy().astype(np.int64)
+
+    # ---- the hot path
+    def advance(self, delta, store_every=0, max_rows=0, **over):
+        """Particle.advance(delta) for every member (rapt/Particle.py:230-309).
+        store_every = k keeps every k-th output row (0: final state only) in `trajectory`."""
+        if self._dev is not None:
+            import torch
+            d = self._dev
+            if store_every > 0 and max_rows > 0:
+                if d.rows is None or tuple(d.rows.shape) != (self.n, max_rows, 8):
+                    d.rows = torch.empty((self.n, max_rows, 8), dtype=torch.float64, device=d.device)
+            engine.particle_advance_dev(self.field, d.cols, d.extras["mass"], d.extras["charge"], float(delta), d.out,
+                                        store_every=store_every, max_rows=max_rows,
+                                        rows=d.rows if store_every > 0 and max_rows > 0 else None,
+                                        check_adiabaticity=self.check_adiabaticity, **over)
+            return self
+        o = engine.particle_advance(self.field, self.state, self.mass, self.charge, float(delta), store_every=store_every,
+                                    max_rows=max_rows, check_adiabaticity=self.check_adiabaticity, **over)
+        self.state = o["state"]; self.tcur = o["tcur"]; self.dt = o["dt"]; self.status = o["status"]
+        self.last_counters = o["counters"].astype(np.int64)
+        self.counters += self.last_counters
+        self.nrows = o["nrows"].astype(np.int64)
+        self.trajectory = o["rows"]; self.nstored = o["nstored"]
+        return self
+
+    def member_trajectory(self, i):
+        """(rows, 7) trajectory array of member i from the last advance(), as Particle.trajectory."""
+        return self.trajectory[i, :self.nstored[i], :7]
+
+    # ---- diagnostics (host)
+    def getke(self):
+        """Kinetic energy (J) of every member at its current state (Particle.getke, Particle.py:442-454)."""
+        p2 = np.sum(self.state[:, 4:7] ** 2, axis=1)
+        g = np.sqrt(1 + p2 / (self.mass * c) ** 2)
+        return np.where(g - 1 < 1e-6, 0.5 * p2 / self.mass, (g - 1) * self.mass * c * c)
+
+
+class GuidingCenterEnsemble:
+    """n guiding centres: GuidingCenter(pos, v, pa, ppar, t0, mass, charge, field) with array arguments
+    (reference constructor: rapt/GuidingCenter.py:63-133).  `state` is (n,5): t,X,Y,Z,p_parallel."""
+
+    def __init__(self, pos, v, pa=None, ppar=None, t0=0.0, mass=None, charge=None, field=None):
+        pos = np.asarray(pos, dtype=np.float64).reshape(-1, 3)
+        n = len(pos)
+        self.n = n
+        self.v = _arr(v, n); self.mass = _arr(mass, n); self.charge = _arr(charge, n)
+        self.field = field
+        t0 = _arr(t0, n)
+        if pa is not None:
+            pp, mu = engine.gc_construct(field, t0, pos, self.v, _arr(pa, n), self.mass)
+        else:
+            # ppar given: mu from utils.magnetic_moment (GuidingCenter.py:129) via pitch angle of (ppar, v)
+            g = 1 / np.sqrt(1 - (self.v / c) ** 2)
+            pp = _arr(ppar, n)
+            Bm = engine.field_ops(field, np.column_stack([t0, pos]), which=["magB"])["magB"]
+            vpar = pp / (self.mass * g)
+            mu = g ** 2 * self.mass * (self.v - vpar) * (self.v + vpar) / (2 * Bm)
+        self.mu = mu
+        self.state = np.column_stack([t0, pos, pp])
+        self.tcur = t0.copy()
+        self.counters = np.zeros((n, 4), dtype=np.int64)
+        self.status = np.ones(n, dtype=np.int32)
+        self.nrows = np.ones(n, dtype=np.int64)
+        self.trajectory = None; self.nstored = None
+        self.check_adiabaticity = False
+        self._dev = None
+
+    def bounceperiod(self):
+        """GuidingCenter.bounceperiod of every member (device field-line traces + host quadrature)."""
+        return engine.bounceperiod(self.field, self.state, self.mu, self.mass, params["fieldlineresolution"])
+
+    def _dt(self):
+        if params["GCtimestep"] != 0:                                # GuidingCenter.py:443-446
+            return np.full(self.n, float(params["GCtimestep"]))
+        return self.bounceperiod() / params["bounceresolution"]
+
+    def cuda(self, device="cuda:0"):
+        self._dev = _DeviceState([self.state[:, i] for i in range(5)],
+                                 dict(mass=self.mass, charge=self.charge, mu=self.mu, v=self.v), device)
+        return self
+
+    def cpu(self):
+        if self._dev is not None:
+            import torch
+            torch.cuda.synchronize(self._dev.device)
+            self.state = np.column_stack([cc.cpu().numpy() for cc in self._dev.cols])
+            o = self._dev.out
+            self.status = o["status"].cpu().numpy(); self.tcur = o["tcur"].cpu().numpy()
+            self.last_counters = o["counters"].cpu().numpy().astype(np.int64)
+            self.nrows = o["nrows"].cpu().numpy().astype(np.int64)
+            self._dev = None
+        return self
+
+    def advance(self, delta, eom="TaoChanBrizardEOM", store_every=0, max_rows=0, dt=None, **over):
+        """GuidingCenter.advance(delta, eom) for every member (rapt/GuidingCenter.py:397-458)."""
+        dt = self._dt() if dt is None else _arr(dt, self.n)
+        if self._dev is not None:
+            import torch
+            d = self._dev
+            d.extras["dt"] = torch.as_tensor(dt, device=d.device)
+            if store_every > 0 and max_rows > 0:
+                if d.rows is None or tuple(d.rows.shape) != (self.n, max_rows, 8):
+                    d.rows = torch.empty((self.n, max_rows, 8), dtype=torch.float64, device=d.device)
+            engine.gc_advance_dev(self.field, d.cols, d.extras["mu"], d.extras["v"], d.extras["mass"], d.extras["charge"],
+                                  d.extras["dt"], float(delta), d.out, eom=eom, store_every=store_every, max_rows=max_rows,
+                                  rows=d.rows if store_every > 0 and max_rows > 0 else None,
+                                  check_adiabaticity=self.check_adiabaticity, **over)
+            return self
+        o = engine.gc_advance(self.field, self.state, self.mu, self.v, self.mass, self.charge, dt, float(delta), eom=eom,
+                              store_every=store_every, max_rows=max_rows, check_adiabaticity=self.check_adiabaticity, **over)
+        self.state = o["state"]; self.tcur = o["tcur"]; self.status = o["status"]
+        self.last_counters = o["counters"].astype(np.int64)
+        self.counters += self.last_counters
+        self.nrows = o["nrows"].astype(np.int64)
+        self.trajectory = o["rows"]; self.nstored = o["nstored"]
+        return self
+
+    def member_trajectory(self, i):
+        return self.trajectory[i, :self.nstored[i], :5]
+
+    def getke(self):
+        """Kinetic energy (J) at the current state (GuidingCenter.getke, GuidingCenter.py:574-591)."""
+        Bm = engine.field_ops(self.field, self.state[:, :4], which=["magB"])["magB"]
+        mc = self.mass * c
+        g = np.sqrt(1 + 2 * self.mu * Bm / (mc * c) + (self.state[:, 4] / mc) ** 2)
+        return np.where(g - 1 < 1e-6, self.mu * Bm + 0.5 * self.state[:, 4] ** 2 / self.mass, (g - 1) * mc * c)
+
+
+class AdaptiveEnsemble:
+    """n Adaptive tracers: Adaptive(pos, vel, t0, mass, charge, field) with array arguments
+    (rapt/Adaptive.py:70-104).  Mode switches run on the device: after every epoch a switch kernel
+    applies the Particle<->GuidingCenter transforms and regroups tracers by mode with warp ballots and
+    a shared-memory scan (rapt_b200/csrc/rapt_aux.cuh).  Needs params['GCtimestep'] != 0."""
+
+    def __init__(self, pos, vel, t0=0.0, mass=None, charge=None, field=None):
+        self.pos = np.asarray(pos, dtype=np.float64).reshape(-1, 3)
+        self.vel = np.asarray(vel, dtype=np.float64).reshape(-1, 3)
+        self.n = len(self.pos)
+        self.t0 = _arr(t0, self.n); self.mass = _arr(mass, self.n); self.charge = _arr(charge, self.n)
+        self.field = field
+        self.result = None
+
+    def advance(self, delta, store_every=1, max_rows=0, **over):
+        """Adaptive.advance(delta) for every member (rapt/Adaptive.py:187-222), from the constructor state."""
+        gc_dt = float(over.pop("GCtimestep", params["GCtimestep"]))
+        if gc_dt == 0:
+            raise ValueError("AdaptiveEnsemble needs params['GCtimestep'] != 0 (the bounce-period output step is a "
+                             "per-tracer host quadrature; use Adaptive objects for that)")
+        self.result = engine.adaptive_advance(self.field, self.pos, self.vel, self.t0, self.mass, self.charge,
+                                              float(delta), gc_dt, store_every=store_every, max_rows=max_rows, **over)
+        return self
+
+    def segments(self, i):
+        """List of (mode, rows) for member i; mode 0 = Particle rows (k,7), 1 = GuidingCenter rows (k,5)."""
+        r = self.result
+        rows = r["rows"][i, :r["nstored"][i]]
+        tags = rows[:, 7].astype(np.int64)
+        out = []
+        for tag in np.unique(tags):
+            seg = rows[tags == tag]
+            mode = int(tag & 1)
+            out.append((mode, seg[:, :7] if mode == 0 else seg[:, :5]))
+        return out

@@ -39,9 +39,12 @@ def test_field_ops_vs_reference(eng, name, arith):
         if k == "curlb" and name == "parabolic":
             noise = 1e-9      # unit vectors of O(1) differenced over d = 1e-6
         assert np.max(np.abs(m - g)) / scale < max(noise, 1e-13), (k, np.max(np.abs(m - g)) / scale)
-    for k in ("dBdt", "dbdt"):
-        g = u[f"{name}_{k}"]; m = o[k]
-        assert np.max(np.abs(m - g)) <= 1e-9 * (np.max(np.abs(g)) + 1e-300) + 0.0, k
+    # time derivatives: central difference over timederivstepsize = 1e-3 s; db/dt of a dipole whose
+    # direction does not change is pure round-off (~1e-16/1e-3), so compare on that absolute scale
+    g = u[f"{name}_dBdt"]; m = o["dBdt"]
+    assert np.max(np.abs(m - g)) <= 1e-9 * np.max(np.abs(g)) + 1e-12 * np.max(np.abs(u[f"{name}_magB"])) / 1e-3
+    g = u[f"{name}_dbdt"]; m = o["dbdt"]
+    assert np.max(np.abs(m - g)) <= 1e-9 * np.max(np.abs(g)) + 1e-12 / 1e-3
     for k in ("lengthscale", "curvature"):
         g = u[f"{name}_{k}"]; m = o[k]
         fin = np.isfinite(g)

@@ -9,6 +9,7 @@ delta = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 arith = sys.argv[3] if len(sys.argv) > 3 else "fast"
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 store_every = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+sort = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 _lib.init(0)
 dev = torch.device("cuda:0")
 ic = synth.config2_protons(n)
@@ -24,9 +25,9 @@ for r in range(reps):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()
     engine.particle_advance_dev(f, cols, mass, charge, delta, out, store_every=store_every, max_rows=max_rows, rows=rows,
-                                arith=arith, cyclotronresolution=20)
+                                arith=arith, cyclotronresolution=20, sort_by_work=sort)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     steps = int(out["counters"][:, 1].to(torch.int64).sum()); nrow = int(out["nrows"].to(torch.int64).sum())
-    print(f"n={n} delta={delta} {arith} store_every={store_every}: {ms:.2f} ms  steps={steps:.4e} rows={nrow:.4e}  {steps/ms*1e3:.4e} steps/s "
+    print(f"n={n} delta={delta} {arith} store_every={store_every} sort={sort}: {ms:.2f} ms  steps={steps:.4e} rows={nrow:.4e}  {steps/ms*1e3:.4e} steps/s "
           f" -> {steps/ms*1e3*1440/1e12:.2f} TFLOP/s alg", flush=True)
