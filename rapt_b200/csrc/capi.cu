@@ -12,6 +12,9 @@
 #include "rapt_launch.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include "embedded_headers.inc"
 
 static_assert(sizeof(rapt_field_t) == sizeof(rapt::FieldP), "FieldP layout");
 static_assert(sizeof(rapt_params_t) == sizeof(rapt::ParamsP), "ParamsP layout");
@@ -91,33 +94,192 @@ void fill_common(rapt::AdvArgs &a, const rapt_field_t *f, const rapt_params_t *p
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// NVRTC path for user-defined analytic fields (rapt/fields.py plugin interface; examples/Creating new
+// fields.ipynb).  The user's snippet (rapt_user_B / rapt_user_E) is compiled together with the SAME
+// kernel templates as the built-ins (headers embedded in this library), for sm_100a, once per
+// (source, arithmetic flavour); the cubin is loaded with cudaLibraryLoadData.  libnvrtc is dlopen'ed on
+// first use so that the library itself loads on machines without the CUDA toolkit's NVRTC.
+// ------------------------------------------------------------------------------------------------
+enum { UK_PARTICLE = 0, UK_GC, UK_PARTICLE_DT, UK_FIELD_OPS, UK_MISC, UK_BOUNCE, UK_ADAPT, UK_COUNT };
+const char *const k_user_kernel_exprs[UK_COUNT] = {
+    "rapt_user::k_particle_dop853<rapt_user::Field<100> >",
+    "rapt_user::k_gc_dopri5<rapt_user::Field<100> >",
+    "rapt_user::k_particle_dt<rapt_user::Field<100> >",
+    "rapt_user::k_field_ops<rapt_user::Field<100> >",
+    "rapt_user::k_misc<rapt_user::Field<100> >",
+    "rapt_user::k_bounce_setup<rapt_user::Field<100> >",
+    "rapt_user::k_adaptive_switch<rapt_user::Field<100> >",
+};
+struct UserModule { bool built = false; cudaLibrary_t lib = nullptr; cudaKernel_t k[UK_COUNT] = {}; };
+struct UserField { std::string src; int has_E = 0; UserModule mod[2]; };
+std::vector<UserField> g_user;
+
+struct Nvrtc {
+    void *h = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram *) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char *const *) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t *) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char *) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t *) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char *) = nullptr;
+    nvrtcResult (*AddNameExpression)(nvrtcProgram, const char *) = nullptr;
+    nvrtcResult (*GetLoweredName)(nvrtcProgram, const char *, const char **) = nullptr;
+    const char *(*GetErrorString)(nvrtcResult) = nullptr;
+} g_nvrtc;
+
+int load_nvrtc()
+{
+    if (g_nvrtc.h) return RAPT_OK;
+    const char *cands[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                           "/usr/local/cuda/targets/x86_64-linux/lib/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+    for (const char *c : cands) { g_nvrtc.h = dlopen(c, RTLD_NOW | RTLD_GLOBAL); if (g_nvrtc.h) break; }
+    if (!g_nvrtc.h) return fail(RAPT_E_NVRTC, "cannot dlopen libnvrtc (%s)", dlerror());
+#define SYM(n) *(void **)(&g_nvrtc.n) = dlsym(g_nvrtc.h, "nvrtc" #n); if (!g_nvrtc.n) return fail(RAPT_E_NVRTC, "libnvrtc lacks nvrtc" #n)
+    SYM(CreateProgram); SYM(DestroyProgram); SYM(CompileProgram); SYM(GetProgramLogSize); SYM(GetProgramLog);
+    SYM(GetCUBINSize); SYM(GetCUBIN); SYM(AddNameExpression); SYM(GetLoweredName); SYM(GetErrorString);
+#undef SYM
+    return RAPT_OK;
+}
+
+// compile (source, flavour) to a cubin; returns the lowered kernel names
+int nvrtc_compile(const UserField &uf, bool strict, std::string &cubin, std::string lowered[UK_COUNT], char *log, int loglen)
+{
+    if (int rc = load_nvrtc()) return rc;
+    std::string src;
+    src += "#define RAPT_USER_FIELD 1\n";
+    src += std::string("#define RAPT_USER_HAS_E ") + (uf.has_E ? "1" : "0") + "\n";
+    src += std::string("#define RAPT_STRICT ") + (strict ? "1" : "0") + "\n";
+    src += "#define RAPT_NS rapt_user\n";
+    src += "#include \"rapt_aux.cuh\"\n";
+    src += "namespace rapt_user {\n"
+           "template <class F> __global__ void k_particle_dt(const rapt::AdvArgs a, double *key, int *idx) {\n"
+           "  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; if (i >= a.nwork) return;\n"
+           "  double mass = a.mass[i], q = a.charge[i], px = a.s4[i], py = a.s5[i], pz = a.s6[i];\n"
+           "  double gm = sqrt(mass * mass + dot3(px, py, pz, px, py, pz) / (RAPT_C_LIGHT * RAPT_C_LIGHT));\n"
+           "  double vx = px / gm, vy = py / gm, vz = pz / gm;\n"
+           "  double gamma = 1.0 / sqrt(1 - dot3(vx, vy, vz, vx, vy, vz) / (RAPT_C_LIGHT * RAPT_C_LIGHT));\n"
+           "  double Bm = F::magB(a.f, a.t[i], a.s1[i], a.s2[i], a.s3[i]);\n"
+           "  double dt = 2 * RAPT_PI * gamma * mass / Bm / fabs(q) / a.p.cyclotronresolution;\n"
+           "  double delta = a.delta_arr ? a.delta_arr[i] : a.delta;\n"
+           "  key[i] = dt / delta; idx[i] = (int)i; }\n}\n";
+    src += "// ---- user snippet\nnamespace rapt_user {\n" + uf.src + "\n}\n";
+    nvrtcProgram prog;
+    nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.c_str(), "rapt_user_field.cu", k_nhdr, k_hdr_srcs, k_hdr_names);
+    if (r != NVRTC_SUCCESS) return fail(RAPT_E_NVRTC, "nvrtcCreateProgram: %s", g_nvrtc.GetErrorString(r));
+    for (int k = 0; k < UK_COUNT; k++) g_nvrtc.AddNameExpression(prog, k_user_kernel_exprs[k]);
+    std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+    if (strict) opts.push_back("--fmad=false");
+    r = g_nvrtc.CompileProgram(prog, (int)opts.size(), opts.data());
+    size_t ls = 0;
+    g_nvrtc.GetProgramLogSize(prog, &ls);
+    if (ls > 1 && log && loglen > 0) {
+        std::string l(ls, '\0');
+        g_nvrtc.GetProgramLog(prog, &l[0]);
+        snprintf(log, loglen, "%s", l.c_str());
+    }
+    if (r != NVRTC_SUCCESS) {
+        g_nvrtc.DestroyProgram(&prog);
+        return fail(RAPT_E_NVRTC, "nvrtcCompileProgram: %s", g_nvrtc.GetErrorString(r));
+    }
+    for (int k = 0; k < UK_COUNT; k++) {
+        const char *ln = nullptr;
+        if (g_nvrtc.GetLoweredName(prog, k_user_kernel_exprs[k], &ln) != NVRTC_SUCCESS || !ln) {
+            g_nvrtc.DestroyProgram(&prog);
+            return fail(RAPT_E_NVRTC, "no lowered name for %s", k_user_kernel_exprs[k]);
+        }
+        lowered[k] = ln;
+    }
+    size_t cs = 0;
+    g_nvrtc.GetCUBINSize(prog, &cs);
+    cubin.resize(cs);
+    g_nvrtc.GetCUBIN(prog, &cubin[0]);
+    g_nvrtc.DestroyProgram(&prog);
+    return RAPT_OK;
+}
+
+int user_module(int uid, bool strict, UserModule **out)
+{
+    if (uid < 0 || uid >= (int)g_user.size()) return fail(RAPT_E_ARG, "unknown user field id %d", uid);
+    UserModule &m = g_user[uid].mod[strict ? 1 : 0];
+    if (!m.built) {
+        std::string cubin, lowered[UK_COUNT];
+        char log[4096] = "";
+        if (int rc = nvrtc_compile(g_user[uid], strict, cubin, lowered, log, sizeof log)) return rc;
+        CK(cudaLibraryLoadData(&m.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+        for (int k = 0; k < UK_COUNT; k++) CK(cudaLibraryGetKernel(&m.k[k], m.lib, lowered[k].c_str()));
+        m.built = true;
+    }
+    *out = &m;
+    return RAPT_OK;
+}
+
+// One launch of kernel family `which` for field f: built-in -> the precompiled flavour; user -> NVRTC module.
+int launch_any(const rapt_field_t *f, bool strict, int which, const void *args, long long n, int grid, cudaStream_t s,
+               double *key = nullptr, int *idx = nullptr)
+{
+    if (f->kind == RAPT_FIELD_USER) {
+        UserModule *m = nullptr;
+        if (int rc = user_module(f->user_id, strict, &m)) return rc;
+        int block = 128;
+        if (which == UK_PARTICLE_DT) { block = 256; grid = (int)((n + 255) / 256); }
+        else if (which == UK_ADAPT) { block = 256; grid = (int)((n + 255) / 256); }
+        else if (which == UK_FIELD_OPS || which == UK_MISC || which == UK_BOUNCE) grid = (int)((n + 127) / 128);
+        void *kargs[3] = {const_cast<void *>(args), &key, &idx};
+        CK(cudaLaunchKernel((const void *)m->k[which], dim3(grid), dim3(block), kargs, 0, s));
+        return RAPT_OK;
+    }
+    switch (which) {
+    case UK_PARTICLE: CK(FLAVOUR(strict, launch_particle, *static_cast<const rapt::AdvArgs *>(args), grid, s)); break;
+    case UK_GC: CK(FLAVOUR(strict, launch_gc, *static_cast<const rapt::AdvArgs *>(args), grid, s)); break;
+    case UK_PARTICLE_DT: CK(FLAVOUR(strict, launch_particle_dt, *static_cast<const rapt::AdvArgs *>(args), key, idx, s)); break;
+    case UK_FIELD_OPS: CK(FLAVOUR(strict, launch_field_ops, args, s)); break;
+    case UK_MISC: CK(FLAVOUR(strict, launch_misc, args, s)); break;
+    case UK_BOUNCE: CK(FLAVOUR(strict, launch_bounce, args, s)); break;
+    case UK_ADAPT: CK(FLAVOUR(strict, launch_adaptive_switch, args, s)); break;
+    default: return fail(RAPT_E_ARG, "bad kernel family");
+    }
+    return RAPT_OK;
+}
+
+int check_field(const rapt_field_t *f)
+{
+    if (!f) return fail(RAPT_E_ARG, "null field");
+    if (f->kind == RAPT_FIELD_USER) {
+        if (f->user_id < 0 || f->user_id >= (int)g_user.size()) return fail(RAPT_E_ARG, "unknown user field id %d", f->user_id);
+        return RAPT_OK;
+    }
+    if (f->kind < 0 || f->kind > 5) return fail(RAPT_E_ARG, "unknown field kind %d", f->kind);
+    return RAPT_OK;
+}
+
 // Longest-first schedule: sort particle indices by dt/delta ascending (fewest-rows last), so the lanes
 // that run dry at the end of the kernel are finishing the SHORTEST particles (SURVEY.md hard part H4).
-cudaError_t build_order(rapt::AdvArgs &a, bool strict, cudaStream_t s)
+int build_order(const rapt_field_t *f, rapt::AdvArgs &a, bool strict, cudaStream_t s)
 {
     const size_t n = (size_t)a.nwork;
-    cudaError_t e;
     if (g_sort.n < n) {
         cudaFree(g_sort.key_in); cudaFree(g_sort.key_out); cudaFree(g_sort.idx_in); cudaFree(g_sort.idx_out);
-        if ((e = cudaMalloc(&g_sort.key_in, n * sizeof(double))) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&g_sort.key_out, n * sizeof(double))) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&g_sort.idx_in, n * sizeof(int))) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&g_sort.idx_out, n * sizeof(int))) != cudaSuccess) return e;
+        CK(cudaMalloc(&g_sort.key_in, n * sizeof(double)));
+        CK(cudaMalloc(&g_sort.key_out, n * sizeof(double)));
+        CK(cudaMalloc(&g_sort.idx_in, n * sizeof(int)));
+        CK(cudaMalloc(&g_sort.idx_out, n * sizeof(int)));
         g_sort.n = n;
     }
-    if ((e = FLAVOUR(strict, launch_particle_dt, a, g_sort.key_in, g_sort.idx_in, s)) != cudaSuccess) return e;
+    if (int rc = launch_any(f, strict, UK_PARTICLE_DT, &a, (long long)n, 0, s, g_sort.key_in, g_sort.idx_in)) return rc;
     g_launches++;
     size_t need = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, need, g_sort.key_in, g_sort.key_out, g_sort.idx_in, g_sort.idx_out, (int)n, 0, 64, s);
     if (need > g_sort.tmp_bytes) {
         cudaFree(g_sort.tmp);
-        if ((e = cudaMalloc(&g_sort.tmp, need)) != cudaSuccess) return e;
+        CK(cudaMalloc(&g_sort.tmp, need));
         g_sort.tmp_bytes = need;
     }
-    e = cub::DeviceRadixSort::SortPairs(g_sort.tmp, need, g_sort.key_in, g_sort.key_out, g_sort.idx_in, g_sort.idx_out, (int)n, 0, 64, s);
+    CK(cub::DeviceRadixSort::SortPairs(g_sort.tmp, need, g_sort.key_in, g_sort.key_out, g_sort.idx_in, g_sort.idx_out, (int)n, 0, 64, s));
     g_launches += 1;
     a.order = g_sort.idx_out;
-    return e;
+    return RAPT_OK;
 }
 
 int grid_for(long long n, int blocks_per_sm)
@@ -212,6 +374,28 @@ int rapt_b200_fp64_peak(int iters, double *tflops, double *sm_clock_mhz)
     return RAPT_OK;
 }
 
+int rapt_b200_field_nvrtc(const char *cuda_src, int has_E, int *user_id, char *log, int loglen)
+{
+    if (!cuda_src || !user_id) return fail(RAPT_E_ARG, "field_nvrtc: null argument");
+    if (log && loglen > 0) log[0] = 0;
+    for (size_t i = 0; i < g_user.size(); i++)
+        if (g_user[i].has_E == (has_E != 0) && g_user[i].src == cuda_src) { *user_id = (int)i; return RAPT_OK; }
+    UserField uf;
+    uf.src = cuda_src; uf.has_E = has_E != 0;
+    // compile the fast flavour now so that syntax errors surface here (no device needed for NVRTC itself)
+    std::string cubin, lowered[UK_COUNT];
+    if (int rc = nvrtc_compile(uf, false, cubin, lowered, log, loglen)) return rc;
+    g_user.push_back(uf);
+    *user_id = (int)g_user.size() - 1;
+    if (rapt_b200_device_count() > 0 && ensure_init() == RAPT_OK) {
+        UserModule &m = g_user.back().mod[0];
+        CK(cudaLibraryLoadData(&m.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+        for (int k = 0; k < UK_COUNT; k++) CK(cudaLibraryGetKernel(&m.k[k], m.lib, lowered[k].c_str()));
+        m.built = true;
+    }
+    return RAPT_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Particle.advance
 // ------------------------------------------------------------------------------------------------
@@ -226,8 +410,7 @@ int rapt_b200_particle_advance_dev(const rapt_field_t *f, const rapt_params_t *p
     if (!f || !p || n < 0 || !t || !x || !y || !z || !px || !py || !pz || !mass || !charge || !nstored || !counters ||
         !status || !tcur)
         return fail(RAPT_E_ARG, "particle_advance: null argument");
-    if (f->kind == RAPT_FIELD_USER) return fail(RAPT_E_UNSUPPORTED, "user fields go through the NVRTC module");
-    if (f->kind < 0 || f->kind > 5) return fail(RAPT_E_ARG, "unknown field kind %d", f->kind);
+    if (int rc = check_field(f)) return rc;
     if (n == 0) return RAPT_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rapt::AdvArgs a;
@@ -239,8 +422,8 @@ int rapt_b200_particle_advance_dev(const rapt_field_t *f, const rapt_params_t *p
     a.nstored = nstored; a.nrows = nrows; a.counters = counters; a.status = status; a.tcur = tcur; a.dt_out = dt_out;
     const bool strict = p->arith == 1;
     const int grid = grid_for(n, FLAVOUR(strict, particle_blocks_per_sm));
-    if (p->sort_by_work && n > (long long)grid * 128) CK(build_order(a, strict, s));
-    CK(FLAVOUR(strict, launch_particle, a, grid, s));
+    if (p->sort_by_work && n > (long long)grid * 128) { if (int rc = build_order(f, a, strict, s)) return rc; }
+    if (int rc = launch_any(f, strict, UK_PARTICLE, &a, n, grid, s)) return rc;
     g_launches++;
     return RAPT_OK;
 }
@@ -299,8 +482,7 @@ int rapt_b200_gc_advance_dev(const rapt_field_t *f, const rapt_params_t *p, int 
     if (!f || !p || n < 0 || !t || !x || !y || !z || !ppar || !mu || !v || !mass || !charge || !dt || !nstored ||
         !counters || !status || !tcur)
         return fail(RAPT_E_ARG, "gc_advance: null argument");
-    if (f->kind == RAPT_FIELD_USER) return fail(RAPT_E_UNSUPPORTED, "user fields go through the NVRTC module");
-    if (f->kind < 0 || f->kind > 5) return fail(RAPT_E_ARG, "unknown field kind %d", f->kind);
+    if (int rc = check_field(f)) return rc;
     if (eom < 0 || eom > 2) return fail(RAPT_E_ARG, "unknown eom %d", eom);
     if (n == 0) return RAPT_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -313,7 +495,7 @@ int rapt_b200_gc_advance_dev(const rapt_field_t *f, const rapt_params_t *p, int 
     a.nstored = nstored; a.nrows = nrows; a.counters = counters; a.status = status; a.tcur = tcur;
     const bool strict = p->arith == 1;
     const int grid = grid_for(n, FLAVOUR(strict, gc_blocks_per_sm));
-    CK(FLAVOUR(strict, launch_gc, a, grid, s));
+    if (int rc = launch_any(f, strict, UK_GC, &a, n, grid, s)) return rc;
     g_launches++;
     return RAPT_OK;
 }
@@ -358,13 +540,6 @@ int rapt_b200_gc_advance(const rapt_field_t *f, const rapt_params_t *p, int eom,
 // ------------------------------------------------------------------------------------------------
 // small per-call kernels (host pointers)
 // ------------------------------------------------------------------------------------------------
-static int check_field(const rapt_field_t *f)
-{
-    if (!f) return fail(RAPT_E_ARG, "null field");
-    if (f->kind == RAPT_FIELD_USER) return fail(RAPT_E_UNSUPPORTED, "user fields go through the NVRTC module");
-    if (f->kind < 0 || f->kind > 5) return fail(RAPT_E_ARG, "unknown field kind %d", f->kind);
-    return RAPT_OK;
-}
 
 int rapt_b200_field_ops(const rapt_field_t *f, int arith, int64_t npt, const double *tpos,
                         double *B, double *E, double *unitb, double *magB, double *gradB, double *jacobianB,
@@ -388,7 +563,7 @@ int rapt_b200_field_ops(const rapt_field_t *f, int arith, int64_t npt, const dou
     a.B = o[0].as<double>(); a.E = o[1].as<double>(); a.unitb = o[2].as<double>(); a.magB = o[3].as<double>();
     a.gradB = o[4].as<double>(); a.jac = o[5].as<double>(); a.curlb = o[6].as<double>(); a.curv = o[7].as<double>();
     a.dBdt = o[8].as<double>(); a.dbdt = o[9].as<double>(); a.lscale = o[10].as<double>(); a.tscale = o[11].as<double>();
-    CK(FLAVOUR(arith == 1, launch_field_ops, &a, s));
+    if (int rc = launch_any(f, arith == 1, UK_FIELD_OPS, &a, npt, 0, s)) return rc;
     g_launches++;
     for (int k = 0; k < 12; k++) if (host[k]) CK(down(host[k], o[k], npt * width[k] * sizeof(double), s));
     CK(cudaStreamSynchronize(s));
@@ -416,7 +591,7 @@ int rapt_b200_gc_construct(const rapt_field_t *f, int arith, int64_t n, const do
     a.a0 = in[0].as<double>(); a.a1 = in[1].as<double>(); a.a2 = in[2].as<double>(); a.a3 = in[3].as<double>();
     a.a4 = in[4].as<double>(); a.a5 = in[5].as<double>(); a.a6 = in[6].as<double>();
     a.o0 = o0.as<double>(); a.o1 = o1.as<double>();
-    CK(FLAVOUR(arith == 1, launch_misc, &a, s));
+    if (int rc = launch_any(f, arith == 1, UK_MISC, &a, n, 0, s)) return rc;
     g_launches++;
     CK(down(ppar, o0, nb, s)); CK(down(mu, o1, nb, s));
     CK(cudaStreamSynchronize(s));
@@ -441,7 +616,7 @@ int rapt_b200_switch_p2g(const rapt_field_t *f, int arith, int64_t n, const doub
     a.n = n; a.op = 1;
     a.a0 = dp.as<double>(); a.a1 = dm.as<double>(); a.a2 = dq.as<double>();
     a.o0 = og.as<double>(); a.o1 = omu.as<double>(); a.o2 = ov.as<double>(); a.io = ost.as<int>();
-    CK(FLAVOUR(arith == 1, launch_misc, &a, s));
+    if (int rc = launch_any(f, arith == 1, UK_MISC, &a, n, 0, s)) return rc;
     g_launches++;
     CK(down(grow5, og, 5 * nb, s)); CK(down(mu, omu, nb, s)); CK(down(v, ov, nb, s)); CK(down(status, ost, n * sizeof(int), s));
     CK(cudaStreamSynchronize(s));
@@ -466,7 +641,7 @@ int rapt_b200_switch_g2p(const rapt_field_t *f, int arith, int64_t n, const doub
     a.n = n; a.op = 2; a.t_eval = t_eval;
     a.a0 = dg.as<double>(); a.a1 = dmu.as<double>(); a.a2 = dm.as<double>(); a.a3 = dq.as<double>();
     a.o0 = op.as<double>();
-    CK(FLAVOUR(arith == 1, launch_misc, &a, s));
+    if (int rc = launch_any(f, arith == 1, UK_MISC, &a, n, 0, s)) return rc;
     g_launches++;
     CK(down(prow7, op, 7 * nb, s));
     CK(cudaStreamSynchronize(s));
@@ -491,7 +666,7 @@ int rapt_b200_isadiabatic(const rapt_field_t *f, const rapt_params_t *p, int mod
     memcpy(&a.f, f, sizeof a.f); memcpy(&a.p, p, sizeof a.p);
     a.n = n; a.op = 3; a.mode = mode; a.stride = row_stride;
     a.a0 = dr.as<double>(); a.a1 = dmu.as<double>(); a.a2 = dm.as<double>(); a.a3 = dq.as<double>(); a.io = oo.as<int>();
-    CK(FLAVOUR(p->arith == 1, launch_misc, &a, s));
+    if (int rc = launch_any(f, p->arith == 1, UK_MISC, &a, n, 0, s)) return rc;
     g_launches++;
     CK(down(out, oo, n * sizeof(int), s));
     CK(cudaStreamSynchronize(s));
@@ -525,7 +700,7 @@ int rapt_b200_bounce_setup(const rapt_field_t *f, int arith, double fieldlineres
     a.ppar = in[4].as<double>(); a.mu = in[5].as<double>(); a.mass = in[6].as<double>();
     a.Bm = oBm.as<double>(); a.v = ov.as<double>(); a.ds = ods.as<double>(); a.npts = onp.as<int>();
     a.curve = ocv.as<double>(); a.scratch = scr.as<double>();
-    CK(FLAVOUR(arith == 1, launch_bounce, &a, s));
+    if (int rc = launch_any(f, arith == 1, UK_BOUNCE, &a, n, 0, s)) return rc;
     g_launches++;
     CK(down(Bm, oBm, nb, s)); if (v) CK(down(v, ov, nb, s)); CK(down(ds, ods, nb, s)); CK(down(npts, onp, n * sizeof(int), s));
     CK(down(curve, ocv, (size_t)n * max_pts * 5 * sizeof(double), s));
@@ -593,7 +768,7 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
     sw.max_rows = want_rows ? max_rows : 0; sw.rows = want_rows ? drows.as<double>() : nullptr;
     sw.listP = dlp.as<int>(); sw.listG = dlg.as<int>(); sw.counts = dcounts.as<int>();
     sw.first = 1;
-    CK(FLAVOUR(strict, launch_adaptive_switch, &sw, s0));
+    if (int rc = launch_any(f, strict, UK_ADAPT, &sw, n, 0, s0)) return rc;
     g_launches++;
     sw.first = 0;
 
@@ -619,7 +794,7 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
             a.store_every = want_rows ? std::max<int64_t>(store_every, 1) : 0; a.max_rows = sw.max_rows; a.rows = sw.rows;
             a.nstored = sw.nstored; a.nrows = nullptr; a.counters = dcnt.as<int>(); a.status = sw.status;
             a.tcur = sw.tcur; a.dt_out = ddtp.as<double>(); a.segtag = sw.segtag; a.append = 1;
-            CK(FLAVOUR(strict, launch_particle, a, std::min(gp, (cnt[0] + 127) / 128), s1));
+            if (int rc = launch_any(f, strict, UK_PARTICLE, &a, cnt[0], std::min(gp, (cnt[0] + 127) / 128), s1)) return rc;
             g_launches++;
         }
         if (cnt[1] > 0) {
@@ -632,11 +807,11 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
             a.store_every = want_rows ? std::max<int64_t>(store_every, 1) : 0; a.max_rows = sw.max_rows; a.rows = sw.rows;
             a.nstored = sw.nstored; a.nrows = nullptr; a.counters = dcnt.as<int>(); a.status = sw.status;
             a.tcur = sw.tcur; a.segtag = sw.segtag; a.append = 1;
-            CK(FLAVOUR(strict, launch_gc, a, std::min(gg, (cnt[1] + 127) / 128), s2));
+            if (int rc = launch_any(f, strict, UK_GC, &a, cnt[1], std::min(gg, (cnt[1] + 127) / 128), s2)) return rc;
             g_launches++;
         }
         CK(cudaStreamSynchronize(s1)); CK(cudaStreamSynchronize(s2));
-        CK(FLAVOUR(strict, launch_adaptive_switch, &sw, s0));
+        if (int rc = launch_any(f, strict, UK_ADAPT, &sw, n, 0, s0)) return rc;
         g_launches++;
     }
     if (epochs_out) *epochs_out = epochs;

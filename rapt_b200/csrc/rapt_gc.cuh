@@ -59,7 +59,7 @@ RAPT_DEV void grad_and_curl(const FieldP &f, double t, double x, double y, doubl
     g[2] = RAPT_FD(mp, mm);
     (void)pxx; (void)mxx; (void)pyy; (void)myy; (void)pzz; (void)mzz;
 #if RAPT_STRICT
-    // summation order of np.dot(_M1, beta) in the reference's BLAS (see oracle/rapt_oracle.c field_curlb)
+    // summation order of np.dot(_M1, beta) in the reference's BLAS ('oracle')
     c[0] = ((pyz + (-myz + -pzy)) + mzy) / den;
     c[1] = ((-pxz + pzx) + (mxz + -mzx)) / den;
     c[2] = ((pxy + myx) + (-mxy + -pyx)) / den;

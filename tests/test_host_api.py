@@ -1,0 +1,137 @@
+"""CPU: the C-ABI library loads and exports every symbol include/rapt_b200.h declares, fails loudly
+without a device, and the host-side mirror of the reference interface (fields, utils, params,
+constructors, getters) reproduces the reference's values.  No compute calls on the GPU here."""
+import ctypes
+import os
+import re
+import numpy as np
+import pytest
+
+import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rapt_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "rapt_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(rapt_b200_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/rapt_b200.h but not exported"
+    assert b"sm_100a" in lib.rapt_b200_version()
+
+
+def test_struct_layouts_match_header():
+    from rapt_b200._lib import FieldT, ParamsT
+    assert ctypes.sizeof(FieldT) == 4 * 4 + 16 * 8 + 2 * 8
+    assert ctypes.sizeof(ParamsT) == 5 * 8 + 8 * 4
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry raises; with one, this test is skipped."""
+    from rapt_b200 import _lib, engine, fields
+    if _lib.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(_lib.RaptB200Error, match="no CUDA device"):
+        engine.particle_advance(fields.EarthDipole(), np.zeros((1, 7)) + 1.0, 1.0, 1.0, 1.0)
+    with pytest.raises(_lib.RaptB200Error):
+        engine.field_ops(fields.EarthDipole(), np.ones((2, 4)))
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through oracle/ (test infrastructure)."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "rapt_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn), errors="replace").read()
+                assert "import oracle" not in src and "liboracle" not in src and "rapt_oracle" not in src, fn
+
+
+def test_host_fields_match_reference():
+    from rapt_b200 import fields
+    u = np.load(H.GOLDEN + "/units.npz")
+    mk = {"earthdipole": fields.EarthDipole(), "doubledipole": fields.DoubleDipole(), "uniformbz": fields.UniformBz(2e-4),
+          "crossedeb": fields.UniformCrossedEB(2.0, 1e-4), "vardipole": fields.VarEarthDipole(0.1, 10),
+          "parabolic": fields.Parabolic()}
+    for name, f in mk.items():
+        for i, tp in enumerate(u[name + "_pts"]):
+            assert np.array_equal(f.B(tp), u[name + "_B"][i])
+            assert np.array_equal(np.asarray(f.E(tp), float), u[name + "_E"][i])
+            assert np.array_equal(f.gradB(tp), u[name + "_gradB"][i])
+            assert np.array_equal(f.jacobianB(tp), u[name + "_jacobianB"][i])
+            assert np.allclose(f.curlb(tp), u[name + "_curlb"][i], rtol=0, atol=1e-9 * (np.abs(u[name + "_curlb"][i]).max() + 1e-30) + 1e-300) \
+                or np.array_equal(f.curlb(tp), u[name + "_curlb"][i])
+            assert f.magB(tp) == u[name + "_magB"][i]
+            assert f.curvature(tp) == u[name + "_curvature"][i] or np.isnan(u[name + "_curvature"][i])
+    d = fields.EarthDipole().device_descriptor()
+    assert d.kind == 0 and d.is_static == 1 and d.gradstep == 6378137 * 1e-6 and d.prm[0] == -3 * 3.07e-5 * 6378137 ** 3
+    d = fields.UniformCrossedEB(2.0, 1e-4).device_descriptor()
+    assert d.kind == 3 and d.is_static == 0 and (d.prm[0], d.prm[1]) == (1e-4, 2.0)
+    with pytest.raises(NotImplementedError):
+        class NoSnippet(fields._Field):
+            pass
+        NoSnippet().device_descriptor()
+
+
+def test_host_utils_match_reference():
+    from rapt_b200 import utils as ru, fields, m_pr, m_el, e
+    u = np.load(H.GOLDEN + "/units.npz")
+    f = fields.DoubleDipole()
+    for i in range(len(u["utils_pos"])):
+        pos, vel = u["utils_pos"][i], u["utils_vel"][i]
+        assert ru.cyclotron_period(0, pos, vel, f, m_pr, e) == u["utils_cycper"][i]
+        assert ru.cyclotron_radius(0, pos, vel, f, m_pr, e) == u["utils_cycrad"][i]
+        R, vp, v = ru.guidingcenter(0, pos, vel, f, m_pr, e)
+        assert np.array_equal(R, u["utils_gc_R"][i]) and vp == u["utils_gc_vp"][i] and v == u["utils_gc_v"][i]
+        assert ru.magnetic_moment(0, R, vp, v, f, m_pr) == u["utils_mu"][i]
+        pp, vv = ru.GCtoFP(0, R, vp, v, f, m_pr, e, 0)
+        assert np.array_equal(pp, u["utils_fp_pos"][i]) and np.array_equal(vv, u["utils_fp_vel"][i])
+    for v, w in zip(u["getperp_in"], u["getperp_out"]):
+        assert np.array_equal(np.asarray(ru.getperp(v), float), w)
+    for k, a, b in zip(u["speed_ke"], u["speed_pr"], u["speed_el"]):
+        assert ru.speedfromKE(k, m_pr) == a and ru.speedfromKE(k, m_el) == b
+
+
+def test_constructors_and_params_snapshot():
+    import rapt_b200 as rb
+    d, _ = H.load("g1_readme")
+    p = rb.Particle(pos=d["pos"], vel=d["vel"], t0=0, mass=rb.m_pr, charge=rb.e, field=rb.fields.EarthDipole())
+    assert np.array_equal(p.trajectory, d["traj"][:1])          # numpy arrays accepted (reference needs tuples on numpy 2)
+    assert p.tcur == 0 and p.check_adiabaticity is False
+    assert rb.Particle().trajectory.shape == (1, 7)
+    d2, _ = H.load("g2_gc_doubledipole")
+    g = rb.GuidingCenter(pos=tuple(d2["pos"]), v=float(d2["v"]), pa=80, mass=rb.m_el, charge=-rb.e, field=rb.fields.DoubleDipole())
+    assert g.mu == float(d2["mu"]) and np.array_equal(g.trajectory, d2["traj"][:1])
+    g90 = rb.GuidingCenter(pos=(-7.8 * rb.Re, 0, 0), v=1e6, pa=90, mass=rb.m_pr, charge=rb.e, field=rb.fields.DoubleDipole())
+    assert g90.trajectory[0, 4] == 0.0                           # quirk Q9: pa == 90 -> p_par exactly 0
+    assert set(["cyclotronresolution", "Ptimestep", "bounceresolution", "GCtimestep", "BCtimestep", "solvertolerances",
+                "fieldlineresolution", "flsolver", "eyegradientstep", "epss", "epst", "enforce equatorial"]) <= set(rb.params)
+    assert rb.params["solvertolerances"] == (1.49012e-8, 1.49012e-8) and rb.params["cyclotronresolution"] == 10
+    s = rb.engine.snapshot_params(None, True, cyclotronresolution=20, **{"enforce equatorial": True})
+    assert (s.cyclotronresolution, s.enforce_equatorial, s.check_adiabaticity, s.rtol) == (20.0, 1, 1, 1.49012e-8)
+    assert rb.params["cyclotronresolution"] == 10, "snapshot overrides must not leak into the global params"
+    with pytest.raises(RuntimeError):
+        rb.BounceCenter(pos=(1, 0, 0), v=1.0, pa=30, mass=1, charge=1, field=rb.fields.UniformCrossedEB())
+    b = rb.BounceCenter(pos=(4 * rb.Re, 0, 0), v=1e7, pa=0.5, mass=rb.m_pr, charge=rb.e, field=rb.fields.EarthDipole())
+    assert b.trajectory.shape == (1, 4) and b.mu > 0
+    with pytest.raises(NotImplementedError):
+        b.advance(1.0)
+    assert issubclass(rb.Adiabatic, Exception) and issubclass(rb.NonAdiabatic, Exception)
+
+
+def test_synthetic_ensembles_are_deterministic():
+    from rapt_b200 import synth
+    a, b = synth.config2_protons(1000), synth.config2_protons(1000)
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    assert np.all(np.abs(a["z"]) > 0) and np.all(a["x"] != 0) and np.all(a["y"] != 0)
+    r = np.sqrt(a["x"] ** 2 + a["y"] ** 2) / synth.Re
+    assert r.min() >= 2 and r.max() <= 6
+    assert a["ke_ev"].min() >= 1e5 and a["ke_ev"].max() <= 1e7
+    v = np.sqrt(a["vx"] ** 2 + a["vy"] ** 2 + a["vz"] ** 2)
+    assert np.all(v < synth.c)
+    c3 = synth.config3_electrons(1000)
+    assert np.all(c3["x"] <= 8 * synth.Re + 1)
+    c4 = synth.config4_speiser(8)
+    assert (c4["x"][0], c4["y"][0], c4["z"][0], c4["vx"][0], c4["vy"][0]) == (5.0, -5.0, 0.9, -0.1, 0.1)
