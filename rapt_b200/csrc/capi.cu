@@ -421,7 +421,8 @@ int rapt_b200_particle_advance_dev(const rapt_field_t *f, const rapt_params_t *p
     a.store_every = rows ? store_every : 0; a.max_rows = rows ? max_rows : 0; a.rows = rows;
     a.nstored = nstored; a.nrows = nrows; a.counters = counters; a.status = status; a.tcur = tcur; a.dt_out = dt_out;
     const bool strict = p->arith == 1;
-    const int grid = grid_for(n, FLAVOUR(strict, particle_blocks_per_sm));
+    const int rkn = !strict && f->is_static && !p->enforce_equatorial && f->kind != RAPT_FIELD_USER && !getenv("RAPT_B200_NO_RKN");
+    const int grid = grid_for(n, FLAVOUR(strict, particle_blocks_per_sm, rkn));
     if (p->sort_by_work && n > (long long)grid * 128) { if (int rc = build_order(f, a, strict, s)) return rc; }
     if (int rc = launch_any(f, strict, UK_PARTICLE, &a, n, grid, s)) return rc;
     g_launches++;
@@ -774,7 +775,7 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
 
     rapt_params_t pc = *p;
     pc.check_adiabaticity = 1;
-    const int gp = grid_for(1 << 30, FLAVOUR(strict, particle_blocks_per_sm));
+    const int gp = grid_for(1 << 30, FLAVOUR(strict, particle_blocks_per_sm, !strict && f->is_static && !p->enforce_equatorial && f->kind != RAPT_FIELD_USER));
     const int gg = grid_for(1 << 30, FLAVOUR(strict, gc_blocks_per_sm));
     int epochs = 0;
     for (;; epochs++) {

@@ -1,13 +1,25 @@
 // kernels_tu.cu -- one translation unit per (arithmetic flavour, kernel family); see Makefile.
 //   -DRAPT_STRICT=0|1 -DRAPT_NS=rapt_fast|rapt_strict -DRAPT_TU_PARTICLE | -DRAPT_TU_GC | -DRAPT_TU_AUX
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include "rapt_launch.h"
 
 #ifdef RAPT_TU_PARTICLE
 #include "rapt_particle.cuh"
+#if !RAPT_STRICT
+#include "rapt_particle_rkn.cuh"
+#endif
 namespace RAPT_NS {
+// fast flavour, static field, no equatorial constraint -> the Nystrom-form kernel (12 warps/SM)
+#if !RAPT_STRICT
+static bool use_rkn(const rapt::AdvArgs &a) { return a.f.is_static && !a.p.enforce_equatorial && !getenv("RAPT_B200_NO_RKN"); }
+#endif
 template <int KIND> static cudaError_t go_particle(const rapt::AdvArgs &a, int grid, cudaStream_t s)
 {
+#if !RAPT_STRICT
+    if (use_rkn(a)) k_particle_rkn<Field<KIND>><<<grid, 128, 0, s>>>(a);
+    else
+#endif
     k_particle_dop853<Field<KIND>><<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
 }
@@ -23,9 +35,12 @@ cudaError_t launch_particle(const rapt::AdvArgs &a, int grid, cudaStream_t s)
     default: return cudaErrorInvalidValue;
     }
 }
-int particle_blocks_per_sm()
+int particle_blocks_per_sm(int rkn)
 {
     int nb = 0;
+#if !RAPT_STRICT
+    if (rkn) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_particle_rkn<Field<0>>, 128, 0); return nb; }
+#endif
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_particle_dop853<Field<0>>, 128, 0);
     return nb;
 }

@@ -6,7 +6,7 @@
 #define RAPT_DECLARE_FLAVOUR(NS)                                                          \
     namespace NS {                                                                        \
     cudaError_t launch_particle(const rapt::AdvArgs &a, int grid, cudaStream_t s);        \
-    int particle_blocks_per_sm();                                                         \
+    int particle_blocks_per_sm(int rkn);                                                       \
     cudaError_t launch_gc(const rapt::AdvArgs &a, int grid, cudaStream_t s);              \
     int gc_blocks_per_sm();                                                               \
     cudaError_t launch_particle_dt(const rapt::AdvArgs &a, double *key, int *idx, cudaStream_t s); \

@@ -1,0 +1,358 @@
+// rapt_particle_rkn.cuh -- Particle.advance for STATIC fields in Nystrom form (fast flavour only).
+//
+// In a static field the reference freezes gamma*m at its entry value (Particle.py:286-291, quirk Q3),
+// so dx/dt = p/(gamma m) is linear in the momentum and the position part of every DOP853 stage follows
+// from the stage *momentum derivatives* K_l alone:
+//     P_i = p + h sum_j a_ij K_j                    X_i = x + (h/gm) (rs_i p + h sum_l (A.A)_il K_l)
+//     p'  = p + h sum_j b_j K_j                     x'  = x + (h/gm) (sb p + h sum_l (b.A)_l K_l)
+// and likewise for the two error estimators (tools/gen_coeffs.py forms A.A, b.A, er.A, w.A exactly from the
+// double tableau and rounds once).  Only 3 of the 6 components of each k-vector are stored: 33 doubles
+// instead of 60, ~165 registers instead of 255, so 12 warps/SM instead of 8 hide the FP64 dependency
+// latency of the field evaluation (profiles/r1_particle_history.md).  Same step-control decisions as
+// k_particle_dop853: the estimators differ from the 6-component form only by its own cancellation
+// round-off (~1e-10 relative of err), positions by ~1 ulp per step.
+// Not used when params["enforce equatorial"] is set or the field is not static (gamma m then varies).
+#pragma once
+#include "rapt_particle.cuh"
+
+namespace RAPT_NS {
+
+// K = dp/dt = q (E + P x B / (gamma m)), Particle.py:295
+template <class F>
+RAPT_DEV void lorentz_K(const FieldP &f, double q, double qg, double t, const double (&X)[3], const double (&P)[3],
+                        double (&K)[3])
+{
+    double bx, by, bz;
+    F::B(f, t, X[0], X[1], X[2], bx, by, bz);
+    const double cx = P[1] * bz - P[2] * by, cy = P[2] * bx - P[0] * bz, cz = P[0] * by - P[1] * bx;
+    if (F::HAS_E) {
+        double ex, ey, ez; F::E(f, t, X[0], X[1], X[2], ex, ey, ez);
+        K[0] = fma(q, ex, qg * cx); K[1] = fma(q, ey, qg * cy); K[2] = fma(q, ez, qg * cz);
+    } else {
+        K[0] = qg * cx; K[1] = qg * cy; K[2] = qg * cz;
+    }
+}
+
+template <class F>
+__global__ void __launch_bounds__(128, 3) k_particle_rkn(const AdvArgs a)
+{
+    const double rtol = a.p.rtol, atol = a.p.atol;
+    const double beta = 0.1, safe = 0.9, fac1 = 0.3, fac2 = 6.0, uround = 2.3e-16;
+    const double expo1 = 1.0 / 8.0 - beta * 0.2, facc1 = 1.0 / fac1, facc2 = 1.0 / fac2;
+    const double pf0 = pow(1e-4, beta);
+
+    double x[3], p[3], K1[3], K2[3], K3[3], K4[3], K5[3], K6[3], K7[3], K8[3], K9[3], K10[3], X[3], P[3], kout[3];
+    double t = 0, h = 0, hg = 0, xend = 0, tstop = 0, dt = 0, facold = 1e-4, hmax = 0, tin = 0, dnf = 0, hnew = 0;
+    double igm = 1, qg = 0, q = 0;
+    int pid = -1;
+    int nstep = 0, naccpt = 0, nrejct = 0, ncalls = 0, nstep_row = 0, naccpt_row = 0;
+    int rowidx = 0, nst = 0, st = ST_OK;
+    bool last = false, reject = false, need_row = false, have = false;
+    double *myrows = nullptr;
+
+    for (;;) {
+        // ---- (A) particle finished?  write it back and fetch the next one
+        if (have && need_row && !(st == ST_OK && t < tstop)) {
+            a.t[pid] = xend; a.s1[pid] = x[0]; a.s2[pid] = x[1]; a.s3[pid] = x[2];
+            a.s4[pid] = p[0]; a.s5[pid] = p[1]; a.s6[pid] = p[2];
+            int *c = a.counters + 4 * (long long)pid;
+            int nf = 2 * ncalls + 11 * nstep + naccpt;       // as scipy counts: SURVEY.md §3.1
+            if (a.append) { c[0] += nf; c[1] += nstep; c[2] += naccpt; c[3] += nrejct; }
+            else { c[0] = nf; c[1] = nstep; c[2] = naccpt; c[3] = nrejct; }
+            a.status[pid] = st;
+            a.tcur[pid] = t + dt;                            // Particle.py:306
+            if (a.nrows) a.nrows[pid] = rowidx + 1;
+            a.nstored[pid] = nst;
+            have = false;
+        }
+        if (!have) {
+            int w = atomicAdd(a.queue, 1);
+            if (w >= a.nwork) break;
+            pid = a.order ? a.order[w] : w;
+            t = a.t[pid];
+            x[0] = a.s1[pid]; x[1] = a.s2[pid]; x[2] = a.s3[pid];
+            p[0] = a.s4[pid]; p[1] = a.s5[pid]; p[2] = a.s6[pid];
+            const double mass = a.mass[pid];
+            q = a.charge[pid];
+            double delta = a.delta_arr ? a.delta_arr[pid] : a.delta;
+            tstop = t + delta;                               // Particle.py:304
+            xend = t;                                        // row label of a tracer that takes no step
+            // Particle.py:274-275, 282: gm (frozen: static field), vel, dt = cyclotron_period / cyclotronresolution
+            double gm = sqrt(mass * mass + dot3(p[0], p[1], p[2], p[0], p[1], p[2]) / (RAPT_C_LIGHT * RAPT_C_LIGHT));
+            igm = 1.0 / gm; qg = q * igm;
+            {
+                double vx = p[0] / gm, vy = p[1] / gm, vz = p[2] / gm;
+                double gamma = 1.0 / sqrt(1 - dot3(vx, vy, vz, vx, vy, vz) / (RAPT_C_LIGHT * RAPT_C_LIGHT));
+                double Bm = F::magB(a.f, t, x[0], x[1], x[2]);
+                dt = 2 * RAPT_PI * gamma * mass / Bm / fabs(q) / a.p.cyclotronresolution;
+            }
+            if (a.dt_out) a.dt_out[pid] = dt;
+            nstep = naccpt = nrejct = ncalls = 0; rowidx = 0; st = ST_OK;
+            myrows = a.rows ? a.rows + (size_t)pid * (size_t)a.max_rows * 8 : nullptr;
+            if (a.append) nst = a.nstored[pid];
+            else {
+                nst = 0;
+                if (myrows && a.store_every > 0 && a.max_rows > 0) {
+                    double2 *r = reinterpret_cast<double2 *>(myrows);
+                    r[0] = make_double2(t, x[0]); r[1] = make_double2(x[1], x[2]);
+                    r[2] = make_double2(p[0], p[1]); r[3] = make_double2(p[2], 0.0);
+                    nst = 1;
+                }
+            }
+            have = true; need_row = true;
+            if (!(t < tstop)) continue;                      // delta <= 0: nothing to do
+            lorentz_K<F>(a.f, q, qg, t, x, p, K1);           // k1 = f(t, y)
+        }
+        // ---- (B) one step attempt; stage 1 = HINIT's Euler probe for lanes that start an output row
+        bool accepted = false, skip = false, hin = false;
+#pragma unroll 1
+        for (int s = 1; s <= 13; s++) {
+            bool active = !skip;
+            switch (s) {
+            case 1:
+                active = need_row;
+                if (active) {
+                    // new output row = new solver call: xend, HINIT part 1
+                    xend = t + dt;                           // Particle.py:305 (also the row's time label)
+                    hmax = fabs(xend - t);
+                    double dny = 0;
+                    dnf = 0;
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        const double iskx = fast_rcp(atol + rtol * fabs(x[i])), iskp = fast_rcp(atol + rtol * fabs(p[i]));
+                        double a_ = p[i] * igm * iskx, b_ = x[i] * iskx;
+                        double c_ = K1[i] * iskp, d_ = p[i] * iskp;
+                        dnf += a_ * a_ + c_ * c_; dny += b_ * b_ + d_ * d_;
+                    }
+                    h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
+                    h = fmin(h, hmax);
+#pragma unroll
+                    for (int i = 0; i < 3; i++) { X[i] = x[i] + h * (p[i] * igm); P[i] = p[i] + h * K1[i]; }
+                    tin = t + h;
+                    hin = true;
+                }
+                break;
+            case 2:
+                if (hin) {
+                    // HINIT part 2: f1 - k1 = ((P - p)/gm, K' - K1) = (h K1/gm, kout - K1)
+                    double der2 = 0;
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        const double iskx = fast_rcp(atol + rtol * fabs(x[i])), iskp = fast_rcp(atol + rtol * fabs(p[i]));
+                        double a_ = h * K1[i] * igm * iskx, c_ = (kout[i] - K1[i]) * iskp;
+                        der2 += a_ * a_ + c_ * c_;
+                    }
+                    der2 = sqrt(der2) / h;
+                    double der12 = fmax(fabs(der2), sqrt(dnf));
+                    double h1;
+                    if (der12 <= 1e-15) h1 = fmax(1e-6, fabs(h) * 1e-3);
+                    else {
+                        double tq = 0.01 / der12, hm2 = hmax * hmax, hm4 = hm2 * hm2;
+                        if (tq > hm4 * hm4 * 1.000001) h1 = hmax;      // h1 >= hmax: not the minimum
+                        else h1 = pow(tq, 1.0 / 8.0);
+                    }
+                    h = fmin(fmin(100 * fabs(h), h1), hmax);
+                    facold = 1e-4; last = false; reject = false; nstep_row = 0; naccpt_row = 0;
+                    ncalls++;
+                    need_row = false;
+                }
+                // step prologue (every lane): failure checks, clip the step to the row end
+                if (nstep_row > 500) st = ST_NMAX;
+                else if (0.1 * fabs(h) <= fabs(t) * uround) st = ST_HSMALL;
+                if (st != ST_OK) {
+                    rowidx++; need_row = true; skip = true; active = false;   // failed row is still appended (Particle.py:304-307)
+                } else {
+                    if ((t + 1.01 * h - xend) > 0.0) { h = xend - t; last = true; }
+                    nstep_row++; nstep++;
+                    hg = h * igm;
+#pragma unroll
+                    for (int i = 0; i < 3; i++) { P[i] = p[i] + h * T8(A2_1) * K1[i]; X[i] = x[i] + hg * T8(A2_1) * p[i]; }
+                    tin = t + T8(C2) * h;
+                }
+                break;
+            case 3:
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        K2[i] = kout[i];
+                        P[i] = p[i] + h * (T8(A3_1) * K1[i] + T8(A3_2) * K2[i]);
+                        X[i] = x[i] + hg * (TN(RS3) * p[i] + h * (TN(AA3_1) * K1[i]));
+                    }
+                    tin = t + T8(C3) * h;
+                }
+                break;
+            case 4:
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        K3[i] = kout[i];
+                        P[i] = p[i] + h * (T8(A4_1) * K1[i] + T8(A4_3) * K3[i]);
+                        X[i] = x[i] + hg * (TN(RS4) * p[i] + h * (TN(AA4_1) * K1[i] + TN(AA4_2) * K2[i]));
+                    }
+                    tin = t + T8(C4) * h;
+                }
+                break;
+            case 5:
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        K4[i] = kout[i];
+                        P[i] = p[i] + h * (T8(A5_1) * K1[i] + T8(A5_3) * K3[i] + T8(A5_4) * K4[i]);
+                        X[i] = x[i] + hg * (TN(RS5) * p[i] + h * (TN(AA5_1) * K1[i] + TN(AA5_2) * K2[i] + TN(AA5_3) * K3[i]));
+                    }
+                    tin = t + T8(C5) * h;
+                }
+                break;
+            case 6:
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        K5[i] = kout[i];
+                        P[i] = p[i] + h * (T8(A6_1) * K1[i] + T8(A6_4) * K4[i] + T8(A6_5) * K5[i]);
+                        X[i] = x[i] + hg * (TN(RS6) * p[i] + h * (TN(AA6_1) * K1[i] + TN(AA6_3) * K3[i] + TN(AA6_4) * K4[i]));
+                    }
+                    tin = t + T8(C6) * h;
+                }
+                break;
+            case 7:
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        K6[i] = kout[i];
+                        P[i] = p[i] + h * (T8(A7_1) * K1[i] + T8(A7_4) * K4[i] + T8(A7_5) * K5[i] + T8(A7_6) * K6[i]);
+                        X[i] = x[i] + hg * (TN(RS7) * p[i] + h * (TN(AA7_1) * K1[i] + TN(AA7_3) * K3[i] + TN(AA7_4) * K4[i] + TN(AA7_5) * K5[i]));
+                    }
+                    tin = t + T8(C7) * h;
+                }
+                break;
+            case 8:
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        K7[i] = kout[i];
+                        P[i] = p[i] + h * (T8(A8_1) * K1[i] + T8(A8_4) * K4[i] + T8(A8_5) * K5[i] + T8(A8_6) * K6[i] + T8(A8_7) * K7[i]);
+                        X[i] = x[i] + hg * (TN(RS8) * p[i] + h * (TN(AA8_1) * K1[i] + TN(AA8_3) * K3[i] + TN(AA8_4) * K4[i] + TN(AA8_5) * K5[i] + TN(AA8_6) * K6[i]));
+                    }
+                    tin = t + T8(C8) * h;
+                }
+                break;
+            case 9:
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        K8[i] = kout[i];
+                        P[i] = p[i] + h * (T8(A9_1) * K1[i] + T8(A9_4) * K4[i] + T8(A9_5) * K5[i] + T8(A9_6) * K6[i] + T8(A9_7) * K7[i] + T8(A9_8) * K8[i]);
+                        X[i] = x[i] + hg * (TN(RS9) * p[i] + h * (TN(AA9_1) * K1[i] + TN(AA9_3) * K3[i] + TN(AA9_4) * K4[i] + TN(AA9_5) * K5[i] + TN(AA9_6) * K6[i] + TN(AA9_7) * K7[i]));
+                    }
+                    tin = t + T8(C9) * h;
+                }
+                break;
+            case 10:
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        K9[i] = kout[i];
+                        P[i] = p[i] + h * (T8(A10_1) * K1[i] + T8(A10_4) * K4[i] + T8(A10_5) * K5[i] + T8(A10_6) * K6[i] + T8(A10_7) * K7[i] + T8(A10_8) * K8[i] + T8(A10_9) * K9[i]);
+                        X[i] = x[i] + hg * (TN(RS10) * p[i] + h * (TN(AA10_1) * K1[i] + TN(AA10_3) * K3[i] + TN(AA10_4) * K4[i] + TN(AA10_5) * K5[i] + TN(AA10_6) * K6[i] + TN(AA10_7) * K7[i] + TN(AA10_8) * K8[i]));
+                    }
+                    tin = t + T8(C10) * h;
+                }
+                break;
+            case 11:
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        K10[i] = kout[i];
+                        P[i] = p[i] + h * (T8(A11_1) * K1[i] + T8(A11_4) * K4[i] + T8(A11_5) * K5[i] + T8(A11_6) * K6[i] + T8(A11_7) * K7[i] + T8(A11_8) * K8[i] + T8(A11_9) * K9[i] + T8(A11_10) * K10[i]);
+                        X[i] = x[i] + hg * (TN(RS11) * p[i] + h * (TN(AA11_1) * K1[i] + TN(AA11_3) * K3[i] + TN(AA11_4) * K4[i] + TN(AA11_5) * K5[i] + TN(AA11_6) * K6[i] + TN(AA11_7) * K7[i] + TN(AA11_8) * K8[i] + TN(AA11_9) * K9[i]));
+                    }
+                    tin = t + T8(C11) * h;
+                }
+                break;
+            case 12:
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        K2[i] = kout[i];
+                        P[i] = p[i] + h * (T8(A12_1) * K1[i] + T8(A12_4) * K4[i] + T8(A12_5) * K5[i] + T8(A12_6) * K6[i] + T8(A12_7) * K7[i] + T8(A12_8) * K8[i] + T8(A12_9) * K9[i] + T8(A12_10) * K10[i] + T8(A12_11) * K2[i]);
+                        X[i] = x[i] + hg * (TN(RS12) * p[i] + h * (TN(AA12_1) * K1[i] + TN(AA12_3) * K3[i] + TN(AA12_4) * K4[i] + TN(AA12_5) * K5[i] + TN(AA12_6) * K6[i] + TN(AA12_7) * K7[i] + TN(AA12_8) * K8[i] + TN(AA12_9) * K9[i] + TN(AA12_10) * K10[i]));
+                    }
+                    tin = t + 1.0 * h;
+                }
+                break;
+            default:   // 13: new state, error estimate, accept/reject; FSAL evaluation for accepted lanes
+                if (active) {
+                    double err = 0, err2 = 0;
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        const double pn = p[i] + h * (T8(B1) * K1[i] + T8(B6) * K6[i] + T8(B7) * K7[i] + T8(B8) * K8[i] + T8(B9) * K9[i] + T8(B10) * K10[i] + T8(B11) * K2[i] + T8(B12) * kout[i]);
+                        const double xn = x[i] + hg * (TN(SB) * p[i] + h * (TN(BA1) * K1[i] + TN(BA6) * K6[i] + TN(BA7) * K7[i] + TN(BA8) * K8[i] + TN(BA9) * K9[i] + TN(BA10) * K10[i] + TN(BA11) * K2[i]));
+                        const double e5p = T8(ER1) * K1[i] + T8(ER6) * K6[i] + T8(ER7) * K7[i] + T8(ER8) * K8[i] + T8(ER9) * K9[i] + T8(ER10) * K10[i] + T8(ER11) * K2[i] + T8(ER12) * kout[i];
+                        const double e3p = TN(W1) * K1[i] + TN(W6) * K6[i] + TN(W7) * K7[i] + TN(W8) * K8[i] + TN(W9) * K9[i] + TN(W10) * K10[i] + TN(W11) * K2[i] + TN(W12) * kout[i];
+                        const double e5x = igm * (TN(SER) * p[i] + h * (TN(ERA1) * K1[i] + TN(ERA4) * K4[i] + TN(ERA5) * K5[i] + TN(ERA6) * K6[i] + TN(ERA7) * K7[i] + TN(ERA8) * K8[i] + TN(ERA9) * K9[i] + TN(ERA10) * K10[i] + TN(ERA11) * K2[i]));
+                        const double e3x = igm * (TN(SW) * p[i] + h * (TN(WA1) * K1[i] + TN(WA4) * K4[i] + TN(WA5) * K5[i] + TN(WA6) * K6[i] + TN(WA7) * K7[i] + TN(WA8) * K8[i] + TN(WA9) * K9[i] + TN(WA10) * K10[i] + TN(WA11) * K2[i]));
+                        const double iskx = fast_rcp(atol + rtol * fmax(fabs(x[i]), fabs(xn)));
+                        const double iskp = fast_rcp(atol + rtol * fmax(fabs(p[i]), fabs(pn)));
+                        const double a3 = e3x * iskx, b3 = e3p * iskp, a5 = e5x * iskx, b5 = e5p * iskp;
+                        err2 += a3 * a3 + b3 * b3; err += a5 * a5 + b5 * b5;
+                        X[i] = xn; P[i] = pn;
+                    }
+                    double deno = err + 0.01 * err2;
+                    if (deno <= 0.0) deno = 1.0;
+                    err = fabs(h) * err * fast_rsqrt(6 * deno);
+                    if (err <= 1.0) {
+                        // accepted.  The controller's new step is only consumed when the row continues.
+                        if (!last) {
+                            double fac11 = RAPT_POW(err, expo1);
+                            double fac = fac11 / ((facold == 1e-4) ? pf0 : RAPT_POW(facold, beta));
+                            fac = fmax(facc2, fmin(facc1, fac / safe));
+                            hnew = h / fac;
+                            if (fabs(hnew) > hmax) hnew = hmax;
+                            if (reject) hnew = fmin(fabs(hnew), fabs(h));
+                        }
+                        facold = fmax(err, 1e-4);
+                        naccpt++; naccpt_row++;
+                        accepted = true;
+                        tin = t + h;
+                    } else {
+                        if (a.p.dop853_reject_rule == 1) h = h / fmin(facc1, RAPT_POW(err, expo1) / safe);
+                        else h = h / facc1;                  // scipy 1.18.1: 0.3 h whatever err is
+                        reject = true;
+                        if (naccpt_row >= 1) nrejct++;
+                        last = false;
+                        active = false;
+                    }
+                }
+                break;
+            }
+            if (active) lorentz_K<F>(a.f, q, qg, tin, X, P, kout);
+        }
+        if (accepted) {
+            // FSAL: k1 = f(t+h, ynew); the step becomes the state
+#pragma unroll
+            for (int i = 0; i < 3; i++) { K1[i] = kout[i]; x[i] = X[i]; p[i] = P[i]; }
+            t = t + h;
+            if (last) {
+                // ---- output row complete (Particle.py:305-309)
+                rowidx++;
+                if (myrows && a.store_every > 0 && (rowidx % a.store_every) == 0 && nst < a.max_rows) {
+                    double2 *r = reinterpret_cast<double2 *>(myrows + (size_t)nst * 8);
+                    double tag = a.segtag ? (double)a.segtag[pid] : (double)nstep;
+                    r[0] = make_double2(xend, x[0]); r[1] = make_double2(x[1], x[2]);
+                    r[2] = make_double2(p[0], p[1]); r[3] = make_double2(p[2], tag);
+                    nst++;
+                }
+                if (a.p.check_adiabaticity) {
+                    const double yy[6] = {x[0], x[1], x[2], p[0], p[1], p[2]};
+                    if (particle_isadiabatic<F>(a.f, a.p, xend, yy, a.mass[pid], a.charge[pid])) st = ST_ADIABATIC;
+                }
+                need_row = true;
+            } else {
+                h = hnew;
+                reject = false;
+            }
+        }
+    }
+}
+
+}  // namespace RAPT_NS
