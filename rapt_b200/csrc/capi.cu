@@ -104,7 +104,7 @@ void fill_common(rapt::AdvArgs &a, const rapt_field_t *f, const rapt_params_t *p
 enum { UK_PARTICLE = 0, UK_GC, UK_PARTICLE_DT, UK_FIELD_OPS, UK_MISC, UK_BOUNCE, UK_ADAPT, UK_COUNT };
 const char *const k_user_kernel_exprs[UK_COUNT] = {
     "rapt_user::k_particle_dop853<rapt_user::Field<100> >",
-    "rapt_user::k_gc_dopri5<rapt_user::Field<100> >",
+    "rapt_user::k_gc_dopri5<rapt_user::Field<100>, 2>",
     "rapt_user::k_particle_dt<rapt_user::Field<100> >",
     "rapt_user::k_field_ops<rapt_user::Field<100> >",
     "rapt_user::k_misc<rapt_user::Field<100> >",

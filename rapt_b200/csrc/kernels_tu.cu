@@ -49,10 +49,15 @@ int particle_blocks_per_sm(int rkn)
 
 #ifdef RAPT_TU_GC
 #include "rapt_gc.cuh"
+#ifndef RAPT_GC_DEFAULT_BLOCKS
+#define RAPT_GC_DEFAULT_BLOCKS 3
+#endif
 namespace RAPT_NS {
+static int gc_minb() { const char *e = getenv("RAPT_B200_GC_BLOCKS"); return e ? atoi(e) : RAPT_GC_DEFAULT_BLOCKS; }
 template <int KIND> static cudaError_t go_gc(const rapt::AdvArgs &a, int grid, cudaStream_t s)
 {
-    k_gc_dopri5<Field<KIND>><<<grid, 128, 0, s>>>(a);
+    if (gc_minb() >= 3) k_gc_dopri5<Field<KIND>, 3><<<grid, 128, 0, s>>>(a);
+    else k_gc_dopri5<Field<KIND>, 2><<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_gc(const rapt::AdvArgs &a, int grid, cudaStream_t s)
@@ -70,7 +75,8 @@ cudaError_t launch_gc(const rapt::AdvArgs &a, int grid, cudaStream_t s)
 int gc_blocks_per_sm()
 {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gc_dopri5<Field<1>>, 128, 0);
+    if (gc_minb() >= 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gc_dopri5<Field<1>, 3>, 128, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gc_dopri5<Field<1>, 2>, 128, 0);
     return nb;
 }
 }  // namespace RAPT_NS

@@ -3,11 +3,12 @@
 // output row, beta -> 0.04, nsteps 500) with the three selectable equations of motion
 // (GuidingCenter.py:329-395) on the finite-difference operators of rapt/fields.py.
 //
-// Loop shape: the right-hand side (7 field evaluations + normalisations) dwarfs the stage
-// arithmetic, so the flat per-lane loop evaluates exactly ONE right-hand side per iteration and a
-// small state machine (stage) decides what the evaluation is for: the k1 of a fresh particle,
-// HINIT's Euler probe, or stage 2..7 of a step.  Lanes in different stages, rows or particles
-// therefore still execute the expensive code together; only the cheap stage bookkeeping diverges.
+// Loop shape (same as the particle kernel): a flat per-lane loop whose body is ONE step attempt; the
+// right-hand side (7 field evaluations + normalisations) has a single call site inside a warp-uniform,
+// non-unrolled stage loop (HINIT's Euler probe for lanes that start an output row, then stages 2..7).
+// The first version ran one RHS per iteration with a per-lane stage: the RHS stayed converged (29 of
+// 32 lanes) but the per-stage bookkeeping then executed once per distinct stage in the warp at ~5
+// lanes and cost as many issue slots as the RHS itself (profiles/r1_gc_v1_ncu_summary.txt).
 //
 // The reference evaluates curlb (6 x unitb) and gradB (6 x magB) at the SAME six shifted points
 // (fields.py:125-131, 191-200); unitb and magB of one point share B and sqrt(B.B), so evaluating each
@@ -159,38 +160,46 @@ RAPT_DEV bool gc_isadiabatic(const FieldP &f, const ParamsP &p, double t, const 
     return per / F::timescale(f, t, y[0], y[1], y[2]) < p.epst;
 }
 
-enum { S_FETCH = 0, S_K1, S_HINIT, S_2, S_3, S_4, S_5, S_6, S_7 };
+#if RAPT_STRICT
+#define RAPT_GC_POW(x, e) pow((x), (e))
+#else
+#define RAPT_GC_POW(x, e) exp((e) * log(x))     // x > 0; ~1e-15 relative, no slow paths
+#endif
 
-template <class F>
-__global__ void __launch_bounds__(128, 2) k_gc_dopri5(const AdvArgs a)
+// MINB = resident CTAs per SM the register allocation is tuned for (2: 255 regs, no spills; 3: 168 regs)
+template <class F, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
 {
     const double rtol = a.p.rtol, atol = a.p.atol;
     const int eqf = a.p.enforce_equatorial, eom = a.eom;
     const double beta = 0.04, safe = 0.9, fac1 = 0.2, fac2 = 10.0, uround = 2.3e-16;
     const double expo1 = 0.2 - beta * 0.75, facc1 = 1.0 / fac1, facc2 = 1.0 / fac2;
+    const double pf0 = pow(1e-4, beta);          // facold^beta at the first step of every row
 
     double y[4], k1[4], k2[4], k3[4], k4[4], k5[4], k6[4], y1[4], yin[4], kout[4];
     double x = 0, h = 0, xend = 0, tstop = 0, dt = 0, facold = 1e-4, hmax = 0, tin = 0, dnf = 0;
     GcConst gc = {0, 0, 0, 0};
-    int pid = -1, stage = S_FETCH;
+    int pid = -1;
     int nstep = 0, naccpt = 0, nrejct = 0, ncalls = 0, nstep_row = 0, naccpt_row = 0;
     int rowidx = 0, nst = 0, st = RAPT_ST_OK;
-    bool last = false, reject = false;
+    bool last = false, reject = false, need_row = false, have = false;
     double *myrows = nullptr;
 
     for (;;) {
-        if (stage == S_FETCH) {
-            if (pid >= 0) {      // write back the finished guiding centre
-                a.t[pid] = x; a.s1[pid] = y[0]; a.s2[pid] = y[1]; a.s3[pid] = y[2]; a.s4[pid] = y[3];
-                int *c = a.counters + 4 * (long long)pid;
-                int nf = 2 * ncalls + 6 * nstep;                 // as scipy counts: SURVEY.md §3.1
-                if (a.append) { c[0] += nf; c[1] += nstep; c[2] += naccpt; c[3] += nrejct; }
-                else { c[0] = nf; c[1] = nstep; c[2] = naccpt; c[3] = nrejct; }
-                a.status[pid] = st;
-                a.tcur[pid] = x;                                 // GuidingCenter.py:456
-                if (a.nrows) a.nrows[pid] = rowidx + 1;
-                a.nstored[pid] = nst;
-            }
+        // ---- (A) guiding centre finished?  write it back and fetch the next one
+        if (have && need_row && !(st == RAPT_ST_OK && x < tstop)) {
+            a.t[pid] = x; a.s1[pid] = y[0]; a.s2[pid] = y[1]; a.s3[pid] = y[2]; a.s4[pid] = y[3];
+            int *c = a.counters + 4 * (long long)pid;
+            int nf = 2 * ncalls + 6 * nstep;                     // as scipy counts: SURVEY.md §3.1
+            if (a.append) { c[0] += nf; c[1] += nstep; c[2] += naccpt; c[3] += nrejct; }
+            else { c[0] = nf; c[1] = nstep; c[2] = naccpt; c[3] = nrejct; }
+            a.status[pid] = st;
+            a.tcur[pid] = x;                                     // GuidingCenter.py:456
+            if (a.nrows) a.nrows[pid] = rowidx + 1;
+            a.nstored[pid] = nst;
+            have = false;
+        }
+        if (!have) {
             int w = atomicAdd(a.queue, 1);
             if (w >= a.nwork) break;
             pid = a.order ? a.order[w] : w;
@@ -212,85 +221,139 @@ __global__ void __launch_bounds__(128, 2) k_gc_dopri5(const AdvArgs a)
                     nst = 1;
                 }
             }
-            if (!(x < tstop)) { stage = S_FETCH; continue; }     // delta <= 0
-            tin = x;
-#pragma unroll
-            for (int i = 0; i < 4; i++) yin[i] = y[i];
-            stage = S_K1;
+            have = true; need_row = true;
+            if (!(x < tstop)) continue;                          // delta <= 0
+            gc_rhs<F>(a.f, gc, eom, eqf, x, y, k1);              // k1 = f(x, y)
         }
-
-        gc_rhs<F>(a.f, gc, eom, eqf, tin, yin, kout);
-
-        bool row_start = false, begin_step = false;
-        switch (stage) {
-        case S_K1:
+        // ---- (B) one step attempt; stage 1 = HINIT's Euler probe for lanes that start an output row
+        bool skip = false, hin = false;
+#pragma unroll 1
+        for (int s = 1; s <= 7; s++) {
+            bool active = !skip;
+            switch (s) {
+            case 1:
+                active = need_row;
+                if (active) {
+                    // new output row = new solver call: HINIT part 1
+                    xend = x + dt;                               // GuidingCenter.py:453
+                    hmax = fabs(xend - x);
+                    double dny = 0;
+                    dnf = 0;
 #pragma unroll
-            for (int i = 0; i < 4; i++) k1[i] = kout[i];
-            row_start = true;
-            break;
-        case S_HINIT: {
-            double der2 = 0;
+                    for (int i = 0; i < 4; i++) {
+                        double sk = atol + rtol * fabs(y[i]);
+                        dnf += (k1[i] / sk) * (k1[i] / sk);
+                        dny += (y[i] / sk) * (y[i] / sk);
+                    }
+                    h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
+                    h = fmin(h, hmax);
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                double sk = atol + rtol * fabs(y[i]);
-                der2 += ((kout[i] - k1[i]) / sk) * ((kout[i] - k1[i]) / sk);
+                    for (int i = 0; i < 4; i++) yin[i] = y[i] + h * k1[i];
+                    tin = x + h;
+                    hin = true;
+                }
+                break;
+            case 2:
+                if (hin) {
+                    double der2 = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        double sk = atol + rtol * fabs(y[i]);
+                        der2 += ((kout[i] - k1[i]) / sk) * ((kout[i] - k1[i]) / sk);
+                    }
+                    der2 = sqrt(der2) / h;
+                    double der12 = fmax(fabs(der2), sqrt(dnf));
+                    double h1;
+                    if (der12 <= 1e-15) h1 = fmax(1e-6, fabs(h) * 1e-3);
+                    else {
+                        // (0.01/der12)^(1/5) only matters when it is the smallest candidate
+                        double tq = 0.01 / der12, hm2 = hmax * hmax;
+                        if (tq > hm2 * hm2 * hmax * 1.000001) h1 = hmax;
+                        else h1 = pow(tq, 1.0 / 5.0);
+                    }
+                    h = fmin(fmin(100 * fabs(h), h1), hmax);
+                    facold = 1e-4; last = false; reject = false; nstep_row = 0; naccpt_row = 0;
+                    ncalls++;
+                    need_row = false;
+                }
+                if (nstep_row > 500) st = RAPT_ST_NMAX;
+                else if (0.1 * fabs(h) <= fabs(x) * uround) st = RAPT_ST_HSMALL;
+                if (st != RAPT_ST_OK) {
+                    rowidx++; need_row = true; skip = true; active = false;   // the failed row is still appended
+                } else {
+                    if ((x + 1.01 * h - xend) > 0.0) { h = xend - x; last = true; }
+                    nstep_row++; nstep++;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) yin[i] = y[i] + h * T5(A2_1) * k1[i];
+                    tin = x + T5(C2) * h;
+                }
+                break;
+            case 3:
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { k2[i] = kout[i]; yin[i] = y[i] + h * (T5(A3_1) * k1[i] + T5(A3_2) * k2[i]); }
+                    tin = x + T5(C3) * h;
+                }
+                break;
+            case 4:
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { k3[i] = kout[i]; yin[i] = y[i] + h * (T5(A4_1) * k1[i] + T5(A4_2) * k2[i] + T5(A4_3) * k3[i]); }
+                    tin = x + T5(C4) * h;
+                }
+                break;
+            case 5:
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { k4[i] = kout[i]; yin[i] = y[i] + h * (T5(A5_1) * k1[i] + T5(A5_2) * k2[i] + T5(A5_3) * k3[i] + T5(A5_4) * k4[i]); }
+                    tin = x + T5(C5) * h;
+                }
+                break;
+            case 6:
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { k5[i] = kout[i]; yin[i] = y[i] + h * (T5(A6_1) * k1[i] + T5(A6_2) * k2[i] + T5(A6_3) * k3[i] + T5(A6_4) * k4[i] + T5(A6_5) * k5[i]); }
+                    tin = x + h;
+                }
+                break;
+            default:  // 7: the new state; its right-hand side is both the 7th stage and the next k1 (FSAL)
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        k6[i] = kout[i];
+                        y1[i] = y[i] + h * (T5(A7_1) * k1[i] + T5(A7_3) * k3[i] + T5(A7_4) * k4[i] + T5(A7_5) * k5[i] + T5(A7_6) * k6[i]);
+                        yin[i] = y1[i];
+                    }
+                    tin = x + h;
+                }
+                break;
             }
-            der2 = sqrt(der2) / h;
-            double der12 = fmax(fabs(der2), sqrt(dnf));
-            double h1 = (der12 <= 1e-15) ? fmax(1e-6, fabs(h) * 1e-3) : pow(0.01 / der12, 1.0 / 5.0);
-            h = fmin(fmin(100 * fabs(h), h1), hmax);
-            facold = 1e-4; last = false; reject = false; nstep_row = 0; naccpt_row = 0;
-            ncalls++;
-            begin_step = true;
-            break; }
-        case S_2:
-#pragma unroll
-            for (int i = 0; i < 4; i++) { k2[i] = kout[i]; yin[i] = y[i] + h * (T5(A3_1) * k1[i] + T5(A3_2) * k2[i]); }
-            tin = x + T5(C3) * h; stage = S_3;
-            break;
-        case S_3:
-#pragma unroll
-            for (int i = 0; i < 4; i++) { k3[i] = kout[i]; yin[i] = y[i] + h * (T5(A4_1) * k1[i] + T5(A4_2) * k2[i] + T5(A4_3) * k3[i]); }
-            tin = x + T5(C4) * h; stage = S_4;
-            break;
-        case S_4:
-#pragma unroll
-            for (int i = 0; i < 4; i++) { k4[i] = kout[i]; yin[i] = y[i] + h * (T5(A5_1) * k1[i] + T5(A5_2) * k2[i] + T5(A5_3) * k3[i] + T5(A5_4) * k4[i]); }
-            tin = x + T5(C5) * h; stage = S_5;
-            break;
-        case S_5:
-#pragma unroll
-            for (int i = 0; i < 4; i++) { k5[i] = kout[i]; yin[i] = y[i] + h * (T5(A6_1) * k1[i] + T5(A6_2) * k2[i] + T5(A6_3) * k3[i] + T5(A6_4) * k4[i] + T5(A6_5) * k5[i]); }
-            tin = x + h; stage = S_6;
-            break;
-        case S_6:
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                k6[i] = kout[i];
-                y1[i] = y[i] + h * (T5(A7_1) * k1[i] + T5(A7_3) * k3[i] + T5(A7_4) * k4[i] + T5(A7_5) * k5[i] + T5(A7_6) * k6[i]);
-                yin[i] = y1[i];
-            }
-            tin = x + h; stage = S_7;
-            break;
-        case S_7: {
+            if (active) gc_rhs<F>(a.f, gc, eom, eqf, tin, yin, kout);
+        }
+        if (!skip) {
+            // ---- error estimate and step control
             double err = 0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                k2[i] = kout[i];
-                double e = (T5(E1) * k1[i] + T5(E3) * k3[i] + T5(E4) * k4[i] + T5(E5) * k5[i] + T5(E6) * k6[i] + T5(E7) * k2[i]) * h;
+                double e = (T5(E1) * k1[i] + T5(E3) * k3[i] + T5(E4) * k4[i] + T5(E5) * k5[i] + T5(E6) * k6[i] + T5(E7) * kout[i]) * h;
                 double sk = atol + rtol * fmax(fabs(y[i]), fabs(y1[i]));
                 err += (e / sk) * (e / sk);
             }
             err = sqrt(err / 4);
-            double fac11 = pow(err, expo1);
-            double fac = fac11 / pow(facold, beta);
-            fac = fmax(facc2, fmin(facc1, fac / safe));
-            double hnew = h / fac;
             if (err <= 1.0) {
+                double hnew = h;
+                if (!last) {
+                    double fac11 = RAPT_GC_POW(err, expo1);
+                    double fac = fac11 / ((facold == 1e-4) ? pf0 : RAPT_GC_POW(facold, beta));
+                    fac = fmax(facc2, fmin(facc1, fac / safe));
+                    hnew = h / fac;
+                    if (fabs(hnew) > hmax) hnew = hmax;
+                    if (reject) hnew = fmin(fabs(hnew), fabs(h));
+                }
                 facold = fmax(err, 1e-4);
                 naccpt++; naccpt_row++;
 #pragma unroll
-                for (int i = 0; i < 4; i++) { k1[i] = k2[i]; y[i] = y1[i]; }
+                for (int i = 0; i < 4; i++) { k1[i] = kout[i]; y[i] = y1[i]; }
                 x = x + h;
                 if (last) {
                     // ---- output row complete (GuidingCenter.py:453-458)
@@ -305,60 +368,18 @@ __global__ void __launch_bounds__(128, 2) k_gc_dopri5(const AdvArgs a)
                     if (a.p.check_adiabaticity) {
                         if (!gc_isadiabatic<F>(a.f, a.p, x, y, gc.mu, gc.mass, gc.q)) st = RAPT_ST_NONADIABATIC;
                     }
-                    if (st == RAPT_ST_OK && x < tstop) row_start = true;
-                    else stage = S_FETCH;
+                    need_row = true;
                 } else {
-                    if (fabs(hnew) > hmax) hnew = hmax;
-                    if (reject) hnew = fmin(fabs(hnew), fabs(h));
-                    reject = false;
                     h = hnew;
-                    begin_step = true;
+                    reject = false;
                 }
             } else {
-                hnew = h / fmin(facc1, fac11 / safe);
+                double fac11 = RAPT_GC_POW(err, expo1);
+                h = h / fmin(facc1, fac11 / safe);
                 reject = true;
                 if (naccpt_row >= 1) nrejct++;
                 last = false;
-                h = hnew;
-                begin_step = true;
             }
-            break; }
-        default: break;
-        }
-
-        if (row_start) {
-            // new output row = new solver call: HINIT part 1
-            xend = x + dt;                                       // GuidingCenter.py:453
-            hmax = fabs(xend - x);
-            double dny = 0;
-            dnf = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                double sk = atol + rtol * fabs(y[i]);
-                dnf += (k1[i] / sk) * (k1[i] / sk);
-                dny += (y[i] / sk) * (y[i] / sk);
-            }
-            h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
-            h = fmin(h, hmax);
-#pragma unroll
-            for (int i = 0; i < 4; i++) yin[i] = y[i] + h * k1[i];
-            tin = x + h;
-            stage = S_HINIT;
-        }
-        if (begin_step) {
-            if (nstep_row > 500) st = RAPT_ST_NMAX;
-            else if (0.1 * fabs(h) <= fabs(x) * uround) st = RAPT_ST_HSMALL;
-            if (st != RAPT_ST_OK) {
-                rowidx++;                                         // the failed row is still appended
-                stage = S_FETCH;
-                continue;
-            }
-            if ((x + 1.01 * h - xend) > 0.0) { h = xend - x; last = true; }
-            nstep_row++; nstep++;
-#pragma unroll
-            for (int i = 0; i < 4; i++) yin[i] = y[i] + h * T5(A2_1) * k1[i];
-            tin = x + T5(C2) * h;
-            stage = S_2;
         }
     }
 }

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(128, 3) k_particle_rkn(const AdvArgs a)
     const double expo1 = 1.0 / 8.0 - beta * 0.2, facc1 = 1.0 / fac1, facc2 = 1.0 / fac2;
     const double pf0 = pow(1e-4, beta);
 
+    double sb_[3];
     double x[3], p[3], K1[3], K2[3], K3[3], K4[3], K5[3], K6[3], K7[3], K8[3], K9[3], K10[3], X[3], P[3], kout[3];
     double t = 0, h = 0, hg = 0, xend = 0, tstop = 0, dt = 0, facold = 1e-4, hmax = 0, tin = 0, dnf = 0, hnew = 0;
     double igm = 1, qg = 0, q = 0;
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(128, 3) k_particle_rkn(const AdvArgs a)
         // ---- (B) one step attempt; stage 1 = HINIT's Euler probe for lanes that start an output row
         bool accepted = false, skip = false, hin = false;
 #pragma unroll 1
-        for (int s = 1; s <= 13; s++) {
+        for (int s = 1; s <= 14; s++) {
             bool active = !skip;
             switch (s) {
             case 1:
@@ -280,22 +281,32 @@ __global__ void __launch_bounds__(128, 3) k_particle_rkn(const AdvArgs a)
                     tin = t + 1.0 * h;
                 }
                 break;
-            default:   // 13: new state, error estimate, accept/reject; FSAL evaluation for accepted lanes
+            case 13:
+                // new state (b-weights); kept in X, P: it is also the input of the FSAL evaluation.
+                // No field evaluation in this pass (its own basic block keeps the coefficient set small).
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        sb_[i] = T8(B1) * K1[i] + T8(B6) * K6[i] + T8(B7) * K7[i] + T8(B8) * K8[i] + T8(B9) * K9[i] + T8(B10) * K10[i] + T8(B11) * K2[i] + T8(B12) * kout[i];
+                        P[i] = p[i] + h * sb_[i];
+                        X[i] = x[i] + hg * (TN(SB) * p[i] + h * (TN(BA1) * K1[i] + TN(BA6) * K6[i] + TN(BA7) * K7[i] + TN(BA8) * K8[i] + TN(BA9) * K9[i] + TN(BA10) * K10[i] + TN(BA11) * K2[i]));
+                    }
+                }
+                active = false;
+                break;
+            default:   // 14: error estimate, accept/reject; FSAL evaluation for accepted lanes
                 if (active) {
                     double err = 0, err2 = 0;
 #pragma unroll
                     for (int i = 0; i < 3; i++) {
-                        const double pn = p[i] + h * (T8(B1) * K1[i] + T8(B6) * K6[i] + T8(B7) * K7[i] + T8(B8) * K8[i] + T8(B9) * K9[i] + T8(B10) * K10[i] + T8(B11) * K2[i] + T8(B12) * kout[i]);
-                        const double xn = x[i] + hg * (TN(SB) * p[i] + h * (TN(BA1) * K1[i] + TN(BA6) * K6[i] + TN(BA7) * K7[i] + TN(BA8) * K8[i] + TN(BA9) * K9[i] + TN(BA10) * K10[i] + TN(BA11) * K2[i]));
                         const double e5p = T8(ER1) * K1[i] + T8(ER6) * K6[i] + T8(ER7) * K7[i] + T8(ER8) * K8[i] + T8(ER9) * K9[i] + T8(ER10) * K10[i] + T8(ER11) * K2[i] + T8(ER12) * kout[i];
-                        const double e3p = TN(W1) * K1[i] + TN(W6) * K6[i] + TN(W7) * K7[i] + TN(W8) * K8[i] + TN(W9) * K9[i] + TN(W10) * K10[i] + TN(W11) * K2[i] + TN(W12) * kout[i];
+                        const double e3p = sb_[i] - T8(BHH1) * K1[i] - T8(BHH2) * K9[i] - T8(BHH3) * kout[i];
                         const double e5x = igm * (TN(SER) * p[i] + h * (TN(ERA1) * K1[i] + TN(ERA4) * K4[i] + TN(ERA5) * K5[i] + TN(ERA6) * K6[i] + TN(ERA7) * K7[i] + TN(ERA8) * K8[i] + TN(ERA9) * K9[i] + TN(ERA10) * K10[i] + TN(ERA11) * K2[i]));
                         const double e3x = igm * (TN(SW) * p[i] + h * (TN(WA1) * K1[i] + TN(WA4) * K4[i] + TN(WA5) * K5[i] + TN(WA6) * K6[i] + TN(WA7) * K7[i] + TN(WA8) * K8[i] + TN(WA9) * K9[i] + TN(WA10) * K10[i] + TN(WA11) * K2[i]));
-                        const double iskx = fast_rcp(atol + rtol * fmax(fabs(x[i]), fabs(xn)));
-                        const double iskp = fast_rcp(atol + rtol * fmax(fabs(p[i]), fabs(pn)));
+                        const double iskx = fast_rcp(atol + rtol * fmax(fabs(x[i]), fabs(X[i])));
+                        const double iskp = fast_rcp(atol + rtol * fmax(fabs(p[i]), fabs(P[i])));
                         const double a3 = e3x * iskx, b3 = e3p * iskp, a5 = e5x * iskx, b5 = e5p * iskp;
                         err2 += a3 * a3 + b3 * b3; err += a5 * a5 + b5 * b5;
-                        X[i] = xn; P[i] = pn;
                     }
                     double deno = err + 0.01 * err2;
                     if (deno <= 0.0) deno = 1.0;

@@ -1,0 +1,124 @@
+"""GPU: size-independent properties at the BASELINE.json ensemble sizes (1 M tracers), where the CPU
+oracle cannot be run in full: invariants of the motion, independence from scheduling (work order,
+permutation of the input, host vs device buffers), decimation consistency, failure statuses."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from rapt_b200 import engine, _lib
+    _lib.init(0)
+    return engine
+
+
+def config2_state(eng, n):
+    from rapt_b200 import synth
+    ic = synth.config2_protons(n)
+    vel = np.column_stack([ic["vx"], ic["vy"], ic["vz"]])
+    return np.column_stack([ic["t0"], ic["x"], ic["y"], ic["z"], eng.particle_momentum(vel, ic["mass"])]), ic
+
+
+def test_config2_full_size_invariants_and_scheduling(eng):
+    """1,048,576 protons (config 2), advance(1 s): |p| conserved (static B), every tracer reaches t0+delta,
+    and the result does not depend on the work order (longest-first sort on/off -> bit-identical)."""
+    n = 1 << 20
+    st, ic = config2_state(eng, n)
+    f = H.gpu_field("EarthDipole", ())
+    a = eng.particle_advance(f, st, ic["mass"], ic["charge"], 1.0, store_every=0, cyclotronresolution=20, sort_by_work=1)
+    b = eng.particle_advance(f, st, ic["mass"], ic["charge"], 1.0, store_every=0, cyclotronresolution=20, sort_by_work=0)
+    assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["counters"], b["counters"])
+    assert np.all(a["status"] == 1)
+    assert np.all(a["state"][:, 0] >= 1.0) and np.all(a["state"][:, 0] < 1.0 + a["dt"] * (1 + 1e-12))
+    assert np.array_equal(a["nrows"], 1 + np.ceil(np.round(1.0 / a["dt"], 9)).astype(np.int64)) or \
+        np.max(np.abs(a["nrows"] - (1 + np.ceil(1.0 / a["dt"])))) <= 1
+    p0 = np.linalg.norm(st[:, 4:7], axis=1); p1 = np.linalg.norm(a["state"][:, 4:7], axis=1)
+    assert np.max(np.abs(p1 / p0 - 1)) < 2e-4          # momentum is not error-controlled (SI atol, quirk Q5)
+    assert np.median(np.abs(p1 / p0 - 1)) < 1e-8
+    # scipy's counter identity nfcn = 2*calls + 11*nstep + naccpt
+    c = a["counters"].astype(np.int64)
+    assert np.array_equal(c[:, 0], 2 * (a["nrows"].astype(np.int64) - 1) + 11 * c[:, 1] + c[:, 2])
+    assert np.all(c[:, 1] >= c[:, 2]) and np.all(c[:, 2] >= a["nrows"] - 1)
+    # first adiabatic invariant of a subsample: conserved to the guiding-centre approximation's accuracy
+    sub = slice(0, 4096)
+    _, mu0, _, s0 = eng.switch_p2g(f, st[sub], ic["mass"][sub], ic["charge"][sub])
+    _, mu1, _, s1 = eng.switch_p2g(f, a["state"][sub], ic["mass"][sub], ic["charge"][sub])
+    ok = (s0 == 0) & (s1 == 0)
+    assert ok.mean() > 0.99
+    assert np.median(np.abs(mu1[ok] / mu0[ok] - 1)) < 0.05
+
+
+def test_permutation_invariance_and_fast_vs_strict(eng):
+    """Per-particle results do not depend on which lane / which order a tracer is integrated in."""
+    n = 50000
+    st, ic = config2_state(eng, n)
+    f = H.gpu_field("EarthDipole", ())
+    a = eng.particle_advance(f, st, ic["mass"], ic["charge"], 0.3, store_every=0, cyclotronresolution=20)
+    perm = np.random.default_rng(1).permutation(n)
+    b = eng.particle_advance(f, st[perm], ic["mass"][perm], ic["charge"][perm], 0.3, store_every=0, cyclotronresolution=20)
+    assert np.array_equal(a["state"][perm], b["state"]) and np.array_equal(a["counters"][perm], b["counters"])
+    s = eng.particle_advance(f, st, ic["mass"], ic["charge"], 0.3, store_every=0, cyclotronresolution=20, arith="strict")
+    assert H.vec_relerr(a["state"][:, 1:4], s["state"][:, 1:4]) < 1e-8
+    assert H.vec_relerr(a["state"][:, 4:7], s["state"][:, 4:7]) < 1e-8
+    assert (a["counters"][:, 1] == s["counters"][:, 1]).mean() > 0.995
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_decimation_and_row_cap(eng, arith):
+    n = 300
+    st, ic = config2_state(eng, n)
+    f = H.gpu_field("EarthDipole", ())
+    kw = dict(cyclotronresolution=20, arith=arith)
+    full = eng.particle_advance(f, st, ic["mass"], ic["charge"], 0.05, store_every=1, max_rows=256, **kw)
+    dec = eng.particle_advance(f, st, ic["mass"], ic["charge"], 0.05, store_every=3, max_rows=256, **kw)
+    cap = eng.particle_advance(f, st, ic["mass"], ic["charge"], 0.05, store_every=1, max_rows=5, **kw)
+    assert np.array_equal(full["state"], dec["state"]) and np.array_equal(full["state"], cap["state"])
+    assert np.all(full["nstored"] == full["nrows"]) and np.all(full["nrows"] <= 256)
+    for i in (0, 7, 299):
+        k = int(full["nstored"][i]); kd = int(dec["nstored"][i])
+        assert np.array_equal(dec["rows"][i, :kd, :7], full["rows"][i, :k:3, :7])
+        assert np.array_equal(dec["rows"][i, :kd, 7], full["rows"][i, :k:3, 7])       # cumulative step counter
+        assert np.array_equal(full["rows"][i, k - 1, :7], full["state"][i])
+        assert np.all(np.diff(full["rows"][i, :k, 7]) >= 1)
+    assert np.all(cap["nstored"] == np.minimum(cap["nrows"], 5)) and np.array_equal(cap["nrows"], full["nrows"])
+
+
+def test_solver_failure_status(eng):
+    """nsteps = 500 per output interval: an absurdly long output step fails like scipy (-2) and the row
+    loop ends after appending the failed row (Particle.py:304-307)."""
+    import oracle as O
+    d, par = H.load("g1b_generic")
+    f = H.gpu_field("EarthDipole", ())
+    o = eng.particle_advance(f, d["traj"][0], float(d["mass"]), float(d["charge"]), 1e6, store_every=1, max_rows=4,
+                             cyclotronresolution=1e-4, arith="strict")
+    r = O.particle_advance(O.make_field("EarthDipole"), O.make_params(cyclotronresolution=1e-4), d["traj"][0], float(d["mass"]),
+                           float(d["charge"]), 1e6, max_rows=4)
+    assert o["status"][0] == -2 == r["status"][0]
+    assert o["nrows"][0] == 2 == r["nrows"][0]
+    assert o["counters"][0, 1] == r["counters"][0, 1] == 501
+
+
+def test_gc_full_size_energy_conservation(eng):
+    """262,144 electrons of config 3 (DoubleDipole, static): kinetic energy of the guiding centre is a
+    constant of the Tao-Chan-Brizard equations; check it after 5 s of bounce + drift."""
+    from rapt_b200 import synth, c
+    n = 1 << 18
+    ic = synth.config3_electrons(n)
+    f = H.gpu_field("DoubleDipole", ())
+    pos = np.column_stack([ic["x"], ic["y"], ic["z"]])
+    ppar, mu = eng.gc_construct(f, ic["t0"], pos, ic["v"], ic["pa"], ic["mass"])
+    st = np.column_stack([ic["t0"], pos, ppar])
+    o = eng.gc_advance(f, st, mu, ic["v"], ic["mass"], ic["charge"], 0.1, 5.0, store_every=0)
+    assert np.all(o["status"] == 1) and np.all(o["nrows"] == 51)
+
+    def gamma(state):
+        Bm = eng.field_ops(f, state[:, :4], which=["magB"])["magB"]
+        mc = ic["mass"] * c
+        return np.sqrt(1 + 2 * mu * Bm / (mc * c) + (state[:, 4] / mc) ** 2)
+    g0, g1 = gamma(st), gamma(o["state"])
+    assert np.max(np.abs((g1 - 1) / (g0 - 1) - 1)) < 1e-4
+    assert np.median(np.abs((g1 - 1) / (g0 - 1) - 1)) < 1e-6
