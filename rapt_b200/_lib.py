@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librapt_b200.so")
+LIB_PATH = os.environ.get("RAPT_B200_LIB", os.path.join(_HERE, "librapt_b200.so"))   # override: A/B builds
 
 RAPT_OK = 0
 FIELD_KIND = {"EarthDipole": 0, "DoubleDipole": 1, "UniformBz": 2, "UniformCrossedEB": 3,

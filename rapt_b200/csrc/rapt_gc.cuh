@@ -28,11 +28,12 @@ RAPT_DEV void mag_and_unit(const FieldP &f, double t, double x, double y, double
                            double &m, double &ux, double &uy, double &uz)
 {
     double bx, by, bz; F::B(f, t, x, y, z, bx, by, bz);
-    m = sqrt(dot3(bx, by, bz, bx, by, bz));
 #if RAPT_STRICT
+    m = sqrt(dot3(bx, by, bz, bx, by, bz));
     ux = bx / m; uy = by / m; uz = bz / m;
 #else
-    double im = fast_rcp(m);
+    const double bb = dot3(bx, by, bz, bx, by, bz), im = fast_rsqrt(bb);
+    m = bb * im;
     ux = bx * im; uy = by * im; uz = bz * im;
 #endif
 }
@@ -82,6 +83,58 @@ RAPT_DEV void gc_rhs(const FieldP &f, const GcConst &c, int eom, int equatorial,
     const double m = c.mass, q = c.q, mu = c.mu, ppar = Y[3];
     double bx, by, bz, gB[3], cb[3];
     F::B(f, t, Y[0], Y[1], Y[2], bx, by, bz);
+#if !RAPT_STRICT
+    // fast flavour: one rsqrt for |B| and b, reciprocals instead of divisions
+    const double bb = dot3(bx, by, bz, bx, by, bz), ib = fast_rsqrt(bb);
+    const double Bmag = bb * ib;
+    const double ux = bx * ib, uy = by * ib, uz = bz * ib;
+    const double iq = fast_rcp(q);
+    grad_and_curl<F>(f, t, Y[0], Y[1], Y[2], gB, cb);
+    if (eom == 0) {
+        const double pm = ppar / (m * RAPT_C_LIGHT);
+        const double g2 = 1 + 2 * mu * Bmag / (m * RAPT_C_LIGHT * RAPT_C_LIGHT) + pm * pm;
+        const double ig = fast_rsqrt(g2);                          // 1/gamma
+        const double pq = ppar * iq;
+        const double Bsx = fma(pq, cb[0], bx), Bsy = fma(pq, cb[1], by), Bsz = fma(pq, cb[2], bz);
+        const double iBsp = fast_rcp(dot3(Bsx, Bsy, Bsz, ux, uy, uz));
+        double ex = 0, ey = 0, ez = 0, dbx = 0, dby = 0, dbz = 0;
+        if (F::HAS_E) F::E(f, t, Y[0], Y[1], Y[2], ex, ey, ez);
+        if (F::TIME_DEP) { if (!f.is_static) F::dbdt(f, t, Y[0], Y[1], Y[2], dbx, dby, dbz); }
+        const double mg = mu * ig;
+        const double Esx = ex - (ppar * dbx + mg * gB[0]) * iq;
+        const double Esy = ey - (ppar * dby + mg * gB[1]) * iq;
+        const double Esz = ez - (ppar * dbz + mg * gB[2]) * iq;
+        const double cx = Esy * uz - Esz * uy, cy = Esz * ux - Esx * uz, cz = Esx * uy - Esy * ux;
+        const double pgm = ppar * ig / m;
+        out[0] = fma(pgm, Bsx, cx) * iBsp;
+        out[1] = fma(pgm, Bsy, cy) * iBsp;
+        out[2] = fma(pgm, Bsz, cz) * iBsp;
+        out[3] = q * dot3(Esx, Esy, Esz, Bsx, Bsy, Bsz) * iBsp;
+    } else if (eom == 1) {
+        const double vc = c.v / RAPT_C_LIGHT;
+        const double ig = sqrt(1 - vc * vc);                       // 1/gamma
+        const double pq = ppar * iq;
+        const double Bsx = fma(pq, cb[0], bx), Bsy = fma(pq, cb[1], by), Bsz = fma(pq, cb[2], bz);
+        const double iBsp = fast_rcp(dot3(Bsx, Bsy, Bsz, ux, uy, uz));
+        const double cx = uy * gB[2] - uz * gB[1], cy = uz * gB[0] - ux * gB[2], cz = ux * gB[1] - uy * gB[0];
+        const double pgm = ppar * ig / m, mqg = mu * iq * ig;
+        out[0] = fma(pgm, Bsx, mqg * cx) * iBsp;
+        out[1] = fma(pgm, Bsy, mqg * cy) * iBsp;
+        out[2] = fma(pgm, Bsz, mqg * cz) * iBsp;
+        out[3] = -mu * dot3(Bsx, Bsy, Bsz, gB[0], gB[1], gB[2]) * ig * iBsp;
+    } else {
+        const double vc = c.v / RAPT_C_LIGHT;
+        const double ig = sqrt(1 - vc * vc);
+        const double igm = ig / m, gm = m / ig;
+        const double cx = uy * gB[2] - uz * gB[1], cy = uz * gB[0] - ux * gB[2], cz = ux * gB[1] - uy * gB[0];
+        const double s = (gm * (c.v * c.v) + ppar * ppar * igm) * 0.5 * iq * (ib * ib);
+        const double pg = ppar * igm;
+        out[0] = fma(s, cx, pg * ux);
+        out[1] = fma(s, cy, pg * uy);
+        out[2] = fma(s, cz, pg * uz);
+        out[3] = -mu * dot3(ux, uy, uz, gB[0], gB[1], gB[2]) * ig;
+    }
+#else
     const double Bmag = sqrt(dot3(bx, by, bz, bx, by, bz));
     const double ux = bx / Bmag, uy = by / Bmag, uz = bz / Bmag;
     grad_and_curl<F>(f, t, Y[0], Y[1], Y[2], gB, cb);
@@ -124,6 +177,7 @@ RAPT_DEV void gc_rhs(const FieldP &f, const GcConst &c, int eom, int equatorial,
         out[2] = s * cz + ppar * uz / gm;
         out[3] = -mu * dot3(ux, uy, uz, gB[0], gB[1], gB[2]) / gamma;
     }
+#endif
     if (equatorial) { out[2] = 0; out[3] = 0; }
 }
 
@@ -241,9 +295,15 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
                     dnf = 0;
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
+#if RAPT_STRICT
                         double sk = atol + rtol * fabs(y[i]);
                         dnf += (k1[i] / sk) * (k1[i] / sk);
                         dny += (y[i] / sk) * (y[i] / sk);
+#else
+                        const double is_ = fast_rcp(atol + rtol * fabs(y[i]));
+                        const double a_ = k1[i] * is_, b_ = y[i] * is_;
+                        dnf += a_ * a_; dny += b_ * b_;
+#endif
                     }
                     h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
                     h = fmin(h, hmax);
@@ -258,8 +318,13 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
                     double der2 = 0;
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
+#if RAPT_STRICT
                         double sk = atol + rtol * fabs(y[i]);
                         der2 += ((kout[i] - k1[i]) / sk) * ((kout[i] - k1[i]) / sk);
+#else
+                        const double d_ = (kout[i] - k1[i]) * fast_rcp(atol + rtol * fabs(y[i]));
+                        der2 += d_ * d_;
+#endif
                     }
                     der2 = sqrt(der2) / h;
                     double der12 = fmax(fabs(der2), sqrt(dnf));
@@ -336,8 +401,13 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 double e = (T5(E1) * k1[i] + T5(E3) * k3[i] + T5(E4) * k4[i] + T5(E5) * k5[i] + T5(E6) * k6[i] + T5(E7) * kout[i]) * h;
+#if RAPT_STRICT
                 double sk = atol + rtol * fmax(fabs(y[i]), fabs(y1[i]));
                 err += (e / sk) * (e / sk);
+#else
+                e *= fast_rcp(atol + rtol * fmax(fabs(y[i]), fabs(y1[i])));
+                err += e * e;
+#endif
             }
             err = sqrt(err / 4);
             if (err <= 1.0) {
