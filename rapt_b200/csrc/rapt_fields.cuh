@@ -137,6 +137,25 @@ template <int KIND> struct Field {
         else { bx = by = bz = 0; }
     }
 
+    // sc * B(t, x): the Lorentz kernels need q/(gamma m) * B; folding the factor into the dipole coefficient
+    // saves three multiplies per evaluation (fast flavour only)
+    static RAPT_DEV void Bs(const FieldP &f, double sc, double t, double x, double y, double z,
+                            double &bx, double &by, double &bz)
+    {
+#if !RAPT_STRICT
+        if (KIND == 0) {
+            const double r2 = x * x + y * y + z * z;
+            const double ir = fast_rsqrt(r2), ir2 = ir * ir;
+            const double w = (sc * f.prm[0] * ir) * (ir2 * ir2);
+            const double wz = w * z;
+            bx = wz * x; by = wz * y; bz = w * fma(z, z, -(1.0 / 3.0) * r2);
+            return;
+        }
+#endif
+        B(f, t, x, y, z, bx, by, bz);
+        bx *= sc; by *= sc; bz *= sc;
+    }
+
     static RAPT_DEV void E(const FieldP &f, double t, double x, double y, double z,
                            double &ex, double &ey, double &ez)
     {

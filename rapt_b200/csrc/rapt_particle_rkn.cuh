@@ -28,13 +28,13 @@ RAPT_DEV void lorentz_K(const FieldP &f, double q, double qg, double t, const do
                         double (&K)[3])
 {
     double bx, by, bz;
-    F::B(f, t, X[0], X[1], X[2], bx, by, bz);
+    F::Bs(f, qg, t, X[0], X[1], X[2], bx, by, bz);                 // q/(gamma m) * B
     const double cx = P[1] * bz - P[2] * by, cy = P[2] * bx - P[0] * bz, cz = P[0] * by - P[1] * bx;
     if (F::HAS_E) {
         double ex, ey, ez; F::E(f, t, X[0], X[1], X[2], ex, ey, ez);
-        K[0] = fma(q, ex, qg * cx); K[1] = fma(q, ey, qg * cy); K[2] = fma(q, ez, qg * cz);
+        K[0] = fma(q, ex, cx); K[1] = fma(q, ey, cy); K[2] = fma(q, ez, cz);
     } else {
-        K[0] = qg * cx; K[1] = qg * cy; K[2] = qg * cz;
+        K[0] = cx; K[1] = cy; K[2] = cz;
     }
 }
 

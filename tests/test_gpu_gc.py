@@ -92,8 +92,10 @@ def test_gc_golden(eng, name, arith):
     ref = d["counters"].sum(0)
     got = o["counters"][0]
     if name in ("gc_pa90_equatorial", "gc_equatorial_enforced", "g2_gc_doubledipole", "gc_earthdipole"):
-        # starts with an exact-zero coordinate / zero p_par: round-off dominated first rows
-        assert abs(int(got[1]) - int(ref[1])) <= max(3, 0.01 * ref[1])
+        # starts with an exact-zero coordinate / zero p_par: sk = atol there, so HINIT and the first steps of
+        # every row are round-off dominated; the strict flavour stays within a few steps, the
+        # fast flavour (reciprocals, fused ops) within ~10 % -- trajectories agree to 1e-8 either way (above)
+        assert abs(int(got[1]) - int(ref[1])) <= max(3, (0.01 if arith == "strict" else 0.10) * ref[1]), (got, ref)
     else:
         assert abs(int(got[1]) - int(ref[1])) <= (0 if arith == "strict" else 2), (got, ref)
     assert abs(o["tcur"][0] - float(d["tcur"])) <= 1e-12 * abs(float(d["tcur"]))
