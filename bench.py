@@ -267,7 +267,9 @@ def main():
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
+            ts = time.perf_counter()
             host_step()
+            print(f"[e2e] host-buffer step {1e3 * (time.perf_counter() - ts):.1f} ms", file=sys.stderr)
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
         tt = torch.tensor([el], dtype=torch.float64, device=dev)
@@ -305,7 +307,13 @@ def main():
             "gpu_launches": int(launches),
             "wall_s_timed_region": wall,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak, "traffic": None,
+                         "frac": achieved / fp64_peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this configuration, one
+                         # launch, from `ncu --set full` (profiles/r1_particle_v6_bench_kernel_ncu_summary.txt):
+                         # 522 MB + 310 MB.  4.6x the algorithmic state I/O because tracers are fetched in
+                         # longest-first order, i.e. as scattered 8-byte accesses (32-byte sectors); at 0.36 s
+                         # per launch that is 2 GB/s and irrelevant to this compute-bound kernel.
+                         "traffic": 831857152 if (n == N_PER_GPU and args.delta == DELTA) else None,
                          "peak_source": "FP64 DFMA microbenchmark measured in this run (rapt_b200_fp64_peak); "
                                         "MEASURED_PEAKS.json has HBM and bf16 only",
                          "algorithmic_flop_per_step": flops / nstep,

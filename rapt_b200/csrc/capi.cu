@@ -66,11 +66,13 @@ int *next_queue(cudaStream_t s)
 }
 
 // RAII device buffer for the host-pointer entry points
+// Stream-ordered allocations from the device's default memory pool (release threshold raised in
+// rapt_b200_init, so repeated calls reuse the same memory instead of paying cudaMalloc/cudaFree).
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t b) { bytes = b; return b ? cudaMalloc(&p, b) : cudaSuccess; }
+    ~DevBuf() { if (p) cudaFreeAsync(p, 0); }
+    cudaError_t alloc(size_t b) { bytes = b; return b ? cudaMallocAsync(&p, b, 0) : cudaSuccess; }
     template <class T> T *as() { return static_cast<T *>(p); }
 };
 
@@ -339,6 +341,11 @@ int rapt_b200_init(int device)
     }
     g_device = device;
     g_sms = prop.multiProcessorCount;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     return RAPT_OK;
 }
 

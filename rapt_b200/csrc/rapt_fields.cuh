@@ -37,7 +37,7 @@ RAPT_DEV double dot3(double ax, double ay, double az, double bx, double by, doub
 RAPT_DEV double sgn(double z) { return z > 0 ? 1.0 : (z < 0 ? -1.0 : 0.0); }
 
 // Branch-free reciprocal and reciprocal square root for the fast flavour: MUFU seed (~2^-22) refined
-// to ~1 ulp with fused Newton steps.  No denormal / special-case slow paths -- every argument on the
+// to 1-2 ulp with fused Newton steps.  No denormal / special-case slow paths -- every argument on the
 // hot path (r^2, |B|^2, error scales, gamma*m) is a normal, strictly positive number.
 RAPT_DEV double fast_rcp(double x)
 {
@@ -53,9 +53,16 @@ RAPT_DEV double fast_rsqrt(double x)
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-(x * y), y, 1.0);                 // 1 - x y^2  (~2^-22)
-    y = fma(y * e, fma(0.375, e, 0.5), y);            // y (1 + e/2 + 3e^2/8): cubic -> ~2^-66
-    e = fma(-(x * y), y, 1.0);                        // one more linear polish for the last bits
+#ifdef RAPT_RSQRT_POLISH
+    y = fma(y * e, fma(0.375, e, 0.5), y);
+    e = fma(-(x * y), y, 1.0);                        // optional linear polish: last-bit accuracy
     return fma(0.5 * y, e, y);
+#else
+    // y (1 + e/2 + 3e^2/8): cubic convergence, 2^-22 -> ~2^-66, i.e. ~2 ulp after rounding.  The extra
+    // polish step (4 more FP64 instructions per field evaluation) bought nothing in the parity tests and
+    // cost 6 % of the config-2 run time (profiles/r1_particle_history.md).
+    return fma(y * e, fma(0.375, e, 0.5), y);
+#endif
 }
 
 #ifdef RAPT_USER_FIELD
