@@ -59,6 +59,7 @@ extern "C" {
 #define RAPT_ST_OK            1   /* advance() ran to t0+delta                                     */
 #define RAPT_ST_ADIABATIC     2   /* Particle: `raise Adiabatic`   (Particle.py:308-309)           */
 #define RAPT_ST_NONADIABATIC  3   /* GuidingCenter: `raise NonAdiabatic` (GuidingCenter.py:457-458)*/
+#define RAPT_ST_SLICE         4   /* internal to adaptive epochs: interrupted at a row boundary, resumed later */
 #define RAPT_ST_NMAX         -2   /* dop: more than nsteps=500 steps in one output interval        */
 #define RAPT_ST_HSMALL       -3   /* dop: step size underflow                                      */
 #define RAPT_ST_GCITER       -5   /* utils.guidingcenter did not converge (utils.py:326)           */

@@ -748,12 +748,15 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
     const double *h[9] = {x, y, z, vx, vy, vz, t0, mass, charge};
     for (int k = 0; k < 9; k++) CK(up(in[k], h[k], nb, s0));
     DevBuf ps[7], gs[7], dmode, dst, dnseg, dtag, dnst, dtvar, drem, dtcur, drows, dlp, dlg, dcounts, dcnt, ddtg, ddtp;
+    DevBuf dsts, dsx, dsdt, dsrow;
     for (int k = 0; k < 7; k++) { CK(ps[k].alloc(nb)); CK(gs[k].alloc(nb)); CK(cudaMemsetAsync(gs[k].p, 0, nb, s0)); CK(cudaMemsetAsync(ps[k].p, 0, nb, s0)); }
     CK(dmode.alloc(ni)); CK(dst.alloc(ni)); CK(dnseg.alloc(ni)); CK(dtag.alloc(ni)); CK(dnst.alloc(ni));
     CK(dtvar.alloc(nb)); CK(drem.alloc(nb)); CK(dtcur.alloc(nb));
     CK(drows.alloc(want_rows ? (size_t)n * max_rows * 8 * sizeof(double) : 0));
     CK(dlp.alloc(ni)); CK(dlg.alloc(ni)); CK(dcounts.alloc(2 * sizeof(int))); CK(dcnt.alloc(4 * ni));
     CK(ddtg.alloc(nb)); CK(ddtp.alloc(nb));
+    CK(dsts.alloc(nb)); CK(dsx.alloc(nb)); CK(dsdt.alloc(nb)); CK(dsrow.alloc(ni));
+    CK(cudaMemsetAsync(dsts.p, 0, nb, s0)); CK(cudaMemsetAsync(dsx.p, 0, nb, s0)); CK(cudaMemsetAsync(dsdt.p, 0, nb, s0)); CK(cudaMemsetAsync(dsrow.p, 0, ni, s0));
     CK(cudaMemsetAsync(dcnt.p, 0, 4 * ni, s0)); CK(cudaMemsetAsync(dcounts.p, 0, 2 * sizeof(int), s0));
     {   // per-tracer GC output step (uniform: params["GCtimestep"])
         std::vector<double> hd((size_t)n, gc_dt);
@@ -775,6 +778,7 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
     sw.nstored = dnst.as<int>(); sw.tvar = dtvar.as<double>(); sw.rem = drem.as<double>(); sw.tcur = dtcur.as<double>();
     sw.max_rows = want_rows ? max_rows : 0; sw.rows = want_rows ? drows.as<double>() : nullptr;
     sw.listP = dlp.as<int>(); sw.listG = dlg.as<int>(); sw.counts = dcounts.as<int>();
+    sw.seg_tstop = dsts.as<double>(); sw.seg_x = dsx.as<double>(); sw.seg_dt = dsdt.as<double>(); sw.seg_row = dsrow.as<int>();
     sw.first = 1;
     if (int rc = launch_any(f, strict, UK_ADAPT, &sw, n, 0, s0)) return rc;
     g_launches++;
@@ -784,13 +788,23 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
     pc.check_adiabaticity = 1;
     const int gp = grid_for(1 << 30, FLAVOUR(strict, particle_blocks_per_sm, !strict && f->is_static && !p->enforce_equatorial && f->kind != RAPT_FIELD_USER));
     const int gg = grid_for(1 << 30, FLAVOUR(strict, gc_blocks_per_sm));
+    // Time-sliced epochs: every launch advances its tracers at most to slice_end, so a tracer that switches
+    // mode early waits one slice, not for the longest segment of the ensemble, and both kernels have work
+    // in (almost) every epoch.  Slices only interrupt at row boundaries and resume bit-identically.
+    double tmin = t0[0];
+    for (int64_t i = 1; i < n; i++) tmin = std::min(tmin, t0[i]);
+    const char *env_sl = getenv("RAPT_B200_ADAPTIVE_SLICES");
+    const int nslices = env_sl ? std::max(1, atoi(env_sl)) : 16;
+    const double slice = (delta > 0 ? delta : 1.0) / nslices;
     int epochs = 0;
     for (;; epochs++) {
+        const double slice_end = tmin + slice * (epochs + 1);
         int cnt[2] = {0, 0};
         CK(cudaMemcpyAsync(cnt, dcounts.p, sizeof cnt, cudaMemcpyDeviceToHost, s0));
         CK(cudaStreamSynchronize(s0));
         if (cnt[0] == 0 && cnt[1] == 0) break;
         if (epochs > 100000) return fail(RAPT_E_CUDA, "adaptive_advance: epoch limit");
+        if (getenv("RAPT_B200_TRACE")) fprintf(stderr, "[rapt_b200] adaptive epoch %d: %d particle-mode, %d guiding-centre-mode tracers\n", epochs, cnt[0], cnt[1]);
         CK(cudaMemsetAsync(dcounts.p, 0, 2 * sizeof(int), s0));
         CK(cudaStreamSynchronize(s0));
         if (cnt[0] > 0) {
@@ -802,6 +816,7 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
             a.store_every = want_rows ? std::max<int64_t>(store_every, 1) : 0; a.max_rows = sw.max_rows; a.rows = sw.rows;
             a.nstored = sw.nstored; a.nrows = nullptr; a.counters = dcnt.as<int>(); a.status = sw.status;
             a.tcur = sw.tcur; a.dt_out = ddtp.as<double>(); a.segtag = sw.segtag; a.append = 1;
+            a.seg_tstop = sw.seg_tstop; a.seg_x = sw.seg_x; a.seg_dt = sw.seg_dt; a.seg_row = sw.seg_row; a.slice_end = slice_end;
             if (int rc = launch_any(f, strict, UK_PARTICLE, &a, cnt[0], std::min(gp, (cnt[0] + 127) / 128), s1)) return rc;
             g_launches++;
         }
@@ -815,6 +830,7 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
             a.store_every = want_rows ? std::max<int64_t>(store_every, 1) : 0; a.max_rows = sw.max_rows; a.rows = sw.rows;
             a.nstored = sw.nstored; a.nrows = nullptr; a.counters = dcnt.as<int>(); a.status = sw.status;
             a.tcur = sw.tcur; a.segtag = sw.segtag; a.append = 1;
+            a.seg_tstop = sw.seg_tstop; a.seg_x = sw.seg_x; a.seg_dt = sw.seg_dt; a.seg_row = sw.seg_row; a.slice_end = slice_end;
             if (int rc = launch_any(f, strict, UK_GC, &a, cnt[1], std::min(gg, (cnt[1] + 127) / 128), s2)) return rc;
             g_launches++;
         }

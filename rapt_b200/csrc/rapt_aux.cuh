@@ -389,6 +389,8 @@ __global__ void __launch_bounds__(256) k_adaptive_switch(const AdaptArgs a)
                 a.tcur[i] = prow[0];                               // Particle.__init__: tcur = t0
             }
         }
+        const bool sliced = (!a.first) && st == RAPT_ST_SLICE;          // interrupted at a slice boundary: resume as is
+        if (sliced) st = RAPT_ST_OK;
         if (newseg && st == RAPT_ST_OK) {
             const int tag = 2 * (nseg - 1) + mode;
             a.segtag[i] = tag;
@@ -414,11 +416,23 @@ __global__ void __launch_bounds__(256) k_adaptive_switch(const AdaptArgs a)
             }
         }
         a.mode[i] = mode; a.nseg[i] = nseg; a.status[i] = st;
-        // Adaptive.py:205,222 : t = current.tcur ; loop while t < delta (absolute tcur vs duration, quirk Q14)
-        double tv = a.first ? 0.0 : a.tcur[i];
-        a.tvar[i] = tv;
-        a.rem[i] = a.delta - tv;
-        if (st == RAPT_ST_OK && tv < a.delta) want = mode;
+        if (sliced) want = mode;
+        else {
+            // Adaptive.py:205,222 : t = current.tcur ; loop while t < delta (absolute tcur vs duration, quirk Q14)
+            double tv = a.first ? 0.0 : a.tcur[i];
+            a.tvar[i] = tv;
+            a.rem[i] = a.delta - tv;
+            if (st == RAPT_ST_OK && tv < a.delta) {
+                // next reference call: current.advance(delta - t) from the tracer's last row (Adaptive.py:207):
+                // tstop = t0 + (delta - t) (Particle.py:304, GuidingCenter.py:452); dt is chosen when it starts
+                want = mode;
+                const double tstart = (mode == 0) ? a.pt[i] : a.gt[i];
+                a.seg_tstop[i] = tstart + (a.delta - tv);
+                a.seg_x[i] = tstart;
+                a.seg_dt[i] = 0.0;
+                if (newseg) a.seg_row[i] = 0;
+            }
+        }
     }
     // ---- regroup by mode: ballot + shared-memory scan + one atomic per block and mode
     __shared__ int wcount[2][8];

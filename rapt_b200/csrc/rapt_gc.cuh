@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
     const double pf0 = pow(1e-4, beta);          // facold^beta at the first step of every row
 
     double y[4], k1[4], k2[4], k3[4], k4[4], k5[4], k6[4], y1[4], yin[4], kout[4];
-    double x = 0, h = 0, xend = 0, tstop = 0, dt = 0, facold = 1e-4, hmax = 0, tin = 0, dnf = 0;
+    double x = 0, h = 0, xend = 0, tstop = 0, tlim = 0, dt = 0, facold = 1e-4, hmax = 0, tin = 0, dnf = 0;
     GcConst gc = {0, 0, 0, 0};
     int pid = -1;
     int nstep = 0, naccpt = 0, nrejct = 0, ncalls = 0, nstep_row = 0, naccpt_row = 0;
@@ -241,7 +241,11 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
 
     for (;;) {
         // ---- (A) guiding centre finished?  write it back and fetch the next one
-        if (have && need_row && !(st == RAPT_ST_OK && x < tstop)) {
+        if (have && need_row && !(st == RAPT_ST_OK && x < tlim)) {
+            if (a.seg_tstop) {                                   // sliced adaptive epoch
+                a.seg_row[pid] = rowidx;
+                if (st == RAPT_ST_OK && x < tstop) st = RAPT_ST_SLICE;
+            }
             a.t[pid] = x; a.s1[pid] = y[0]; a.s2[pid] = y[1]; a.s3[pid] = y[2]; a.s4[pid] = y[3];
             int *c = a.counters + 4 * (long long)pid;
             int nf = 2 * ncalls + 6 * nstep;                     // as scipy counts: SURVEY.md §3.1
@@ -263,7 +267,10 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
             dt = a.dtin[pid];
             double delta = a.delta_arr ? a.delta_arr[pid] : a.delta;
             tstop = x + delta;                                   // GuidingCenter.py:452
-            nstep = naccpt = nrejct = ncalls = 0; rowidx = 0; st = RAPT_ST_OK;
+            tlim = tstop;
+            int row0 = 0;
+            if (a.seg_tstop) { tstop = a.seg_tstop[pid]; tlim = fmin(tstop, a.slice_end); row0 = a.seg_row[pid]; }
+            nstep = naccpt = nrejct = ncalls = 0; rowidx = row0; st = RAPT_ST_OK;
             myrows = a.rows ? a.rows + (size_t)pid * (size_t)a.max_rows * 8 : nullptr;
             if (a.append) nst = a.nstored[pid];
             else {
@@ -276,7 +283,7 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
                 }
             }
             have = true; need_row = true;
-            if (!(x < tstop)) continue;                          // delta <= 0
+            if (!(x < tlim)) continue;                           // delta <= 0 (or beyond this slice)
             gc_rhs<F>(a.f, gc, eom, eqf, x, y, k1);              // k1 = f(x, y)
         }
         // ---- (B) one step attempt; stage 1 = HINIT's Euler probe for lanes that start an output row

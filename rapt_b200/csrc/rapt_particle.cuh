@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128, 2) k_particle_dop853(const AdvArgs a)
     const double pf0 = pow(1e-4, beta);          // facold^beta at the first step of every row
 
     double y[6], k1[6], k2[6], k3[6], k4[6], k5[6], k6[6], k7[6], k8[6], k9[6], k10[6], yin[6], kout[6];
-    double x = 0, h = 0, xend = 0, label = 0, tstop = 0, dt = 0, facold = 1e-4, hmax = 0, tin = 0, dnf = 0, hnew = 0;
+    double x = 0, h = 0, xend = 0, label = 0, tstop = 0, tlim = 0, dt = 0, facold = 1e-4, hmax = 0, tin = 0, dnf = 0, hnew = 0;
     double mass = 0, q = 0, gm = 1, igm = 1;
     int pid = -1;
     int nstep = 0, naccpt = 0, nrejct = 0, ncalls = 0, nstep_row = 0, naccpt_row = 0;
@@ -132,7 +132,11 @@ __global__ void __launch_bounds__(128, 2) k_particle_dop853(const AdvArgs a)
 
     for (;;) {
         // ---- (A) particle finished?  write it back and fetch the next one
-        if (have && need_row && !(st == ST_OK && x < tstop)) {
+        if (have && need_row && !(st == ST_OK && x < tlim)) {
+            if (a.seg_tstop) {                               // sliced adaptive epoch: keep the call's state
+                a.seg_x[pid] = x; a.seg_dt[pid] = dt; a.seg_row[pid] = rowidx;
+                if (st == ST_OK && x < tstop) st = RAPT_ST_SLICE;
+            }
             a.t[pid] = label; a.s1[pid] = y[0]; a.s2[pid] = y[1]; a.s3[pid] = y[2];
             a.s4[pid] = y[3]; a.s5[pid] = y[4]; a.s6[pid] = y[5];
             int *c = a.counters + 4 * (long long)pid;
@@ -155,7 +159,14 @@ __global__ void __launch_bounds__(128, 2) k_particle_dop853(const AdvArgs a)
             mass = a.mass[pid]; q = a.charge[pid];
             double delta = a.delta_arr ? a.delta_arr[pid] : a.delta;
             tstop = x + delta;                               // Particle.py:304  (t0 + delta)
+            tlim = tstop;
             label = x;
+            double dt_fixed = 0;
+            int row0 = 0;
+            if (a.seg_tstop) {                               // resume a sliced call
+                tstop = a.seg_tstop[pid]; tlim = fmin(tstop, a.slice_end);
+                x = a.seg_x[pid]; dt_fixed = a.seg_dt[pid]; row0 = a.seg_row[pid];
+            }
             // Particle.py:274-275, 282: gm, vel, dt = cyclotron_period / cyclotronresolution
             gm = sqrt(mass * mass + dot3(y[3], y[4], y[5], y[3], y[4], y[5]) / (RAPT_C_LIGHT * RAPT_C_LIGHT));
             igm = 1.0 / gm;
@@ -165,8 +176,9 @@ __global__ void __launch_bounds__(128, 2) k_particle_dop853(const AdvArgs a)
                 double Bm = F::magB(a.f, x, y[0], y[1], y[2]);
                 dt = 2 * RAPT_PI * gamma * mass / Bm / fabs(q) / a.p.cyclotronresolution;
             }
+            if (dt_fixed > 0) dt = dt_fixed;
             if (a.dt_out) a.dt_out[pid] = dt;
-            nstep = naccpt = nrejct = ncalls = 0; rowidx = 0; st = ST_OK;
+            nstep = naccpt = nrejct = ncalls = 0; rowidx = row0; st = ST_OK;
             myrows = a.rows ? a.rows + (size_t)pid * (size_t)a.max_rows * 8 : nullptr;
             if (a.append) nst = a.nstored[pid];
             else {
@@ -179,7 +191,7 @@ __global__ void __launch_bounds__(128, 2) k_particle_dop853(const AdvArgs a)
                 }
             }
             have = true; need_row = true;
-            if (!(x < tstop)) continue;                      // delta <= 0: nothing to do
+            if (!(x < tlim)) continue;                       // delta <= 0 (or beyond this slice): nothing to do
             particle_rhs<F>(a.f, q, mass, gm, igm, eqf, x, y, k1);           // k1 = f(x, y)
         }
         // ---- (B) one step attempt; stage 1 = HINIT for lanes that start an output row

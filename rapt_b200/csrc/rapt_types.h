@@ -37,6 +37,14 @@ struct AdvArgs {
     const int *segtag;            // adaptive: column-7 tag per particle, or NULL
     int append;                   // adaptive: rows appended after nstored[pid]; counters accumulated
     int eom;                      // guiding centre only
+    // adaptive, time-sliced epochs: a segment (= one reference advance() call) may be interrupted at a row
+    // boundary once the solver time passes slice_end and resumed by a later launch.  Everything the call
+    // fixed at its start is kept here so that the resumed run is bit-identical to an uninterrupted one.
+    double *seg_tstop;            // absolute end time of the call (t0 + delta), or NULL: not sliced
+    double *seg_x;                // Particle: solver time (can differ from the row label by an ulp)
+    double *seg_dt;               // Particle: output step chosen at the start of the call (0: not chosen yet)
+    int *seg_row;                 // output-row index within the call (decimation phase)
+    double slice_end;
 };
 
 // batched _Field operators
@@ -86,6 +94,8 @@ struct AdaptArgs {
     double *gt, *gx, *gy, *gz, *gpp, *mu, *v;           // GuidingCenter-mode state (last row), mu, speed
     int *mode, *status, *nseg, *segtag, *nstored;
     double *tvar, *rem, *tcur;                          // Adaptive.advance's `t`, delta - t, current.tcur
+    double *seg_tstop, *seg_x, *seg_dt;                 // per-call resume state (see AdvArgs)
+    int *seg_row;
     long long max_rows;
     double *rows;
     int *listP, *listG, *counts;                        // compacted work lists by mode; counts[0..1]
@@ -97,6 +107,9 @@ struct AdaptArgs {
 #define RAPT_ST_OK 1
 #define RAPT_ST_ADIABATIC 2
 #define RAPT_ST_NONADIABATIC 3
+#ifndef RAPT_ST_SLICE
+#define RAPT_ST_SLICE 4          /* adaptive: segment interrupted at a row boundary, to be resumed */
+#endif
 #define RAPT_ST_NMAX (-2)
 #define RAPT_ST_HSMALL (-3)
 #define RAPT_ST_GCITER (-5)
