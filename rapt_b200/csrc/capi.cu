@@ -788,13 +788,16 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
     pc.check_adiabaticity = 1;
     const int gp = grid_for(1 << 30, FLAVOUR(strict, particle_blocks_per_sm, !strict && f->is_static && !p->enforce_equatorial && f->kind != RAPT_FIELD_USER));
     const int gg = grid_for(1 << 30, FLAVOUR(strict, gc_blocks_per_sm));
-    // Time-sliced epochs: every launch advances its tracers at most to slice_end, so a tracer that switches
-    // mode early waits one slice, not for the longest segment of the ensemble, and both kernels have work
-    // in (almost) every epoch.  Slices only interrupt at row boundaries and resume bit-identically.
+    // Optional time-sliced epochs (RAPT_B200_ADAPTIVE_SLICES=k): every launch advances its tracers at most to
+    // slice_end, so a tracer that switches mode early waits one slice instead of the longest segment of the
+    // ensemble.  Slices only interrupt at row boundaries and resume bit-identically (tests run with 16).
+    // Measured on config 4 it does NOT pay: 1 M Speiser tracers 3.7 s unsliced vs 5.1 s with 8-32 slices,
+    // 65,536 tracers 1.6 s vs 2.2-2.4 s (profiles/r1_other_configs.md) -- the relaunch of every tracer per slice
+    // costs more than the idle lanes it removes -- so the default is one slice.
     double tmin = t0[0];
     for (int64_t i = 1; i < n; i++) tmin = std::min(tmin, t0[i]);
     const char *env_sl = getenv("RAPT_B200_ADAPTIVE_SLICES");
-    const int nslices = env_sl ? std::max(1, atoi(env_sl)) : 16;
+    const int nslices = env_sl ? std::max(1, atoi(env_sl)) : 1;
     const double slice = (delta > 0 ? delta : 1.0) / nslices;
     int epochs = 0;
     for (;; epochs++) {

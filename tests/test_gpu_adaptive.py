@@ -32,9 +32,16 @@ def split_segments(d):
     return out
 
 
+@pytest.fixture(params=[1, 16], ids=["unsliced", "16slices"])
+def slices(request, monkeypatch):
+    """Epochs unsliced (default) and time-sliced: a sliced run must resume every call bit-identically."""
+    monkeypatch.setenv("RAPT_B200_ADAPTIVE_SLICES", str(request.param))
+    return request.param
+
+
 @pytest.mark.parametrize("arith", ["strict", "fast"])
 @pytest.mark.parametrize("name", ["g3_speiser", "e4_speiser_1", "e4_speiser_2", "e4_speiser_3", "e4_speiser_4", "e4_speiser_5"])
-def test_adaptive_ensemble_kernel_vs_reference(rb, name, arith):
+def test_adaptive_ensemble_kernel_vs_reference(rb, name, arith, slices):
     """Device epoch loop (advance kernels + switch/compaction kernel), one tracer per golden file."""
     d, par = H.load(name)
     f = H.gpu_field(*H.ADAPTIVE_CASES[name])

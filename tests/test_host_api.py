@@ -135,3 +135,43 @@ def test_synthetic_ensembles_are_deterministic():
     assert np.all(c3["x"] <= 8 * synth.Re + 1)
     c4 = synth.config4_speiser(8)
     assert (c4["x"][0], c4["y"][0], c4["z"][0], c4["vx"][0], c4["vy"][0]) == (5.0, -5.0, 0.9, -0.1, 0.1)
+
+
+def test_halfbouncepath_host_leg_matches_reference():
+    """The host leg of GuidingCenter.bounceperiod (flutils.py:274-316: trimming, equatorial 3-point formula,
+    scipy spline/brentq/quad) on the reference's own traced curves gives the reference's value exactly."""
+    from rapt_b200 import engine
+    for name in ("g2_gc_doubledipole", "gc_earthdipole", "gc_pa90_equatorial"):
+        d, _ = H.load(name)
+        s, b, Bm = d["bs_curve"][:, 0], d["bs_B"], float(d["bs_Bm"])
+        hp = engine.halfbouncepath_from_curve(s, b, Bm)
+        assert hp == float(d["bs_halfpath"]), name
+        assert (2 / float(d["bs_v"])) * hp == float(d["bs_period"])
+
+
+def test_nystrom_tables_are_consistent_with_the_tableau():
+    """rapt_particle_rkn.cuh integrates in Nystrom form with A.A, b.A, er.A, w.A (tools/gen_coeffs.py):
+    check the generated constants against the DOP853 tableau and the order conditions they must inherit."""
+    import re
+    from fractions import Fraction as Fr
+    from scipy.integrate._ivp import dop853_coefficients as dc
+    co = open(os.path.join(ROOT, "rapt_b200", "csrc", "dop_coeffs.h")).read()
+    val = {m.group(1): float(m.group(2)) for m in re.finditer(r"#define (D8N?_\w+) (\S+)", co)}
+    A = dc.A[:12, :12]; B = dc.B[:12]; E5 = dc.E5[:12]; E3 = dc.E3[:12]
+    AA = A @ A
+    for i in range(2, 12):
+        assert abs(val[f"D8N_RS{i+1}"] - A[i].sum()) < 1e-15
+        assert abs(val[f"D8N_RS{i+1}"] - dc.C[i]) < 3e-15          # row-sum condition c_i = sum_j a_ij
+        for l in range(i - 1):
+            got = val.get(f"D8N_AA{i+1}_{l+1}", 0.0)
+            assert abs(got - AA[i, l]) < 1e-14 * max(1.0, abs(AA[i, l])), (i, l)
+    for name, w in (("BA", B), ("ERA", E5), ("WA", E3)):
+        wa = w @ A
+        for l in range(11):
+            assert abs(val.get(f"D8N_{name}{l+1}", 0.0) - wa[l]) < 1e-14 * max(1.0, abs(wa[l])), (name, l)
+    assert val["D8N_SB"] == 1.0 and abs(val["D8N_SER"]) < 1e-16 and abs(val["D8N_SW"]) < 1e-15
+    # second-order condition of the position update: sum_l (b.A)_l = 1/2
+    assert abs(sum(val.get(f"D8N_BA{l+1}", 0.0) for l in range(11)) - 0.5) < 1e-15
+    # exact arithmetic agrees with what the generator rounded
+    exact = float(sum(Fr(float(B[j])) * Fr(float(A[j, 5])) for j in range(12)))
+    assert val["D8N_BA6"] == exact
