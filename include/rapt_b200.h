@@ -174,6 +174,15 @@ int rapt_b200_bounce_setup(const rapt_field_t *f, int arith, double fieldlineres
                            const double *mu, const double *mass,
                            double *Bm, double *v, double *ds, int32_t *npts, int64_t max_pts, double *curve);
 
+/* ---- GuidingCenter.bounceperiod entirely on the device: the trace above followed by
+ * flutils.halfbouncepath (flutils.py:274-316) with scipy's quadratic interpolating spline rebuilt per thread
+ * and the mirror points and the integral of 1/sqrt(1 - B(s)/Bm) taken in closed form span by span.  The
+ * result equals the reference's up to the error of its own QUADPACK call (epsrel 1e-4 requested; 1e-7 typical, up to 2e-5 observed).
+ * period[i] = NaN if the trace did not bracket both mirror points.  npts may be NULL.  HOST pointers. */
+int rapt_b200_bounce_period(const rapt_field_t *f, int arith, double fieldlineresolution, int64_t n,
+                            const double *t, const double *x, const double *y, const double *z, const double *ppar,
+                            const double *mu, const double *mass, double *period, int32_t *npts);
+
 /* ---- Adaptive.__init__ + Adaptive.advance (Adaptive.py:70-104, 187-222) for an ensemble.
  * In: particle position/velocity (as the Adaptive constructor takes them), t0, mass, charge.
  * gc_dt: guiding-centre output step (params["GCtimestep"], must be != 0 for ensembles).

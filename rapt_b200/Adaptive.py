@@ -88,26 +88,13 @@ class Adaptive:
             res = np.concatenate((res, getattr(p, name)()))
         return res
 
-    def gett(self):
-        return self._cat("gett")
 
-    def getx(self):
-        return self._cat("getx")
+def _concatenating(name):
+    def get(self):
+        return self._cat(name)
+    get.__doc__ = f"`{name}()` of every segment in `trajlist`, concatenated (rapt/Adaptive.py:224-274)."
+    return get
 
-    def gety(self):
-        return self._cat("gety")
 
-    def getz(self):
-        return self._cat("getz")
-
-    def getr(self):
-        return self._cat("getr")
-
-    def getphi(self):
-        return self._cat("getphi")
-
-    def gettheta(self):
-        return self._cat("gettheta")
-
-    def getke(self):
-        return self._cat("getke")
+for _name in ("gett", "getx", "gety", "getz", "getr", "getphi", "gettheta", "getke"):
+    setattr(Adaptive, _name, _concatenating(_name))

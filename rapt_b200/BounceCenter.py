@@ -50,18 +50,6 @@ class BounceCenter:
         for k in p.__dict__.keys():
             self.__dict__[k] = p.__dict__[k]
 
-    def gett(self):
-        return self.trajectory[:, 0]
-
-    def getx(self):
-        return self.trajectory[:, 1]
-
-    def gety(self):
-        return self.trajectory[:, 2]
-
-    def getz(self):
-        return self.trajectory[:, 3]
-
     def getr(self):
         return np.sqrt(self.getx() ** 2 + self.gety() ** 2 + self.getz() ** 2)
 
@@ -73,3 +61,7 @@ class BounceCenter:
 
     def getB(self):
         return np.array([self.field.magB(row) for row in self.trajectory])
+
+
+for _i, _name in enumerate(("gett", "getx", "gety", "getz")):
+    setattr(BounceCenter, _name, (lambda i: lambda self: self.trajectory[:, i])(_i))

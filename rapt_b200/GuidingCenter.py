@@ -145,22 +145,7 @@ class GuidingCenter:
         if self.check_adiabaticity and status == 3:
             raise NonAdiabatic
 
-    # ---- getters (rapt/GuidingCenter.py:460-591)
-    def gett(self):
-        return self.trajectory[:, 0]
-
-    def getx(self):
-        return self.trajectory[:, 1]
-
-    def gety(self):
-        return self.trajectory[:, 2]
-
-    def getz(self):
-        return self.trajectory[:, 3]
-
-    def getpp(self):
-        return self.trajectory[:, 4]
-
+    # ---- getters (rapt/GuidingCenter.py:460-591): gett, getx, gety, getz, getpp are column views (attached below)
     def getr(self):
         return np.sqrt(self.getx() ** 2 + self.gety() ** 2 + self.getz() ** 2)
 
@@ -232,3 +217,15 @@ class GuidingCenter:
     def geteye(self, step=1):
         raise NotImplementedError("the second invariant (flutils.eye) is off the advance hot path and is broken in "
                                   "the reference (flutils.py:130); see DESIGN.md 'out of scope'")
+
+
+def _column_getter(index, what):
+    def get(self):
+        return self.trajectory[:, index]
+    get.__doc__ = f"1-d array of {what} along the trajectory."
+    return get
+
+
+for _i, (_name, _what) in enumerate((("gett", "time values"), ("getx", "the x coordinate"), ("gety", "the y coordinate"),
+                                     ("getz", "the z coordinate"), ("getpp", "the parallel momentum"))):
+    setattr(GuidingCenter, _name, _column_getter(_i, _what))

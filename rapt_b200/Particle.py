@@ -135,28 +135,8 @@ class Particle:
         (rapt/Particle.py:345-384); evaluated by the same device code the advance kernel uses."""
         return bool(engine.isadiabatic(self.field, 0, self.trajectory[-1], 0.0, self.mass, self.charge)[0])
 
-    # ---- getters (rapt/Particle.py:386-461)
-    def gett(self):
-        return self.trajectory[:, 0]
-
-    def getx(self):
-        return self.trajectory[:, 1]
-
-    def gety(self):
-        return self.trajectory[:, 2]
-
-    def getz(self):
-        return self.trajectory[:, 3]
-
-    def getpx(self):
-        return self.trajectory[:, 4]
-
-    def getpy(self):
-        return self.trajectory[:, 5]
-
-    def getpz(self):
-        return self.trajectory[:, 6]
-
+    # ---- getters (rapt/Particle.py:386-461): gett, getx, gety, getz, getpx, getpy, getpz are column views,
+    # attached below from _COLUMNS
     def getp(self):
         return np.sqrt(self.getpx() ** 2 + self.getpy() ** 2 + self.getpz() ** 2)
 
@@ -217,3 +197,17 @@ class Particle:
         t, r, mom = self.trajectory[-1, 0], self.trajectory[-1, 1:4], self.trajectory[-1, 4:]
         gm = np.sqrt(self.mass ** 2 + np.dot(mom, mom) / c ** 2)
         return ru.cyclotron_period(t, r, mom / gm, self.field, self.mass, self.charge)
+
+
+def _column_getter(index, what):
+    def get(self):
+        return self.trajectory[:, index]
+    get.__doc__ = f"1-d array of {what} along the trajectory."
+    return get
+
+
+_COLUMNS = (("gett", "time values"), ("getx", "the x coordinate"), ("gety", "the y coordinate"), ("getz", "the z coordinate"),
+            ("getpx", "the x component of the momentum"), ("getpy", "the y component of the momentum"),
+            ("getpz", "the z component of the momentum"))
+for _i, (_name, _what) in enumerate(_COLUMNS):
+    setattr(Particle, _name, _column_getter(_i, _what))

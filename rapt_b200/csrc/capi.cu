@@ -681,20 +681,54 @@ int rapt_b200_isadiabatic(const rapt_field_t *f, const rapt_params_t *p, int mod
     return RAPT_OK;
 }
 
+static int bounce_impl(const rapt_field_t *f, int arith, double fieldlineresolution, int64_t n,
+                       const double *t, const double *x, const double *y, const double *z, const double *ppar,
+                       const double *mu, const double *mass,
+                       double *Bm, double *v, double *ds, int32_t *npts, int64_t max_pts, double *curve, double *period);
+
 int rapt_b200_bounce_setup(const rapt_field_t *f, int arith, double fieldlineresolution, int64_t n,
                            const double *t, const double *x, const double *y, const double *z, const double *ppar,
                            const double *mu, const double *mass,
                            double *Bm, double *v, double *ds, int32_t *npts, int64_t max_pts, double *curve)
 {
+    if (!curve) return fail(RAPT_E_ARG, "bounce_setup: curve buffer required");
+    return bounce_impl(f, arith, fieldlineresolution, n, t, x, y, z, ppar, mu, mass, Bm, v, ds, npts, max_pts, curve, nullptr);
+}
+
+int rapt_b200_bounce_period(const rapt_field_t *f, int arith, double fieldlineresolution, int64_t n,
+                            const double *t, const double *x, const double *y, const double *z, const double *ppar,
+                            const double *mu, const double *mass, double *period, int32_t *npts)
+{
+    if (!period || !mu || !ppar || !mass) return fail(RAPT_E_ARG, "bounce_period: null argument");
+    if (n <= 0) return n < 0 ? fail(RAPT_E_ARG, "n < 0") : RAPT_OK;
+    std::vector<double> Bm((size_t)n), v((size_t)n), ds((size_t)n);
+    std::vector<int32_t> np_local((size_t)n);
+    int32_t *np_out = npts ? npts : np_local.data();
+    for (int64_t max_pts = 128; max_pts <= 8192; max_pts *= 4) {
+        int rc = bounce_impl(f, arith, fieldlineresolution, n, t, x, y, z, ppar, mu, mass, Bm.data(), v.data(), ds.data(),
+                             np_out, max_pts, nullptr, period);
+        if (rc) return rc;
+        int32_t mx = 0;
+        for (int64_t i = 0; i < n; i++) mx = std::max(mx, np_out[i]);
+        if (mx <= max_pts) return RAPT_OK;
+    }
+    return fail(RAPT_E_ARG, "bounce_period: a field line needs more than 8192 points");
+}
+
+static int bounce_impl(const rapt_field_t *f, int arith, double fieldlineresolution, int64_t n,
+                       const double *t, const double *x, const double *y, const double *z, const double *ppar,
+                       const double *mu, const double *mass,
+                       double *Bm, double *v, double *ds, int32_t *npts, int64_t max_pts, double *curve, double *period)
+{
     if (int rc = ensure_init()) return rc;
     if (int rc = check_field(f)) return rc;
-    if (n < 0 || max_pts < 3 || (n > 0 && (!t || !x || !y || !z || !Bm || !ds || !npts || !curve)))
+    if (n < 0 || max_pts < 3 || (n > 0 && (!t || !x || !y || !z || !Bm || !ds || !npts)))
         return fail(RAPT_E_ARG, "bounce_setup: bad argument");
     if (mu && (!ppar || !mass || !v)) return fail(RAPT_E_ARG, "bounce_setup: ppar, mass, v required with mu");
     if (n == 0) return RAPT_OK;
     cudaStream_t s = 0;
     const size_t nb = n * sizeof(double);
-    DevBuf in[7], oBm, ov, ods, onp, ocv, scr;
+    DevBuf in[7], oBm, ov, ods, onp, ocv, scr, oper;
     const double *h[7] = {t, x, y, z, ppar, mu, mass};
     for (int k = 0; k < 7; k++) if (h[k]) CK(up(in[k], h[k], nb, s));
     if (mu) CK(oBm.alloc(nb)); else CK(up(oBm, Bm, nb, s));      // mu == NULL: Bm is an input
@@ -708,10 +742,12 @@ int rapt_b200_bounce_setup(const rapt_field_t *f, int arith, double fieldlineres
     a.ppar = in[4].as<double>(); a.mu = in[5].as<double>(); a.mass = in[6].as<double>();
     a.Bm = oBm.as<double>(); a.v = ov.as<double>(); a.ds = ods.as<double>(); a.npts = onp.as<int>();
     a.curve = ocv.as<double>(); a.scratch = scr.as<double>();
+    if (period) { CK(oper.alloc(nb)); a.period = oper.as<double>(); }
     if (int rc = launch_any(f, arith == 1, UK_BOUNCE, &a, n, 0, s)) return rc;
     g_launches++;
     CK(down(Bm, oBm, nb, s)); if (v) CK(down(v, ov, nb, s)); CK(down(ds, ods, nb, s)); CK(down(npts, onp, n * sizeof(int), s));
-    CK(down(curve, ocv, (size_t)n * max_pts * 5 * sizeof(double), s));
+    if (curve) CK(down(curve, ocv, (size_t)n * max_pts * 5 * sizeof(double), s));
+    if (period) CK(down(period, oper, nb, s));
     CK(cudaStreamSynchronize(s));
     return RAPT_OK;
 }

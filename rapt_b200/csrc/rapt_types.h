@@ -78,7 +78,8 @@ struct BounceArgs {
     double *Bm, *v, *ds;
     int *npts;
     double *curve;            // [n][max_pts][5] : s, x, y, z, |B|
-    double *scratch;          // [n][max_pts][4] : backward half before reversal
+    double *scratch;          // [n][max_pts][4] : backward half before reversal; then spline work arrays
+    double *period;           // optional: bounce period by closed-form quadrature of the quadratic spline
 };
 
 // Adaptive: per-tracer state of both modes + the epoch bookkeeping (rapt/Adaptive.py:70-104, 187-222)

@@ -188,3 +188,38 @@ def test_switch_transforms_and_predicates(eng, arith):
     ga_gpu = eng.isadiabatic(f, 1, grow, mu, m_pr, e, arith=arith, **par)
     ga_ref = [O.gc_isadiabatic(of, O.make_params(**par), grow[i], mu[i], m_pr, e) for i in range(len(grow))]
     assert list(ga_gpu) == ga_ref
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_bounce_period_device_closed_form(eng, arith):
+    """rapt_b200_bounce_period: trace + spline + closed-form quadrature on the device vs the reference's
+    bounce periods (golden) -- agreement to QUADPACK's own error (epsrel 1e-4 requested, ~1e-7 delivered)."""
+    from rapt_b200 import synth
+    for name in ("g2_gc_doubledipole", "gc_earthdipole", "gc_pa90_equatorial"):
+        d, par = H.load(name)
+        f = H.gpu_field(*H.GC_CASES[name])
+        traj = d["traj"]
+        st0 = traj[0]
+        bp = eng.bounceperiod_device(f, st0, float(d["mu"]), float(d["mass"]), arith=arith)[0]
+        assert abs(bp / float(d["bs_period"]) - 1) < 2e-6, (name, bp, float(d["bs_period"]))
+    d, par = H.load("e3_config3_first16")
+    n = int(d["n"]); ic = synth.config3_electrons(n); f = H.gpu_field("DoubleDipole", ())
+    pos = np.column_stack([ic["x"], ic["y"], ic["z"]])
+    ppar, mu = eng.gc_construct(f, ic["t0"], pos, ic["v"], ic["pa"], ic["mass"], arith=arith)
+    st = np.column_stack([ic["t0"], pos, ppar])
+    bp = eng.bounceperiod_device(f, st, mu, ic["mass"], arith=arith)
+    # the closed form is the exact integral of the spline; the difference is the error of the reference's
+    # QUADPACK call, which asked for epsrel = 1e-4 (flutils.py:314): typically 1e-7, a few 1e-6 observed
+    assert np.max(np.abs(bp / d["bounceperiod"] - 1)) < 1e-4
+    assert np.median(np.abs(bp / d["bounceperiod"] - 1)) < 1e-6
+    # 20,000 guiding centres in one call: finite, positive, and consistent with the host (scipy) leg on a subset
+    ic = synth.config3_electrons(20000)
+    pos = np.column_stack([ic["x"], ic["y"], ic["z"]])
+    ppar, mu = eng.gc_construct(f, ic["t0"], pos, ic["v"], ic["pa"], ic["mass"], arith=arith)
+    st = np.column_stack([ic["t0"], pos, ppar])
+    bp = eng.bounceperiod_device(f, st, mu, ic["mass"], arith=arith)
+    assert np.isfinite(bp).mean() > 0.999 and np.nanmin(bp) > 0
+    host = eng.bounceperiod(f, st[:64], mu[:64], ic["mass"][:64], arith=arith)
+    ok = np.isfinite(bp[:64])
+    assert np.max(np.abs(bp[:64][ok] / host[ok] - 1)) < 1e-4
+    assert np.median(np.abs(bp[:64][ok] / host[ok] - 1)) < 2e-6
