@@ -55,3 +55,60 @@ def test_user_field_ops_and_gc(rb):
         cuda_source = "__device__ void rapt_user_B(double t, double x, double y, double z, const double* prm, double* B) { B[0] = nonsense; }"
     with pytest.raises(_lib.RaptB200Error, match="nonsense"):
         rb.engine.field_ops(Broken(), pts)
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_user_field_guiding_centre_and_switches(rb, arith):
+    """The NVRTC module carries every kernel family: guiding-centre advance, constructor, switch transforms
+    and predicates with a user field, against the CPU oracle's restatement of the same field."""
+    import oracle as O
+    f = make_charged_dipole()(B0=3.0e-5 * 6378137.0 ** 3, Q=0.0)       # dipole moment of Earth's size, no charge
+    f.static = True
+    f.gradientstepsize = 6378137.0 / 1000
+    of = O.make_field("ChargedDipole", 3.0e-5 * 6378137.0 ** 3, 0.0, gradstep=6378137.0 / 1000, static=True)
+    Re = 6378137.0
+    n = 64
+    rng = np.random.default_rng(5)
+    pos = np.column_stack([rng.uniform(3, 6, n) * Re, rng.uniform(-1, 1, n) * Re, rng.uniform(-0.3, 0.3, n) * Re])
+    v = np.full(n, 1.5e8); pa = rng.uniform(35, 85, n); mass = np.full(n, rb.m_el); q = np.full(n, -rb.e)
+    ppar, mu = rb.engine.gc_construct(f, 0.0, pos, v, pa, mass, arith=arith)
+    ppar_o, mu_o = O.gc_construct(of, 0.0, pos, v, pa, mass)
+    assert H.relerr(mu, mu_o) < 1e-12
+    st = np.column_stack([np.zeros(n), pos, ppar_o])
+    got = rb.engine.gc_advance(f, st, mu_o, v, mass, q, 0.05, 1.0, store_every=0, arith=arith)
+    ref = O.gc_advance(of, O.make_params(), st, mu_o, v, mass, q, 0.05, 1.0, store_every=0, nthreads=4)
+    assert np.array_equal(got["nrows"], ref["nrows"])
+    assert H.vec_relerr(got["state"][:, 1:4], ref["state"][:, 1:4]) < 1e-8
+    assert (got["counters"][:, 1] == ref["counters"][:, 1]).mean() > 0.9
+    # particle <-> guiding centre with the user field
+    vel = rng.normal(size=(n, 3)); vel *= (1.0e8 / np.linalg.norm(vel, axis=1))[:, None]
+    prow = np.column_stack([np.zeros(n), pos, rb.engine.particle_momentum(vel, mass)])
+    grow, mu2, v2, st2 = rb.engine.switch_p2g(f, prow, mass, q, arith=arith)
+    for i in range(0, n, 7):
+        rc, g_o, mu_r, v_r = O.switch_P2G(of, prow[i], mass[i], q[i])
+        assert rc == st2[i]
+        if rc == 0:
+            assert H.vec_relerr(grow[i, 1:4], g_o[1:4]) < 1e-10 and abs(mu2[i] / mu_r - 1) < 1e-8
+    ad = rb.engine.isadiabatic(f, 0, prow, 0.0, mass, q, arith=arith)
+    ad_o = [O.particle_isadiabatic(of, O.make_params(), r, mass[0], q[0]) for r in prow]
+    assert list(ad) == ad_o
+
+
+def test_guiding_centre_ensemble_default_output_step(rb):
+    """GuidingCenterEnsemble with params['GCtimestep'] == 0: dt = bounceperiod()/bounceresolution
+    (GuidingCenter.py:443-446); above HOST_QUADRATURE_MAX members the bounce periods come from the
+    device closed-form quadrature."""
+    from rapt_b200 import synth
+    n = 6000
+    ic = synth.config3_electrons(n)
+    pos = np.column_stack([ic["x"], ic["y"], ic["z"]])
+    g = rb.GuidingCenterEnsemble(pos, ic["v"], pa=ic["pa"], mass=ic["mass"], charge=ic["charge"], field=rb.fields.DoubleDipole())
+    assert rb.params["GCtimestep"] == 0 and g.n > g.HOST_QUADRATURE_MAX
+    bp = g.bounceperiod()
+    assert np.isfinite(bp).all() and bp.min() > 0.1 and bp.max() < 10
+    sub = rb.GuidingCenterEnsemble(pos[:32], ic["v"][:32], pa=ic["pa"][:32], mass=ic["mass"][:32], charge=ic["charge"][:32],
+                                   field=rb.fields.DoubleDipole())
+    assert np.max(np.abs(bp[:32] / sub.bounceperiod(method="scipy") - 1)) < 1e-4
+    g.advance(1.0)
+    assert np.all(g.status == 1)
+    assert np.all(g.nrows == 1 + np.ceil(1.0 / (bp / rb.params["bounceresolution"]) - 1e-9))

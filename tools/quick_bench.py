@@ -17,7 +17,7 @@ vel = np.column_stack([ic["vx"], ic["vy"], ic["vz"]]); mom = engine.particle_mom
 st0 = [torch.tensor(a, device=dev) for a in (ic["t0"], ic["x"], ic["y"], ic["z"], mom[:, 0], mom[:, 1], mom[:, 2])]
 mass = torch.tensor(ic["mass"], device=dev); charge = torch.tensor(ic["charge"], device=dev)
 out = engine.alloc_outputs(n, dev)
-max_rows = 32 if store_every else 0
+max_rows = (int(sys.argv[7]) if len(sys.argv) > 7 else 32) if store_every else 0
 rows = torch.empty((n, max_rows, 8), dtype=torch.float64, device=dev) if store_every else None
 f = fields.EarthDipole()
 for r in range(reps):
@@ -29,5 +29,8 @@ for r in range(reps):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     steps = int(out["counters"][:, 1].to(torch.int64).sum()); nrow = int(out["nrows"].to(torch.int64).sum())
+    if store_every:
+        nst = int(out["nstored"].to(torch.int64).sum())
+        print(f"   stored rows {nst:.4e} x 64 B = {nst*64/1e9:.2f} GB -> {nst*64/ms/1e6:.1f} GB/s written; buffer {n*max_rows*64/1e9:.1f} GB", flush=True)
     print(f"n={n} delta={delta} {arith} store_every={store_every} sort={sort}: {ms:.2f} ms  steps={steps:.4e} rows={nrow:.4e}  {steps/ms*1e3:.4e} steps/s "
           f" -> {steps/ms*1e3*1440/1e12:.2f} TFLOP/s alg", flush=True)
