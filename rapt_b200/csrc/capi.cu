@@ -418,6 +418,8 @@ int rapt_b200_particle_advance_dev(const rapt_field_t *f, const rapt_params_t *p
         !status || !tcur)
         return fail(RAPT_E_ARG, "particle_advance: null argument");
     if (int rc = check_field(f)) return rc;
+    if (!(p->rtol > 0) || !(p->atol > 0) || !(p->cyclotronresolution > 0))
+        return fail(RAPT_E_ARG, "particle_advance: solvertolerances and cyclotronresolution must be positive");
     if (n == 0) return RAPT_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rapt::AdvArgs a;
@@ -492,6 +494,7 @@ int rapt_b200_gc_advance_dev(const rapt_field_t *f, const rapt_params_t *p, int 
         return fail(RAPT_E_ARG, "gc_advance: null argument");
     if (int rc = check_field(f)) return rc;
     if (eom < 0 || eom > 2) return fail(RAPT_E_ARG, "unknown eom %d", eom);
+    if (!(p->rtol > 0) || !(p->atol > 0)) return fail(RAPT_E_ARG, "gc_advance: solvertolerances must be positive");
     if (n == 0) return RAPT_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rapt::AdvArgs a;

@@ -283,6 +283,8 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
                 }
             }
             have = true; need_row = true;
+            if (!(dt > 0.0) || dt > 1e300) { st = RAPT_ST_HSMALL; continue; }   // degenerate output step (B = 0 or inf, bad
+                                                                             // resolution): the reference would never return
             if (!(x < tlim)) continue;                           // delta <= 0 (or beyond this slice)
             gc_rhs<F>(a.f, gc, eom, eqf, x, y, k1);              // k1 = f(x, y)
         }

@@ -118,6 +118,8 @@ __global__ void __launch_bounds__(128, 3) k_particle_rkn(const AdvArgs a)
                 }
             }
             have = true; need_row = true;
+            if (!(dt > 0.0) || dt > 1e300) { st = RAPT_ST_HSMALL; continue; }   // degenerate output step (B = 0 or inf, bad
+                                                                             // resolution): the reference would never return
             if (!(t < tlim)) continue;                       // delta <= 0 (or beyond this slice): nothing to do
             lorentz_K<F>(a.f, q, qg, t, x, p, K1);           // k1 = f(t, y)
         }

@@ -122,3 +122,40 @@ def test_gc_full_size_energy_conservation(eng):
     g0, g1 = gamma(st), gamma(o["state"])
     assert np.max(np.abs((g1 - 1) / (g0 - 1) - 1)) < 1e-4
     assert np.median(np.abs((g1 - 1) / (g0 - 1) - 1)) < 1e-6
+
+
+def test_abi_argument_checks_and_degenerate_inputs(eng):
+    """Bad arguments return an error code (never crash, never hang); degenerate tracers terminate with a
+    failure status instead of looping forever."""
+    import ctypes as C
+    from rapt_b200 import _lib, fields
+    from rapt_b200._lib import ptr
+    lib = _lib.load()
+    f = fields.EarthDipole().device_descriptor()
+    p = eng.snapshot_params(None, False)
+    one = np.ones(1); i1 = np.zeros(1, np.int32); i4 = np.zeros(4, np.int32)
+    args = [C.byref(f), C.byref(p), C.c_int64(1)] + [ptr(one.copy()) for _ in range(7)] + [ptr(one), ptr(one), C.c_double(1.0),
+            C.c_int64(0), C.c_int64(0), None, ptr(i1), ptr(i1.copy()), ptr(i4), ptr(i1.copy()), ptr(one.copy()), ptr(one.copy())]
+    bad = list(args); bad[2] = C.c_int64(-1)
+    assert lib.rapt_b200_particle_advance(*bad) == -3 and b"n < 0" in lib.rapt_b200_last_error()
+    bad = list(args); bad[4] = None
+    assert lib.rapt_b200_particle_advance(*bad) == -3
+    f2 = fields.EarthDipole().device_descriptor(); f2.kind = 42
+    bad = list(args); bad[0] = C.byref(f2)
+    assert lib.rapt_b200_particle_advance(*bad) == -3 and b"unknown field kind" in lib.rapt_b200_last_error()
+    with pytest.raises(_lib.RaptB200Error):
+        eng.particle_advance(fields.EarthDipole(), np.ones((1, 7)), 1.0, 1.0, 1.0, cyclotronresolution=-5)
+    with pytest.raises(_lib.RaptB200Error):
+        eng.particle_advance(fields.EarthDipole(), np.ones((1, 7)), 1.0, 1.0, 1.0, solvertolerances=(0.0, 1e-8))
+    # degenerate tracers: NaN position, zero field (particle at infinity), zero charge -> finite run time, failure status
+    d, par = H.load("g1b_generic")
+    st = np.tile(d["traj"][0], (4, 1))
+    st[1, 1] = np.nan
+    st[2, 1:4] = 1e200
+    q = np.full(4, float(d["charge"])); q[3] = 0.0
+    o = eng.particle_advance(fields.EarthDipole(), st, float(d["mass"]), q, 0.5, store_every=0, cyclotronresolution=20)
+    assert o["status"][0] == 1
+    assert np.all(o["status"][1:] < 0)
+    # guiding centres with a non-positive output step terminate too
+    g = eng.gc_advance(fields.DoubleDipole(), np.array([[0.0, 5e7, 1e6, 1e5, 1e-23]]), 1e-7, 1e8, 9.1e-31, -1.6e-19, 0.0, 1.0, store_every=0)
+    assert g["status"][0] < 0
