@@ -112,3 +112,30 @@ def test_guiding_centre_ensemble_default_output_step(rb):
     g.advance(1.0)
     assert np.all(g.status == 1)
     assert np.all(g.nrows == 1 + np.ceil(1.0 / (bp / rb.params["bounceresolution"]) - 1e-9))
+
+
+def test_user_field_adaptive_epochs(rb):
+    """Adaptive epochs (advance kernels + switch/compaction kernel) from the NVRTC module of a user field."""
+    import oracle as O
+    Re = 6378137.0
+    M = 3.0e-5 * Re ** 3
+    f = make_charged_dipole()(B0=M, Q=0.0); f.static = True; f.gradientstepsize = Re / 1000
+    of = O.make_field("ChargedDipole", M, 0.0, gradstep=Re / 1000, static=True)
+    n = 12
+    rng = np.random.default_rng(11)
+    pos = np.column_stack([rng.uniform(2.5, 4.5, n) * Re, rng.uniform(-0.5, 0.5, n) * Re, rng.uniform(-0.2, 0.2, n) * Re])
+    spd = rb.utils.speedfromKE(3e4, rb.m_pr)
+    d = rng.normal(size=(n, 3)); vel = d / np.linalg.norm(d, axis=1)[:, None] * spd
+    par = dict(epss=0.05)
+    o = rb.engine.adaptive_advance(f, pos, vel, 0.0, rb.m_pr, rb.e, 3.0, 0.25, store_every=1, max_rows=4096, arith="strict", **par)
+    op = O.make_params(GCtimestep=0.25, **par)
+    for i in range(n):
+        nseg, rows, seglog, cnt = O.adaptive_c(of, op, pos[i], vel[i], 0.0, rb.m_pr, rb.e, 3.0)
+        if nseg < 0:
+            assert o["status"][i] == nseg
+            continue
+        assert o["status"][i] == 1 and o["nseg"][i] == nseg
+        mine = o["rows"][i, :o["nstored"][i]]
+        assert len(mine) == len(rows)
+        assert np.max(np.abs(mine[:, 0] - rows[:, 0])) < 1e-9
+        assert H.vec_relerr(mine[:, 1:4], rows[:, 1:4]) < 1e-7
