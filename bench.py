@@ -43,6 +43,15 @@ def algorithmic_flops(nstep, naccpt, ncalls):
     return nstep * (11 * F_RHS + F_STAGE) + naccpt * F_RHS + ncalls * (F_RHS + 60)
 
 
+WORKLOAD_NAME = {
+    "particle": "config2: 1M protons per GPU / EarthDipole / Particle.advance(10 s) / cyclotronresolution 20 / "
+                "KE 0.1-10 MeV / seed 20260201",
+    "gc": "config3: electrons / DoubleDipole / GuidingCenter.advance (TaoChanBrizard) / GCtimestep 0.1 / KE 50 keV-1 MeV / "
+          "seed 20260301",
+    "belt": "config5: electrons / VarEarthDipole(0.1, 10 s) / GuidingCenter.advance / GCtimestep 0.05 / seed 20260501",
+}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -101,7 +110,49 @@ def make_ensemble(world, rank, n_per_gpu, workload):
         cols = [ic["t0"][sl], ic["x"][sl], ic["y"][sl], ic["z"][sl], mom[:, 0], mom[:, 1], mom[:, 2]]
         return dict(cols=[np.ascontiguousarray(c) for c in cols], mass=np.ascontiguousarray(ic["mass"][sl]),
                     charge=np.ascontiguousarray(ic["charge"][sl]))
+    if workload in ("gc", "belt"):
+        ic = synth.config3_electrons(n_total) if workload == "gc" else synth.config5_belt(n_total)
+        sl = slice(rank, n_total, world)
+        field = gc_field(workload)
+        pos = np.column_stack([ic["x"][sl], ic["y"][sl], ic["z"][sl]])
+        ppar, mu = engine.gc_construct(field, ic["t0"][sl], pos, ic["v"][sl], ic["pa"][sl], ic["mass"][sl], arith="fast")
+        cols = [ic["t0"][sl], pos[:, 0], pos[:, 1], pos[:, 2], ppar]
+        return dict(cols=[np.ascontiguousarray(c) for c in cols], mass=np.ascontiguousarray(ic["mass"][sl]),
+                    charge=np.ascontiguousarray(ic["charge"][sl]), mu=mu, v=np.ascontiguousarray(ic["v"][sl]),
+                    dt=np.full(len(mu), GC_DT[workload]))
     raise ValueError(workload)
+
+
+GC_DT = {"gc": 0.1, "belt": 0.05}          # params["GCtimestep"] of configs 3 and 5
+
+
+def gc_field(workload):
+    from rapt_b200 import fields
+    return fields.DoubleDipole() if workload == "gc" else fields.VarEarthDipole(0.1, 10)
+
+
+def gc_flops(workload, nstep, ncalls):
+    """6 RHS + stage sums per attempted step, HINIT per row; RHS = n_B field evaluations + 176."""
+    f_b, n_b = (48, 7) if workload == "gc" else (40, 9)
+    f_rhs = n_b * f_b + 176
+    return nstep * (6 * f_rhs + 4 * 64 + 20) + ncalls * (f_rhs + 40)
+
+
+def cpu_sample_gc(workload, n_sample, delta, nthreads):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    from rapt_b200 import synth
+    ic = synth.config3_electrons(n_sample) if workload == "gc" else synth.config5_belt(n_sample)
+    f = O.make_field("DoubleDipole") if workload == "gc" else O.make_field("VarEarthDipole", 0.1, 10)
+    pos = np.column_stack([ic["x"], ic["y"], ic["z"]])
+    ppar, mu = O.gc_construct(f, ic["t0"], pos, ic["v"], ic["pa"], ic["mass"])
+    st = np.column_stack([ic["t0"], pos, ppar])
+    t = time.perf_counter()
+    o = O.gc_advance(f, O.make_params(), st, mu, ic["v"], ic["mass"], ic["charge"], GC_DT[workload], delta, store_every=0,
+                     nthreads=nthreads)
+    el = time.perf_counter() - t
+    steps = int(o["counters"][:, 1].sum())
+    return steps / el, steps, el
 
 
 def cpu_sample(n_sample, delta, nthreads):
@@ -131,18 +182,18 @@ def run_reference(args):
     n_sample = args.cpu_sample
     vals = []
     for i in range(args.warmup + args.steps):
-        v, steps, el = cpu_sample(n_sample, DELTA, cores)
+        v, steps, el = (cpu_sample(n_sample, DELTA, cores) if args.workload == "particle"
+                        else cpu_sample_gc(args.workload, n_sample, DELTA, cores))
         if i >= args.warmup:
             vals.append((v, steps, el))
     steps = sum(s for _, s, _ in vals); el = sum(e for _, _, e in vals)
     value = steps / el
-    sample = f"first {n_sample} protons of the config-2 ensemble, advance({DELTA} s) each, OpenMP x{cores}"
+    sample = f"first {n_sample} tracers of the {WORKLOAD_NAME[args.workload].split(':')[0]} ensemble, advance({DELTA} s) each, OpenMP x{cores}"
     print(json.dumps({
         "impl": "reference", "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / max(len(vals), 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config2: protons / EarthDipole / Particle.advance(10 s) / cyclotronresolution 20",
-                   "sample": sample},
+        "config": {"workload": WORKLOAD_NAME[args.workload], "sample": sample},
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -155,7 +206,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="particle")
+    ap.add_argument("--workload", default="particle", choices=["particle", "gc", "belt"])
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
     ap.add_argument("--delta", type=float, default=DELTA)
     ap.add_argument("--cpu-sample", type=int, default=8192)
@@ -180,15 +231,19 @@ def main():
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     _lib.init(local)
-    field = fields.EarthDipole()
+    is_gc = args.workload != "particle"
+    field = gc_field(args.workload) if is_gc else fields.EarthDipole()
     n = args.n_per_gpu
     ens = make_ensemble(world, rank, n, args.workload)
+    ncol = len(ens["cols"])
     pristine = [torch.tensor(c, device=dev) for c in ens["cols"]]
     mass = torch.tensor(ens["mass"], device=dev); charge = torch.tensor(ens["charge"], device=dev)
+    if is_gc:
+        gmu = torch.tensor(ens["mu"], device=dev); gv = torch.tensor(ens["v"], device=dev); gdt = torch.tensor(ens["dt"], device=dev)
     out = engine.alloc_outputs(n, dev)
     work = [torch.empty_like(c) for c in pristine]
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    gathered = torch.empty((world, n, 7), dtype=torch.float64, device=dev) if world > 1 else None
+    gathered = torch.empty((world, n, ncol), dtype=torch.float64, device=dev) if world > 1 else None
     nbins = 64
     hist_edges = torch.logspace(4.5, 7.5, nbins + 1, dtype=torch.float64, device=dev)
 
@@ -198,13 +253,19 @@ def main():
         flush.fill_(1)                                                   # L2 flush between steps
         if timed_events is not None:
             timed_events[0].record()
-        engine.particle_advance_dev(field, work, mass, charge, args.delta, out, arith=args.arith, **PARAMS)
+        if is_gc:
+            engine.gc_advance_dev(field, work, gmu, gv, mass, charge, gdt, args.delta, out, arith=args.arith)
+        else:
+            engine.particle_advance_dev(field, work, mass, charge, args.delta, out, arith=args.arith, **PARAMS)
         if world > 1:
             fin = torch.stack(work, dim=1)
             dist.all_gather_into_tensor(gathered.view(-1), fin.view(-1))
-            p2 = (fin[:, 4:7] ** 2).sum(1)
-            ke_ev = (torch.sqrt(1 + p2 / (mass * 299792458.0) ** 2) - 1) * mass * 299792458.0 ** 2 / 1.602176565e-19
-            h = torch.histc(torch.log10(ke_ev), bins=nbins, min=4.5, max=7.5)
+            if is_gc:      # diagnostic: histogram of the radial distance (drift-shell occupation)
+                h = torch.histc(torch.sqrt((fin[:, 1:4] ** 2).sum(1)) / 6378137.0, bins=nbins, min=0.0, max=16.0)
+            else:          # diagnostic: kinetic-energy histogram
+                p2 = (fin[:, 4:7] ** 2).sum(1)
+                ke_ev = (torch.sqrt(1 + p2 / (mass * 299792458.0) ** 2) - 1) * mass * 299792458.0 ** 2 / 1.602176565e-19
+                h = torch.histc(torch.log10(ke_ev), bins=nbins, min=4.5, max=7.5)
             dist.all_reduce(h)
         if timed_events is not None:
             timed_events[1].record()
@@ -243,7 +304,7 @@ def main():
 
     # ---- end to end through the host-buffer C ABI (pinned inputs, H2D + D2H inside the timed region)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not is_gc:
         pin = [torch.tensor(c).pin_memory() for c in ens["cols"]]
         pm = torch.tensor(ens["mass"]).pin_memory(); pq = torch.tensor(ens["charge"]).pin_memory()
         hwork = [torch.empty_like(c).pin_memory() for c in pin]
@@ -282,10 +343,29 @@ def main():
         e2e = {"value": float(st2[0]) * args.steps / float(tt[0]), "unit": "particle-steps/s",
                "h2d_bytes_per_step": n * 9 * 8, "d2h_bytes_per_step": n * (7 * 8 + 2 * 8 + 4 * 4 + 3 * 4)}
 
+    if not args.no_e2e and is_gc:
+        # guiding-centre workloads: host-buffer C ABI (numpy in, numpy out; H2D + D2H inside the call)
+        st_host = np.column_stack(ens["cols"])
+        engine.gc_advance(field, st_host, ens["mu"], ens["v"], ens["mass"], ens["charge"], ens["dt"], args.delta,
+                          store_every=0, arith=args.arith)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            oh = engine.gc_advance(field, st_host, ens["mu"], ens["v"], ens["mass"], ens["charge"], ens["dt"], args.delta,
+                                   store_every=0, arith=args.arith)
+        el = time.perf_counter() - t0
+        tt = torch.tensor([el], dtype=torch.float64, device=dev)
+        st2 = torch.tensor([float(oh["counters"][:, 1].astype(np.int64).sum())], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(st2)
+        e2e = {"value": float(st2[0]) * args.steps / float(tt[0]), "unit": "particle-steps/s",
+               "h2d_bytes_per_step": n * 10 * 8, "d2h_bytes_per_step": n * (5 * 8 + 8 + 4 * 4 + 3 * 4)}
+
     if rank == 0:
-        flops = algorithmic_flops(nstep, naccpt, ncalls)           # all ranks, one step
+        flops = gc_flops(args.workload, nstep, ncalls) if is_gc else algorithmic_flops(nstep, naccpt, ncalls)
         achieved = flops / world / (ms_per_step * 1e-3) / 1e12     # per GPU: the kernel's own rate
-        io_bytes = n * (9 * 8 + 7 * 8 + 2 * 8 + 7 * 4)
+        io_bytes = n * ((10 * 8 + 5 * 8 + 8 + 7 * 4) if is_gc else (9 * 8 + 7 * 8 + 2 * 8 + 7 * 4))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -295,10 +375,8 @@ def main():
             "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config2: 1M protons per GPU / EarthDipole / Particle.advance(10 s) / "
-                                   "cyclotronresolution 20 / KE 0.1-10 MeV / seed 20260201",
-                       "particles_per_gpu": n, "delta_s": args.delta, "arith": args.arith,
-                       "l2": "512 MiB flush write between steps (inputs 72 MB < L2)",
+            "config": {"workload": WORKLOAD_NAME[args.workload], "particles_per_gpu": n, "delta_s": args.delta, "arith": args.arith,
+                       "l2": "512 MiB flush write between steps (inputs < L2)",
                        "particle_steps_per_bench_step": nstep, "accepted": naccpt, "output_rows": ncalls,
                        "solver_failures": int(n * world - nok),     # members whose row loop ended on scipy's nsteps=500
                                                                    # limit, exactly as the reference's does (checked vs the oracle)
@@ -313,7 +391,7 @@ def main():
                          # 522 MB + 310 MB.  4.6x the algorithmic state I/O because tracers are fetched in
                          # longest-first order, i.e. as scattered 8-byte accesses (32-byte sectors); at 0.36 s
                          # per launch that is 2 GB/s and irrelevant to this compute-bound kernel.
-                         "traffic": 831857152 if (n == N_PER_GPU and args.delta == DELTA) else None,
+                         "traffic": 831857152 if (n == N_PER_GPU and args.delta == DELTA and not is_gc) else None,
                          "peak_source": "FP64 DFMA microbenchmark measured in this run (rapt_b200_fp64_peak); "
                                         "MEASURED_PEAKS.json has HBM and bf16 only",
                          "algorithmic_flop_per_step": flops / nstep,
@@ -324,9 +402,10 @@ def main():
             res["e2e"] = e2e
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            v, steps, el = cpu_sample(args.cpu_sample, args.delta, cores)
+            v, steps, el = (cpu_sample_gc(args.workload, min(args.cpu_sample, 2048), args.delta, cores) if is_gc
+                            else cpu_sample(args.cpu_sample, args.delta, cores))
             res["cpu_baseline"] = {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": "port",
-                                   "sample": f"first {args.cpu_sample} protons of the same ensemble, advance({args.delta} s), "
+                                   "sample": f"first {min(args.cpu_sample, 2048) if is_gc else args.cpu_sample} tracers of the same ensemble, advance({args.delta} s), "
                                              f"{steps} steps in {el:.1f} s, C oracle port with OpenMP"}
         print(json.dumps(res))
     if world > 1:
