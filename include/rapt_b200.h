@@ -13,6 +13,8 @@
  *   - arrays are contiguous little-endian float64 / int32.  Ensemble state is structure-of-arrays.
  *   - `_dev` variants take DEVICE pointers and a cudaStream_t (as void*) and do no host<->device
  *     copies and no synchronisation; the plain variants take HOST pointers, copy in, run, copy out.
+ *   - one host thread per call; `_dev` calls share library-owned scratch (work queue counters, the
+ *     longest-first ordering buffers), so issue them on one stream or otherwise order them yourself.
  *   - there is NO CPU fallback: without a CUDA device every compute entry returns RAPT_E_NODEVICE.
  *
  * Trajectory rows: 8 doubles (64 B) per stored row, particle-major:

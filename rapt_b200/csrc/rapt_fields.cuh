@@ -84,6 +84,21 @@ template <int KIND> struct Field {
         (KIND == 3);
     static constexpr bool TIME_DEP = (KIND == 4) || (KIND == 100);
     static constexpr bool UNIFORM = (KIND == 2) || (KIND == 3);
+    // B(t, x) = tfactor(t) * Bspace(x): lets the guiding-centre stencil evaluate the time factor once per
+    // right-hand side instead of once per stencil point (fast flavour; VarEarthDipole, fields.py:469-470)
+    static constexpr bool SEPARABLE = (KIND == 4) && !RAPT_STRICT;
+
+    static RAPT_DEV double tfactor(const FieldP &f, double t)
+    {
+        return 1 + f.prm[0] * sin(2 * RAPT_PI * t / f.prm[1]);
+    }
+    static RAPT_DEV void Bspace(const FieldP &f, double x, double y, double z, double &bx, double &by, double &bz)
+    {
+        const double ir = fast_rsqrt(x * x + y * y + z * z), ir2 = ir * ir;
+        const double w = (-RAPT_EARTH_B0 * (RAPT_EARTH_RE * RAPT_EARTH_RE * RAPT_EARTH_RE)) * (ir2 * ir2 * ir);
+        const double tz = 3 * z;
+        bx = w * (tz * x); by = w * (tz * y); bz = w * fma(2 * z, z, -fma(x, x, y * y));
+    }
 
     static RAPT_DEV void B(const FieldP &f, double t, double x, double y, double z,
                            double &bx, double &by, double &bz)

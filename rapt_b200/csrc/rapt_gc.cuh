@@ -22,12 +22,14 @@ namespace RAPT_NS {
 using rapt::ParamsP;
 using rapt::AdvArgs;
 
-// |B| and b at one point
+// |B| and b at one point.  tf: time factor of a separable field (already evaluated by the caller).
 template <class F>
-RAPT_DEV void mag_and_unit(const FieldP &f, double t, double x, double y, double z,
+RAPT_DEV void mag_and_unit(const FieldP &f, double t, double tf, double x, double y, double z,
                            double &m, double &ux, double &uy, double &uz)
 {
-    double bx, by, bz; F::B(f, t, x, y, z, bx, by, bz);
+    double bx, by, bz;
+    if (F::SEPARABLE) { F::Bspace(f, x, y, z, bx, by, bz); bx *= tf; by *= tf; bz *= tf; }
+    else F::B(f, t, x, y, z, bx, by, bz);
 #if RAPT_STRICT
     m = sqrt(dot3(bx, by, bz, bx, by, bz));
     ux = bx / m; uy = by / m; uz = bz / m;
@@ -40,7 +42,7 @@ RAPT_DEV void mag_and_unit(const FieldP &f, double t, double x, double y, double
 
 // gradB (fields.py:125-131) and curlb (fields.py:191-200) from one pass over the six shifted points
 template <class F>
-RAPT_DEV void grad_and_curl(const FieldP &f, double t, double x, double y, double z,
+RAPT_DEV void grad_and_curl(const FieldP &f, double t, double tf, double x, double y, double z,
                             double (&g)[3], double (&c)[3])
 {
     if (F::UNIFORM) { g[0] = g[1] = g[2] = 0; c[0] = c[1] = c[2] = 0; return; }
@@ -53,11 +55,11 @@ RAPT_DEV void grad_and_curl(const FieldP &f, double t, double x, double y, doubl
     const double i2d = 1.0 / (2 * d);
 #define RAPT_FD(a, b) (((a) - (b)) * i2d)
 #endif
-    mag_and_unit<F>(f, t, x + d, y, z, mp, pxx, pxy, pxz); mag_and_unit<F>(f, t, x - d, y, z, mm, mxx, mxy, mxz);
+    mag_and_unit<F>(f, t, tf, x + d, y, z, mp, pxx, pxy, pxz); mag_and_unit<F>(f, t, tf, x - d, y, z, mm, mxx, mxy, mxz);
     g[0] = RAPT_FD(mp, mm);
-    mag_and_unit<F>(f, t, x, y + d, z, mp, pyx, pyy, pyz); mag_and_unit<F>(f, t, x, y - d, z, mm, myx, myy, myz);
+    mag_and_unit<F>(f, t, tf, x, y + d, z, mp, pyx, pyy, pyz); mag_and_unit<F>(f, t, tf, x, y - d, z, mm, myx, myy, myz);
     g[1] = RAPT_FD(mp, mm);
-    mag_and_unit<F>(f, t, x, y, z + d, mp, pzx, pzy, pzz); mag_and_unit<F>(f, t, x, y, z - d, mm, mzx, mzy, mzz);
+    mag_and_unit<F>(f, t, tf, x, y, z + d, mp, pzx, pzy, pzz); mag_and_unit<F>(f, t, tf, x, y, z - d, mm, mzx, mzy, mzz);
     g[2] = RAPT_FD(mp, mm);
     (void)pxx; (void)mxx; (void)pyy; (void)myy; (void)pzz; (void)mzz;
 #if RAPT_STRICT
@@ -82,14 +84,16 @@ RAPT_DEV void gc_rhs(const FieldP &f, const GcConst &c, int eom, int equatorial,
 {
     const double m = c.mass, q = c.q, mu = c.mu, ppar = Y[3];
     double bx, by, bz, gB[3], cb[3];
-    F::B(f, t, Y[0], Y[1], Y[2], bx, by, bz);
+    double tf = 1.0;
+    if (F::SEPARABLE) { tf = F::tfactor(f, t); F::Bspace(f, Y[0], Y[1], Y[2], bx, by, bz); bx *= tf; by *= tf; bz *= tf; }
+    else F::B(f, t, Y[0], Y[1], Y[2], bx, by, bz);
 #if !RAPT_STRICT
     // fast flavour: one rsqrt for |B| and b, reciprocals instead of divisions
     const double bb = dot3(bx, by, bz, bx, by, bz), ib = fast_rsqrt(bb);
     const double Bmag = bb * ib;
     const double ux = bx * ib, uy = by * ib, uz = bz * ib;
     const double iq = fast_rcp(q);
-    grad_and_curl<F>(f, t, Y[0], Y[1], Y[2], gB, cb);
+    grad_and_curl<F>(f, t, tf, Y[0], Y[1], Y[2], gB, cb);
     if (eom == 0) {
         const double pm = ppar / (m * RAPT_C_LIGHT);
         const double g2 = 1 + 2 * mu * Bmag / (m * RAPT_C_LIGHT * RAPT_C_LIGHT) + pm * pm;
@@ -99,7 +103,9 @@ RAPT_DEV void gc_rhs(const FieldP &f, const GcConst &c, int eom, int equatorial,
         const double iBsp = fast_rcp(dot3(Bsx, Bsy, Bsz, ux, uy, uz));
         double ex = 0, ey = 0, ez = 0, dbx = 0, dby = 0, dbz = 0;
         if (F::HAS_E) F::E(f, t, Y[0], Y[1], Y[2], ex, ey, ez);
-        if (F::TIME_DEP) { if (!f.is_static) F::dbdt(f, t, Y[0], Y[1], Y[2], dbx, dby, dbz); }
+        // a separable field changes its magnitude, not its direction: db/dt = 0 (the reference's central
+        // difference of unit vectors returns pure round-off, ~1e-13, there)
+        if (F::TIME_DEP && !F::SEPARABLE) { if (!f.is_static) F::dbdt(f, t, Y[0], Y[1], Y[2], dbx, dby, dbz); }
         const double mg = mu * ig;
         const double Esx = ex - (ppar * dbx + mg * gB[0]) * iq;
         const double Esy = ey - (ppar * dby + mg * gB[1]) * iq;
@@ -137,7 +143,7 @@ RAPT_DEV void gc_rhs(const FieldP &f, const GcConst &c, int eom, int equatorial,
 #else
     const double Bmag = sqrt(dot3(bx, by, bz, bx, by, bz));
     const double ux = bx / Bmag, uy = by / Bmag, uz = bz / Bmag;
-    grad_and_curl<F>(f, t, Y[0], Y[1], Y[2], gB, cb);
+    grad_and_curl<F>(f, t, tf, Y[0], Y[1], Y[2], gB, cb);
     if (eom == 0) {
         const double pm = ppar / (m * RAPT_C_LIGHT);
         const double gamma = sqrt(1 + 2 * mu * Bmag / (m * RAPT_C_LIGHT * RAPT_C_LIGHT) + pm * pm);
