@@ -17,7 +17,7 @@ static bool use_rkn(const rapt::AdvArgs &a) { return a.f.is_static && !a.p.enfor
 template <int KIND> static cudaError_t go_particle(const rapt::AdvArgs &a, int grid, cudaStream_t s)
 {
 #if !RAPT_STRICT
-    if (use_rkn(a)) k_particle_rkn<Field<KIND>><<<grid, 128, 0, s>>>(a);
+    if (use_rkn(a)) k_particle_rkn<Field<KIND>><<<(grid * 128 + RAPT_RKN_THREADS - 1) / RAPT_RKN_THREADS, RAPT_RKN_THREADS, 0, s>>>(a);
     else
 #endif
     k_particle_dop853<Field<KIND>><<<grid, 128, 0, s>>>(a);
@@ -39,7 +39,10 @@ int particle_blocks_per_sm(int rkn)
 {
     int nb = 0;
 #if !RAPT_STRICT
-    if (rkn) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_particle_rkn<Field<0>>, 128, 0); return nb; }
+    if (rkn) {   // in units of 128 lanes, rounded up: surplus blocks of the persistent kernel find the queue empty
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_particle_rkn<Field<0>>, RAPT_RKN_THREADS, 0);
+        return (nb * RAPT_RKN_THREADS + 127) / 128;
+    }
 #endif
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_particle_dop853<Field<0>>, 128, 0);
     return nb;

@@ -48,6 +48,39 @@ RAPT_DEV double fast_rcp(double x)
     e = fma(-x, y, 1.0);
     return fma(y, e, y);
 }
+// log and exp for the step-size controllers: branch-free, ~3e-14 relative, positive normal arguments
+// (log) and |y| < 700 (exp).  The library versions are ~100 instructions each with slow paths.
+RAPT_DEV double fast_log(double x)
+{
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    double m = __hiloint2double(hi, lo);                    // [1, 2)
+    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }       // [sqrt(1/2), sqrt(2))
+    const double s = (m - 1.0) * fast_rcp(m + 1.0), s2 = s * s;
+    double p = 1.0 / 15.0;
+    p = fma(p, s2, 1.0 / 13.0); p = fma(p, s2, 1.0 / 11.0); p = fma(p, s2, 1.0 / 9.0); p = fma(p, s2, 1.0 / 7.0);
+    p = fma(p, s2, 1.0 / 5.0); p = fma(p, s2, 1.0 / 3.0); p = fma(p, s2, 1.0);
+    return fma((double)e, 0.6931471805599453, 2.0 * s * p);
+}
+RAPT_DEV double fast_exp(double y)
+{
+    const double n = rint(y * 1.4426950408889634);
+    const double f = fma(-n, 0.6931471805599453, y);        // |f| <= 0.3466
+    double p = 1.0 / 39916800.0;
+    p = fma(p, f, 1.0 / 3628800.0); p = fma(p, f, 1.0 / 362880.0); p = fma(p, f, 1.0 / 40320.0); p = fma(p, f, 1.0 / 5040.0);
+    p = fma(p, f, 1.0 / 720.0); p = fma(p, f, 1.0 / 120.0); p = fma(p, f, 1.0 / 24.0); p = fma(p, f, 1.0 / 6.0);
+    p = fma(p, f, 0.5); p = fma(p, f, 1.0); p = fma(p, f, 1.0);
+    return __hiloint2double(__double2hiint(p) + ((int)n << 20), __double2loint(p));
+}
+// one Newton step: ~2^-45; enough for the error-norm scale factors 1/(atol + rtol |y|)
+RAPT_DEV double fast_rcp1(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return fma(y, fma(-x, y, 1.0), y);
+}
 RAPT_DEV double fast_rsqrt(double x)
 {
     double y;

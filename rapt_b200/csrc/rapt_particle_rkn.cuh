@@ -20,6 +20,12 @@
 #pragma once
 #include "rapt_particle.cuh"
 
+#ifndef RAPT_RKN_MINB
+#define RAPT_RKN_MINB 4
+#endif
+#ifndef RAPT_RKN_THREADS
+#define RAPT_RKN_THREADS 128
+#endif
 namespace RAPT_NS {
 
 // K = dp/dt = q (E + P x B / (gamma m)), Particle.py:295
@@ -39,16 +45,20 @@ RAPT_DEV void lorentz_K(const FieldP &f, double q, double qg, double t, const do
 }
 
 template <class F>
-__global__ void __launch_bounds__(128, 3) k_particle_rkn(const AdvArgs a)
+#ifdef RAPT_RKN_MAXNREG
+__global__ void __maxnreg__(RAPT_RKN_MAXNREG) k_particle_rkn(const AdvArgs a)
+#else
+__global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rkn(const AdvArgs a)
+#endif
+
 {
     const double rtol = a.p.rtol, atol = a.p.atol;
     const double beta = 0.1, safe = 0.9, fac1 = 0.3, fac2 = 6.0, uround = 2.3e-16;
     const double expo1 = 1.0 / 8.0 - beta * 0.2, facc1 = 1.0 / fac1, facc2 = 1.0 / fac2;
-    const double pf0 = pow(1e-4, beta);
+    const double lf0 = beta * -9.210340371976182;            // beta * log(1e-4): log of facold^beta at the start of a call
 
-    double sb_[3];
-    double x[3], p[3], K1[3], K2[3], K3[3], K4[3], K5[3], K6[3], K7[3], K8[3], K9[3], K10[3], X[3], P[3], kout[3];
-    double t = 0, h = 0, hg = 0, xend = 0, tstop = 0, tlim = 0, dt = 0, facold_b = 0, hmax = 0, tin = 0, dnf = 0, hnew = 0;
+    double x[3], p[3], K1[3], X[3], P[3];
+    double t = 0, h = 0, xend = 0, tstop = 0, tlim = 0, dt = 0, lfacold = 0, hmax = 0;
     double igm = 1, qg = 0, q = 0;
     int pid = -1;
     int nstep = 0, naccpt = 0, nrejct = 0, ncalls = 0, nstep_row = 0, naccpt_row = 0;
@@ -57,7 +67,112 @@ __global__ void __launch_bounds__(128, 3) k_particle_rkn(const AdvArgs a)
     double *myrows = nullptr;
 
     for (;;) {
-        // ---- (A) particle finished?  write it back and fetch the next one
+        // ---- (A) one step attempt: failure checks, clip the step to the row end.  The loop is ordered
+        // step -> write back / fetch -> HINIT so that the divergent parts (B), (C) sit at the END of an
+        // iteration: the warp reconverges at the loop's back edge and runs the step with all lanes.
+        // (With HINIT in front of the step the lanes that skipped it ran ahead: 19 of 32 lanes per issue.)
+        if (have && !need_row) {
+        if (nstep_row > 500) st = ST_NMAX;
+        else if (0.1 * fabs(h) <= fabs(t) * uround) st = ST_HSMALL;
+        if (st != ST_OK) { rowidx++; need_row = true; }   // failed row is still appended (Particle.py:304-307)
+        else {
+        if ((t + 1.01 * h - xend) > 0.0) { h = xend - t; last = true; }
+        nstep_row++; nstep++;
+        const double hg = h * igm;
+        double K2[3], K3[3], K4[3], K5[3], K6[3], K7[3], K8[3], K9[3], K10[3], K11[3], K12[3];
+#define RKN_STAGE(PSUM, XSUM, CS, KOUT)                                                            \
+        {                                                                                          \
+            _Pragma("unroll") for (int i = 0; i < 3; i++) { P[i] = p[i] + h * (PSUM); X[i] = x[i] + hg * (XSUM); } \
+            lorentz_K<F>(a.f, q, qg, t + (CS) * h, X, P, KOUT);                                     \
+        }
+        RKN_STAGE(T8(A2_1) * K1[i], T8(A2_1) * p[i], T8(C2), K2)
+        RKN_STAGE(T8(A3_1) * K1[i] + T8(A3_2) * K2[i],
+                  TN(RS3) * p[i] + h * (TN(AA3_1) * K1[i]), T8(C3), K3)
+        RKN_STAGE(T8(A4_1) * K1[i] + T8(A4_3) * K3[i],
+                  TN(RS4) * p[i] + h * (TN(AA4_1) * K1[i] + TN(AA4_2) * K2[i]), T8(C4), K4)
+        RKN_STAGE(T8(A5_1) * K1[i] + T8(A5_3) * K3[i] + T8(A5_4) * K4[i],
+                  TN(RS5) * p[i] + h * (TN(AA5_1) * K1[i] + TN(AA5_2) * K2[i] + TN(AA5_3) * K3[i]), T8(C5), K5)
+        RKN_STAGE(T8(A6_1) * K1[i] + T8(A6_4) * K4[i] + T8(A6_5) * K5[i],
+                  TN(RS6) * p[i] + h * (TN(AA6_1) * K1[i] + TN(AA6_3) * K3[i] + TN(AA6_4) * K4[i]), T8(C6), K6)
+        RKN_STAGE(T8(A7_1) * K1[i] + T8(A7_4) * K4[i] + T8(A7_5) * K5[i] + T8(A7_6) * K6[i],
+                  TN(RS7) * p[i] + h * (TN(AA7_1) * K1[i] + TN(AA7_3) * K3[i] + TN(AA7_4) * K4[i] + TN(AA7_5) * K5[i]), T8(C7), K7)
+        RKN_STAGE(T8(A8_1) * K1[i] + T8(A8_4) * K4[i] + T8(A8_5) * K5[i] + T8(A8_6) * K6[i] + T8(A8_7) * K7[i],
+                  TN(RS8) * p[i] + h * (TN(AA8_1) * K1[i] + TN(AA8_3) * K3[i] + TN(AA8_4) * K4[i] + TN(AA8_5) * K5[i] + TN(AA8_6) * K6[i]), T8(C8), K8)
+        RKN_STAGE(T8(A9_1) * K1[i] + T8(A9_4) * K4[i] + T8(A9_5) * K5[i] + T8(A9_6) * K6[i] + T8(A9_7) * K7[i] + T8(A9_8) * K8[i],
+                  TN(RS9) * p[i] + h * (TN(AA9_1) * K1[i] + TN(AA9_3) * K3[i] + TN(AA9_4) * K4[i] + TN(AA9_5) * K5[i] + TN(AA9_6) * K6[i] + TN(AA9_7) * K7[i]), T8(C9), K9)
+        RKN_STAGE(T8(A10_1) * K1[i] + T8(A10_4) * K4[i] + T8(A10_5) * K5[i] + T8(A10_6) * K6[i] + T8(A10_7) * K7[i] + T8(A10_8) * K8[i] + T8(A10_9) * K9[i],
+                  TN(RS10) * p[i] + h * (TN(AA10_1) * K1[i] + TN(AA10_3) * K3[i] + TN(AA10_4) * K4[i] + TN(AA10_5) * K5[i] + TN(AA10_6) * K6[i] + TN(AA10_7) * K7[i] + TN(AA10_8) * K8[i]), T8(C10), K10)
+        RKN_STAGE(T8(A11_1) * K1[i] + T8(A11_4) * K4[i] + T8(A11_5) * K5[i] + T8(A11_6) * K6[i] + T8(A11_7) * K7[i] + T8(A11_8) * K8[i] + T8(A11_9) * K9[i] + T8(A11_10) * K10[i],
+                  TN(RS11) * p[i] + h * (TN(AA11_1) * K1[i] + TN(AA11_3) * K3[i] + TN(AA11_4) * K4[i] + TN(AA11_5) * K5[i] + TN(AA11_6) * K6[i] + TN(AA11_7) * K7[i] + TN(AA11_8) * K8[i] + TN(AA11_9) * K9[i]), T8(C11), K11)
+        RKN_STAGE(T8(A12_1) * K1[i] + T8(A12_4) * K4[i] + T8(A12_5) * K5[i] + T8(A12_6) * K6[i] + T8(A12_7) * K7[i] + T8(A12_8) * K8[i] + T8(A12_9) * K9[i] + T8(A12_10) * K10[i] + T8(A12_11) * K11[i],
+                  TN(RS12) * p[i] + h * (TN(AA12_1) * K1[i] + TN(AA12_3) * K3[i] + TN(AA12_4) * K4[i] + TN(AA12_5) * K5[i] + TN(AA12_6) * K6[i] + TN(AA12_7) * K7[i] + TN(AA12_8) * K8[i] + TN(AA12_9) * K9[i] + TN(AA12_10) * K10[i]), 1.0, K12)
+#undef RKN_STAGE
+        // new state (b-weights) in X, P and the two error estimators
+        double err = 0, err2 = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const double sb = T8(B1) * K1[i] + T8(B6) * K6[i] + T8(B7) * K7[i] + T8(B8) * K8[i] + T8(B9) * K9[i] + T8(B10) * K10[i] + T8(B11) * K11[i] + T8(B12) * K12[i];
+            P[i] = p[i] + h * sb;
+            X[i] = x[i] + hg * (TN(SB) * p[i] + h * (TN(BA1) * K1[i] + TN(BA6) * K6[i] + TN(BA7) * K7[i] + TN(BA8) * K8[i] + TN(BA9) * K9[i] + TN(BA10) * K10[i] + TN(BA11) * K11[i]));
+            const double e5p = T8(ER1) * K1[i] + T8(ER6) * K6[i] + T8(ER7) * K7[i] + T8(ER8) * K8[i] + T8(ER9) * K9[i] + T8(ER10) * K10[i] + T8(ER11) * K11[i] + T8(ER12) * K12[i];
+            const double e3p = sb - T8(BHH1) * K1[i] - T8(BHH2) * K9[i] - T8(BHH3) * K12[i];
+            const double e5x = igm * (TN(SER) * p[i] + h * (TN(ERA1) * K1[i] + TN(ERA4) * K4[i] + TN(ERA5) * K5[i] + TN(ERA6) * K6[i] + TN(ERA7) * K7[i] + TN(ERA8) * K8[i] + TN(ERA9) * K9[i] + TN(ERA10) * K10[i] + TN(ERA11) * K11[i]));
+            const double e3x = igm * (TN(SW) * p[i] + h * (TN(WA1) * K1[i] + TN(WA4) * K4[i] + TN(WA5) * K5[i] + TN(WA6) * K6[i] + TN(WA7) * K7[i] + TN(WA8) * K8[i] + TN(WA9) * K9[i] + TN(WA10) * K10[i] + TN(WA11) * K11[i]));
+            const double iskx = fast_rcp1(atol + rtol * fmax(fabs(x[i]), fabs(X[i])));
+            const double iskp = fast_rcp1(atol + rtol * fmax(fabs(p[i]), fabs(P[i])));
+            const double a3 = e3x * iskx, b3 = e3p * iskp, a5 = e5x * iskx, b5 = e5p * iskp;
+            err2 += a3 * a3 + b3 * b3; err += a5 * a5 + b5 * b5;
+        }
+        double deno = err + 0.01 * err2;
+        if (deno <= 0.0) deno = 1.0;
+        err = fabs(h) * err * fast_rsqrt(6 * deno);
+        if (err <= 1.0) {
+            // accepted.  The controller's new step is only consumed when the row continues.
+            if (!last) {
+                // fac11 / facold^beta = exp(expo1 log(err) - beta log(facold)): one log and one exp, both
+                // branch-free polynomial forms (~3e-14): this path runs at ~3 lanes in 9 of 10 iterations,
+                // so its length matters
+                const double lg = fast_log(fmax(err, 1e-300));
+                double fac = fast_exp(fma(expo1, lg, -lfacold));
+                fac = fmax(facc2, fmin(facc1, fac / safe));
+                double hnew = h / fac;
+                if (fabs(hnew) > hmax) hnew = hmax;
+                if (reject) hnew = fmin(fabs(hnew), fabs(h));
+                lfacold = beta * fmax(lg, -9.210340371976182);       // facold = max(err, 1e-4)
+                t = t + h;
+                h = hnew;
+                reject = false;
+            } else t = t + h;
+            naccpt++; naccpt_row++;
+            lorentz_K<F>(a.f, q, qg, t, X, P, K1);           // FSAL: k1 = f(t+h, ynew); the step becomes the state
+#pragma unroll
+            for (int i = 0; i < 3; i++) { x[i] = X[i]; p[i] = P[i]; }
+            if (last) {
+                // ---- output row complete (Particle.py:305-309)
+                rowidx++;
+                if (myrows && a.store_every > 0 && (rowidx % a.store_every) == 0 && nst < a.max_rows) {
+                    double2 *r = reinterpret_cast<double2 *>(myrows + (size_t)nst * 8);
+                    double tag = a.segtag ? (double)a.segtag[pid] : (double)nstep;
+                    r[0] = make_double2(xend, x[0]); r[1] = make_double2(x[1], x[2]);
+                    r[2] = make_double2(p[0], p[1]); r[3] = make_double2(p[2], tag);
+                    nst++;
+                }
+                if (a.p.check_adiabaticity) {
+                    const double yy[6] = {x[0], x[1], x[2], p[0], p[1], p[2]};
+                    if (particle_isadiabatic<F>(a.f, a.p, xend, yy, a.mass[pid], a.charge[pid])) st = ST_ADIABATIC;
+                }
+                need_row = true;
+            }
+        } else {
+            if (a.p.dop853_reject_rule == 1) h = h / fmin(facc1, RAPT_POW(err, expo1) / safe);
+            else h = h / facc1;                              // scipy 1.18.1: 0.3 h whatever err is
+            reject = true;
+            if (naccpt_row >= 1) nrejct++;
+            last = false;
+        }
+        }   // st == ST_OK
+        }   // have && !need_row
+        // ---- (B) particle finished?  write it back and fetch the next one
         if (have && need_row && !(st == ST_OK && t < tlim)) {
             if (a.seg_tstop) {                               // sliced adaptive epoch: keep the call's state
                 a.seg_x[pid] = t; a.seg_dt[pid] = dt; a.seg_row[pid] = rowidx;
@@ -118,272 +233,52 @@ __global__ void __launch_bounds__(128, 3) k_particle_rkn(const AdvArgs a)
                 }
             }
             have = true; need_row = true;
-            if (!(dt > 0.0) || dt > 1e300) { st = RAPT_ST_HSMALL; continue; }   // degenerate output step (B = 0 or inf, bad
-                                                                             // resolution): the reference would never return
-            if (!(t < tlim)) continue;                       // delta <= 0 (or beyond this slice): nothing to do
-            lorentz_K<F>(a.f, q, qg, t, x, p, K1);           // k1 = f(t, y)
+            // degenerate output step (B = 0 or inf, bad resolution): the reference would never return.
+            // delta <= 0 (or beyond this slice): nothing to do
+            if (!(dt > 0.0) || dt > 1e300) st = RAPT_ST_HSMALL;
+            else if (t < tlim) lorentz_K<F>(a.f, q, qg, t, x, p, K1);          // k1 = f(t, y)
         }
-        // ---- (B) one step attempt; stage 1 = HINIT's Euler probe for lanes that start an output row
-        bool accepted = false, skip = false, hin = false;
+        // ---- (C) a new output row is a new solver call: xend, hmax, HINIT
+        if (need_row && st == ST_OK && t < tlim) {
+            xend = t + dt;                                   // Particle.py:305 (also the row's time label)
+            hmax = fabs(xend - t);
+            double iskx[3], iskp[3];
+            double dny = 0, dnf = 0, s1 = 0;
 #pragma unroll
-        for (int s = 1; s <= 14; s++) {
-            bool active = !skip;
-            switch (s) {
-            case 1:
-                active = need_row;
-                if (active) {
-                    // new output row = new solver call: xend, HINIT part 1
-                    xend = t + dt;                           // Particle.py:305 (also the row's time label)
-                    hmax = fabs(xend - t);
-                    double dny = 0;
-                    dnf = 0;
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        const double iskx = fast_rcp(atol + rtol * fabs(x[i])), iskp = fast_rcp(atol + rtol * fabs(p[i]));
-                        double a_ = p[i] * igm * iskx, b_ = x[i] * iskx;
-                        double c_ = K1[i] * iskp, d_ = p[i] * iskp;
-                        dnf += a_ * a_ + c_ * c_; dny += b_ * b_ + d_ * d_;
-                    }
-                    h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
-                    h = fmin(h, hmax);
-#pragma unroll
-                    for (int i = 0; i < 3; i++) { X[i] = x[i] + h * (p[i] * igm); P[i] = p[i] + h * K1[i]; }
-                    tin = t + h;
-                    hin = true;
-                }
-                break;
-            case 2:
-                if (hin) {
-                    // HINIT part 2: f1 - k1 = ((P - p)/gm, K' - K1) = (h K1/gm, kout - K1)
-                    double der2 = 0;
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        const double iskx = fast_rcp(atol + rtol * fabs(x[i])), iskp = fast_rcp(atol + rtol * fabs(p[i]));
-                        double a_ = h * K1[i] * igm * iskx, c_ = (kout[i] - K1[i]) * iskp;
-                        der2 += a_ * a_ + c_ * c_;
-                    }
-                    der2 = sqrt(der2) / h;
-                    double der12 = fmax(fabs(der2), sqrt(dnf));
-                    double h1;
-                    if (der12 <= 1e-15) h1 = fmax(1e-6, fabs(h) * 1e-3);
-                    else {
-                        double tq = 0.01 / der12, hm2 = hmax * hmax, hm4 = hm2 * hm2;
-                        if (tq > hm4 * hm4 * 1.000001) h1 = hmax;      // h1 >= hmax: not the minimum
-                        else h1 = pow(tq, 1.0 / 8.0);
-                    }
-                    h = fmin(fmin(100 * fabs(h), h1), hmax);
-                    facold_b = pf0; last = false; reject = false; nstep_row = 0; naccpt_row = 0;   // facold = 1e-4
-                    ncalls++;
-                    need_row = false;
-                }
-                // step prologue (every lane): failure checks, clip the step to the row end
-                if (nstep_row > 500) st = ST_NMAX;
-                else if (0.1 * fabs(h) <= fabs(t) * uround) st = ST_HSMALL;
-                if (st != ST_OK) {
-                    rowidx++; need_row = true; skip = true; active = false;   // failed row is still appended (Particle.py:304-307)
-                } else {
-                    if ((t + 1.01 * h - xend) > 0.0) { h = xend - t; last = true; }
-                    nstep_row++; nstep++;
-                    hg = h * igm;
-#pragma unroll
-                    for (int i = 0; i < 3; i++) { P[i] = p[i] + h * T8(A2_1) * K1[i]; X[i] = x[i] + hg * T8(A2_1) * p[i]; }
-                    tin = t + T8(C2) * h;
-                }
-                break;
-            case 3:
-                if (active) {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        K2[i] = kout[i];
-                        P[i] = p[i] + h * (T8(A3_1) * K1[i] + T8(A3_2) * K2[i]);
-                        X[i] = x[i] + hg * (TN(RS3) * p[i] + h * (TN(AA3_1) * K1[i]));
-                    }
-                    tin = t + T8(C3) * h;
-                }
-                break;
-            case 4:
-                if (active) {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        K3[i] = kout[i];
-                        P[i] = p[i] + h * (T8(A4_1) * K1[i] + T8(A4_3) * K3[i]);
-                        X[i] = x[i] + hg * (TN(RS4) * p[i] + h * (TN(AA4_1) * K1[i] + TN(AA4_2) * K2[i]));
-                    }
-                    tin = t + T8(C4) * h;
-                }
-                break;
-            case 5:
-                if (active) {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        K4[i] = kout[i];
-                        P[i] = p[i] + h * (T8(A5_1) * K1[i] + T8(A5_3) * K3[i] + T8(A5_4) * K4[i]);
-                        X[i] = x[i] + hg * (TN(RS5) * p[i] + h * (TN(AA5_1) * K1[i] + TN(AA5_2) * K2[i] + TN(AA5_3) * K3[i]));
-                    }
-                    tin = t + T8(C5) * h;
-                }
-                break;
-            case 6:
-                if (active) {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        K5[i] = kout[i];
-                        P[i] = p[i] + h * (T8(A6_1) * K1[i] + T8(A6_4) * K4[i] + T8(A6_5) * K5[i]);
-                        X[i] = x[i] + hg * (TN(RS6) * p[i] + h * (TN(AA6_1) * K1[i] + TN(AA6_3) * K3[i] + TN(AA6_4) * K4[i]));
-                    }
-                    tin = t + T8(C6) * h;
-                }
-                break;
-            case 7:
-                if (active) {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        K6[i] = kout[i];
-                        P[i] = p[i] + h * (T8(A7_1) * K1[i] + T8(A7_4) * K4[i] + T8(A7_5) * K5[i] + T8(A7_6) * K6[i]);
-                        X[i] = x[i] + hg * (TN(RS7) * p[i] + h * (TN(AA7_1) * K1[i] + TN(AA7_3) * K3[i] + TN(AA7_4) * K4[i] + TN(AA7_5) * K5[i]));
-                    }
-                    tin = t + T8(C7) * h;
-                }
-                break;
-            case 8:
-                if (active) {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        K7[i] = kout[i];
-                        P[i] = p[i] + h * (T8(A8_1) * K1[i] + T8(A8_4) * K4[i] + T8(A8_5) * K5[i] + T8(A8_6) * K6[i] + T8(A8_7) * K7[i]);
-                        X[i] = x[i] + hg * (TN(RS8) * p[i] + h * (TN(AA8_1) * K1[i] + TN(AA8_3) * K3[i] + TN(AA8_4) * K4[i] + TN(AA8_5) * K5[i] + TN(AA8_6) * K6[i]));
-                    }
-                    tin = t + T8(C8) * h;
-                }
-                break;
-            case 9:
-                if (active) {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        K8[i] = kout[i];
-                        P[i] = p[i] + h * (T8(A9_1) * K1[i] + T8(A9_4) * K4[i] + T8(A9_5) * K5[i] + T8(A9_6) * K6[i] + T8(A9_7) * K7[i] + T8(A9_8) * K8[i]);
-                        X[i] = x[i] + hg * (TN(RS9) * p[i] + h * (TN(AA9_1) * K1[i] + TN(AA9_3) * K3[i] + TN(AA9_4) * K4[i] + TN(AA9_5) * K5[i] + TN(AA9_6) * K6[i] + TN(AA9_7) * K7[i]));
-                    }
-                    tin = t + T8(C9) * h;
-                }
-                break;
-            case 10:
-                if (active) {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        K9[i] = kout[i];
-                        P[i] = p[i] + h * (T8(A10_1) * K1[i] + T8(A10_4) * K4[i] + T8(A10_5) * K5[i] + T8(A10_6) * K6[i] + T8(A10_7) * K7[i] + T8(A10_8) * K8[i] + T8(A10_9) * K9[i]);
-                        X[i] = x[i] + hg * (TN(RS10) * p[i] + h * (TN(AA10_1) * K1[i] + TN(AA10_3) * K3[i] + TN(AA10_4) * K4[i] + TN(AA10_5) * K5[i] + TN(AA10_6) * K6[i] + TN(AA10_7) * K7[i] + TN(AA10_8) * K8[i]));
-                    }
-                    tin = t + T8(C10) * h;
-                }
-                break;
-            case 11:
-                if (active) {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        K10[i] = kout[i];
-                        P[i] = p[i] + h * (T8(A11_1) * K1[i] + T8(A11_4) * K4[i] + T8(A11_5) * K5[i] + T8(A11_6) * K6[i] + T8(A11_7) * K7[i] + T8(A11_8) * K8[i] + T8(A11_9) * K9[i] + T8(A11_10) * K10[i]);
-                        X[i] = x[i] + hg * (TN(RS11) * p[i] + h * (TN(AA11_1) * K1[i] + TN(AA11_3) * K3[i] + TN(AA11_4) * K4[i] + TN(AA11_5) * K5[i] + TN(AA11_6) * K6[i] + TN(AA11_7) * K7[i] + TN(AA11_8) * K8[i] + TN(AA11_9) * K9[i]));
-                    }
-                    tin = t + T8(C11) * h;
-                }
-                break;
-            case 12:
-                if (active) {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        K2[i] = kout[i];
-                        P[i] = p[i] + h * (T8(A12_1) * K1[i] + T8(A12_4) * K4[i] + T8(A12_5) * K5[i] + T8(A12_6) * K6[i] + T8(A12_7) * K7[i] + T8(A12_8) * K8[i] + T8(A12_9) * K9[i] + T8(A12_10) * K10[i] + T8(A12_11) * K2[i]);
-                        X[i] = x[i] + hg * (TN(RS12) * p[i] + h * (TN(AA12_1) * K1[i] + TN(AA12_3) * K3[i] + TN(AA12_4) * K4[i] + TN(AA12_5) * K5[i] + TN(AA12_6) * K6[i] + TN(AA12_7) * K7[i] + TN(AA12_8) * K8[i] + TN(AA12_9) * K9[i] + TN(AA12_10) * K10[i]));
-                    }
-                    tin = t + 1.0 * h;
-                }
-                break;
-            case 13:
-                // new state (b-weights); kept in X, P: it is also the input of the FSAL evaluation.
-                // No field evaluation in this pass (its own basic block keeps the coefficient set small).
-                if (active) {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        sb_[i] = T8(B1) * K1[i] + T8(B6) * K6[i] + T8(B7) * K7[i] + T8(B8) * K8[i] + T8(B9) * K9[i] + T8(B10) * K10[i] + T8(B11) * K2[i] + T8(B12) * kout[i];
-                        P[i] = p[i] + h * sb_[i];
-                        X[i] = x[i] + hg * (TN(SB) * p[i] + h * (TN(BA1) * K1[i] + TN(BA6) * K6[i] + TN(BA7) * K7[i] + TN(BA8) * K8[i] + TN(BA9) * K9[i] + TN(BA10) * K10[i] + TN(BA11) * K2[i]));
-                    }
-                }
-                active = false;
-                break;
-            default:   // 14: error estimate, accept/reject; FSAL evaluation for accepted lanes
-                if (active) {
-                    double err = 0, err2 = 0;
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        const double e5p = T8(ER1) * K1[i] + T8(ER6) * K6[i] + T8(ER7) * K7[i] + T8(ER8) * K8[i] + T8(ER9) * K9[i] + T8(ER10) * K10[i] + T8(ER11) * K2[i] + T8(ER12) * kout[i];
-                        const double e3p = sb_[i] - T8(BHH1) * K1[i] - T8(BHH2) * K9[i] - T8(BHH3) * kout[i];
-                        const double e5x = igm * (TN(SER) * p[i] + h * (TN(ERA1) * K1[i] + TN(ERA4) * K4[i] + TN(ERA5) * K5[i] + TN(ERA6) * K6[i] + TN(ERA7) * K7[i] + TN(ERA8) * K8[i] + TN(ERA9) * K9[i] + TN(ERA10) * K10[i] + TN(ERA11) * K2[i]));
-                        const double e3x = igm * (TN(SW) * p[i] + h * (TN(WA1) * K1[i] + TN(WA4) * K4[i] + TN(WA5) * K5[i] + TN(WA6) * K6[i] + TN(WA7) * K7[i] + TN(WA8) * K8[i] + TN(WA9) * K9[i] + TN(WA10) * K10[i] + TN(WA11) * K2[i]));
-                        const double iskx = fast_rcp(atol + rtol * fmax(fabs(x[i]), fabs(X[i])));
-                        const double iskp = fast_rcp(atol + rtol * fmax(fabs(p[i]), fabs(P[i])));
-                        const double a3 = e3x * iskx, b3 = e3p * iskp, a5 = e5x * iskx, b5 = e5p * iskp;
-                        err2 += a3 * a3 + b3 * b3; err += a5 * a5 + b5 * b5;
-                    }
-                    double deno = err + 0.01 * err2;
-                    if (deno <= 0.0) deno = 1.0;
-                    err = fabs(h) * err * fast_rsqrt(6 * deno);
-                    if (err <= 1.0) {
-                        // accepted.  The controller's new step is only consumed when the row continues.
-                        if (!last) {
-                            // err^expo1 and (for the next step's Lund stabilisation) max(err,1e-4)^beta share
-                            // one log: this path runs at ~3 lanes in 9 of 10 iterations, so its length matters
-                            const double lg = log(err);
-                            double fac11 = exp(expo1 * lg);
-                            double fac = fac11 / facold_b;
-                            fac = fmax(facc2, fmin(facc1, fac / safe));
-                            hnew = h / fac;
-                            if (fabs(hnew) > hmax) hnew = hmax;
-                            if (reject) hnew = fmin(fabs(hnew), fabs(h));
-                            facold_b = (err > 1e-4) ? exp(beta * lg) : pf0;      // facold^beta for the next step
-                        }
-                        naccpt++; naccpt_row++;
-                        accepted = true;
-                        tin = t + h;
-                    } else {
-                        if (a.p.dop853_reject_rule == 1) h = h / fmin(facc1, RAPT_POW(err, expo1) / safe);
-                        else h = h / facc1;                  // scipy 1.18.1: 0.3 h whatever err is
-                        reject = true;
-                        if (naccpt_row >= 1) nrejct++;
-                        last = false;
-                        active = false;
-                    }
-                }
-                break;
+            for (int i = 0; i < 3; i++) {
+                iskx[i] = fast_rcp1(atol + rtol * fabs(x[i])); iskp[i] = fast_rcp1(atol + rtol * fabs(p[i]));
+                const double a_ = p[i] * igm * iskx[i], b_ = x[i] * iskx[i];
+                const double c_ = K1[i] * iskp[i], d_ = p[i] * iskp[i], e_ = K1[i] * iskx[i];
+                dnf += a_ * a_ + c_ * c_; dny += b_ * b_ + d_ * d_; s1 = fma(e_, e_, s1);
             }
-            if (active) lorentz_K<F>(a.f, q, qg, tin, X, P, kout);
-        }
-        if (accepted) {
-            // FSAL: k1 = f(t+h, ynew); the step becomes the state
+            double h0 = 1e-6;
+            if (!(dnf <= 1e-10 || dny <= 1e-10)) { const double qq = dny * fast_rcp(dnf); h0 = (qq * fast_rsqrt(qq)) * 0.01; }
+            h0 = fmin(h0, hmax);
+            // Euler probe f1 = f(t + h0, y + h0 f0); f1 - f0 = (h0 K1 / gm, K' - K1)
 #pragma unroll
-            for (int i = 0; i < 3; i++) { K1[i] = kout[i]; x[i] = X[i]; p[i] = P[i]; }
-            t = t + h;
-            if (last) {
-                // ---- output row complete (Particle.py:305-309)
-                rowidx++;
-                if (myrows && a.store_every > 0 && (rowidx % a.store_every) == 0 && nst < a.max_rows) {
-                    double2 *r = reinterpret_cast<double2 *>(myrows + (size_t)nst * 8);
-                    double tag = a.segtag ? (double)a.segtag[pid] : (double)nstep;
-                    r[0] = make_double2(xend, x[0]); r[1] = make_double2(x[1], x[2]);
-                    r[2] = make_double2(p[0], p[1]); r[3] = make_double2(p[2], tag);
-                    nst++;
-                }
-                if (a.p.check_adiabaticity) {
-                    const double yy[6] = {x[0], x[1], x[2], p[0], p[1], p[2]};
-                    if (particle_isadiabatic<F>(a.f, a.p, xend, yy, a.mass[pid], a.charge[pid])) st = ST_ADIABATIC;
-                }
-                need_row = true;
-            } else {
-                h = hnew;
-                reject = false;
+            for (int i = 0; i < 3; i++) { X[i] = x[i] + h0 * (p[i] * igm); P[i] = p[i] + h0 * K1[i]; }
+            double Kp[3];
+            lorentz_K<F>(a.f, q, qg, t + h0, X, P, Kp);
+            double d2 = 0;
+#pragma unroll
+            for (int i = 0; i < 3; i++) { const double c_ = (Kp[i] - K1[i]) * iskp[i]; d2 = fma(c_, c_, d2); }
+            const double hi = h0 * igm;
+            d2 = fma(hi * hi, s1, d2);
+            // der2 = sqrt(d2)/h0, der12 = max(der2, sqrt(dnf)), h1 = (0.01/der12)^(1/8): compared in squares, the
+            // root is only taken when h1 could be the minimum
+            const double ih0 = fast_rcp(h0);
+            const double d12 = fmax(d2 * ih0 * ih0, dnf);
+            double h1;
+            if (d12 <= 1e-30) h1 = fmax(1e-6, h0 * 1e-3);
+            else {
+                const double hm2 = hmax * hmax, hm4 = hm2 * hm2, hm8 = hm4 * hm4, hm16 = hm8 * hm8;
+                if (hm16 > 1e-280 && d12 * hm16 * 1.000003 < 1e-4) h1 = hmax;      // h1 > hmax: not the minimum
+                else h1 = pow(0.01 / sqrt(d12), 1.0 / 8.0);
             }
+            h = fmin(fmin(100 * h0, h1), hmax);
+            lfacold = lf0; last = false; reject = false; nstep_row = 0; naccpt_row = 0;   // facold = 1e-4
+            ncalls++;
+            need_row = false;
         }
     }
 }
