@@ -10,7 +10,7 @@
 #include "rapt_particle_rkn.cuh"
 #endif
 namespace RAPT_NS {
-// fast flavour, static field, no equatorial constraint -> the Nystrom-form kernel (12 warps/SM)
+// fast flavour, static field, no equatorial constraint -> the Nystrom-form kernel (16 warps/SM)
 #if !RAPT_STRICT
 static bool use_rkn(const rapt::AdvArgs &a) { return a.f.is_static && !a.p.enforce_equatorial && !getenv("RAPT_B200_NO_RKN"); }
 #endif
@@ -53,13 +53,14 @@ int particle_blocks_per_sm(int rkn)
 #ifdef RAPT_TU_GC
 #include "rapt_gc.cuh"
 #ifndef RAPT_GC_DEFAULT_BLOCKS
-#define RAPT_GC_DEFAULT_BLOCKS 3
+#define RAPT_GC_DEFAULT_BLOCKS 4
 #endif
 namespace RAPT_NS {
 static int gc_minb() { const char *e = getenv("RAPT_B200_GC_BLOCKS"); return e ? atoi(e) : RAPT_GC_DEFAULT_BLOCKS; }
 template <int KIND> static cudaError_t go_gc(const rapt::AdvArgs &a, int grid, cudaStream_t s)
 {
-    if (gc_minb() >= 3) k_gc_dopri5<Field<KIND>, 3><<<grid, 128, 0, s>>>(a);
+    if (gc_minb() >= 4) k_gc_dopri5<Field<KIND>, 4><<<grid, 128, 0, s>>>(a);
+    else if (gc_minb() == 3) k_gc_dopri5<Field<KIND>, 3><<<grid, 128, 0, s>>>(a);
     else k_gc_dopri5<Field<KIND>, 2><<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
 }
@@ -78,7 +79,8 @@ cudaError_t launch_gc(const rapt::AdvArgs &a, int grid, cudaStream_t s)
 int gc_blocks_per_sm()
 {
     int nb = 0;
-    if (gc_minb() >= 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gc_dopri5<Field<1>, 3>, 128, 0);
+    if (gc_minb() >= 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gc_dopri5<Field<1>, 4>, 128, 0);
+    else if (gc_minb() == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gc_dopri5<Field<1>, 3>, 128, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gc_dopri5<Field<1>, 2>, 128, 0);
     return nb;
 }

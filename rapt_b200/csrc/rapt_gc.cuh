@@ -226,7 +226,7 @@ RAPT_DEV bool gc_isadiabatic(const FieldP &f, const ParamsP &p, double t, const 
 #define RAPT_GC_POW(x, e) exp((e) * log(x))     // x > 0; ~1e-15 relative, no slow paths
 #endif
 
-// MINB = resident CTAs per SM the register allocation is tuned for (2: 255 regs, no spills; 3: 168 regs)
+// MINB = resident CTAs per SM the register allocation is tuned for (2: 255 regs, no spills; 3: 168 regs; 4: 128 regs, ~0.5 KB of spill traffic per step, fastest: profiles/r1_other_configs.md)
 template <class F, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
 {
@@ -320,7 +320,12 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
                         dnf += a_ * a_; dny += b_ * b_;
 #endif
                     }
+#if RAPT_STRICT
                     h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
+#else
+                    h = 1e-6;
+                    if (!(dnf <= 1e-10 || dny <= 1e-10)) { const double qq = dny * fast_rcp(dnf); h = (qq * fast_rsqrt(qq)) * 0.01; }
+#endif
                     h = fmin(h, hmax);
 #pragma unroll
                     for (int i = 0; i < 4; i++) yin[i] = y[i] + h * k1[i];
@@ -341,6 +346,7 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
                         der2 += d_ * d_;
 #endif
                     }
+#if RAPT_STRICT
                     der2 = sqrt(der2) / h;
                     double der12 = fmax(fabs(der2), sqrt(dnf));
                     double h1;
@@ -351,8 +357,17 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
                         if (tq > hm2 * hm2 * hmax * 1.000001) h1 = hmax;
                         else h1 = pow(tq, 1.0 / 5.0);
                     }
+#else
+                    // der12^2 = max(der2/h^2, dnf); h1 = (0.01/der12)^(1/5) = exp((log 0.01 - log(der12^2)/2)/5):
+                    // no square root or division, branch-free log/exp
+                    const double ih = fast_rcp(h);
+                    const double d12 = fmax(der2 * ih * ih, dnf);
+                    double h1;
+                    if (d12 <= 1e-30) h1 = fmax(1e-6, fabs(h) * 1e-3);
+                    else h1 = fast_exp(0.2 * fma(-0.5, fast_log(d12), -4.605170185988091));
+#endif
                     h = fmin(fmin(100 * fabs(h), h1), hmax);
-                    facold = 1e-4; last = false; reject = false; nstep_row = 0; naccpt_row = 0;
+                    facold = RAPT_STRICT ? 1e-4 : beta * -9.210340371976182; last = false; reject = false; nstep_row = 0; naccpt_row = 0;
                     ncalls++;
                     need_row = false;
                 }
@@ -424,18 +439,33 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
                 err += e * e;
 #endif
             }
+#if RAPT_STRICT
             err = sqrt(err / 4);
+#else
+            err *= 0.25;
+            err = (err > 0.0) ? err * fast_rsqrt(err) : 0.0;
+#endif
             if (err <= 1.0) {
                 double hnew = h;
                 if (!last) {
+#if RAPT_STRICT
                     double fac11 = RAPT_GC_POW(err, expo1);
                     double fac = fac11 / ((facold == 1e-4) ? pf0 : RAPT_GC_POW(facold, beta));
+#else
+                    // err^expo1 / facold^beta as one branch-free log and one exp; facold is carried as
+                    // beta * log(facold) (only read when the row continues, so only updated here)
+                    const double lg = fast_log(fmax(err, 1e-300));
+                    double fac = fast_exp(fma(expo1, lg, -facold));
+                    facold = beta * fmax(lg, -9.210340371976182);
+#endif
                     fac = fmax(facc2, fmin(facc1, fac / safe));
                     hnew = h / fac;
                     if (fabs(hnew) > hmax) hnew = hmax;
                     if (reject) hnew = fmin(fabs(hnew), fabs(h));
                 }
+#if RAPT_STRICT
                 facold = fmax(err, 1e-4);
+#endif
                 naccpt++; naccpt_row++;
 #pragma unroll
                 for (int i = 0; i < 4; i++) { k1[i] = kout[i]; y[i] = y1[i]; }
@@ -459,7 +489,11 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
                     reject = false;
                 }
             } else {
+#if RAPT_STRICT
                 double fac11 = RAPT_GC_POW(err, expo1);
+#else
+                double fac11 = fast_exp(expo1 * fast_log(fmin(err, 1e300)));
+#endif
                 h = h / fmin(facc1, fac11 / safe);
                 reject = true;
                 if (naccpt_row >= 1) nrejct++;

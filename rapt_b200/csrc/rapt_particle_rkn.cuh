@@ -7,16 +7,16 @@
 //     p'  = p + h sum_j b_j K_j                     x'  = x + (h/gm) (sb p + h sum_l (b.A)_l K_l)
 // and likewise for the two error estimators (tools/gen_coeffs.py forms A.A, b.A, er.A, w.A exactly from the
 // double tableau and rounds once).  Only 3 of the 6 components of each k-vector are stored: 33 doubles
-// instead of 60, ~165 registers instead of 255, so 12 warps/SM instead of 8 hide the FP64 dependency
+// instead of 60, 128 registers instead of 255, so 16 warps/SM instead of 8 hide the FP64 dependency
 // latency of the field evaluation (profiles/r1_particle_history.md).  Same step-control decisions as
 // k_particle_dop853: the estimators differ from the 6-component form only by its own cancellation
 // round-off (~1e-10 relative of err), positions by ~1 ulp per step.
 // Not used when params["enforce equatorial"] is set or the field is not static (gamma m then varies).
 //
-// The 14-pass stage loop is FULLY unrolled here: with 3-component vectors and the branch-free rsqrt the
-// whole step is ~2.5k SASS instructions, the 13 copies of the field evaluation write straight into their
-// K_l registers (no copies, no switch/branch overhead) and the loop still streams from the instruction
-// cache: 394 ms vs 482 ms for the rolled loop on config 2 (profiles/r1_particle_history.md).
+// The step is STRAIGHT-LINE code: with 3-component vectors and the branch-free rsqrt the 12 stages, the new
+// state and both error estimators are ~1.1k SASS instructions, the 13 copies of the field evaluation write
+// straight into their K_l registers (no copies, no switch/branch overhead) and the loop still streams from
+// the instruction cache (profiles/r1_particle_history.md: rolled 482 ms, unrolled 394 ms, this form 269 ms).
 #pragma once
 #include "rapt_particle.cuh"
 
