@@ -333,6 +333,44 @@ def case_e5():
          final=np.array(fin), nrows=np.array(nrows), totals=np.array(tot), mu=np.array(mu))
 
 
+def case_eye():
+    """GuidingCenter.geteye (GuidingCenter.py:608-624 -> flutils.eye, flutils.py:65-151).
+    pa 80: equatorial pitch angle >= 70 degrees, the spline/brentq/quad branch, UNMODIFIED reference.
+    pa 45: the Simpson branch, which raises NameError in the unmodified reference (`simps`, flutils.py:130,
+    is never imported; scipy.integrate.simpson is).  For that fixture only, the missing name is bound in the
+    imported module's namespace to simpson(y, x=x) -- no reference file is changed -- and the fixture says so."""
+    from rapt import flutils as rfu
+    from rapt.fieldline import Fieldline
+    from scipy.integrate import simpson
+    f = rf.EarthDipole()
+    v = ru.speedfromKE(1e6, m_el)
+    for pa, name in ((80, "eye_pa80"), (45, "eye_pa45_simpson")):
+        refshim.reset_params(rapt, GCtimestep=0.05)
+        g = rapt.GuidingCenter(pos=(5 * Re, 0, 0), v=v, pa=pa, mass=m_el, charge=-e, field=f)
+        g.advance(0.4)
+        patched = False
+        try:
+            out = g.geteye(step=3)
+        except NameError:
+            rfu.simps = lambda y, x: simpson(y, x=x)
+            patched = True
+            out = g.geteye(step=3)
+            del rfu.simps
+        Bm = g.getBm()[::3]
+        rows = g.trajectory[::3]
+        curves = []
+        for row, bm in zip(rows, Bm):
+            fl = Fieldline(row[:4], f, Bmax=bm); fl.trace()
+            curves.append(np.column_stack([fl.gets(), fl.getB()]))
+        k = max(len(cv) for cv in curves)
+        cur = np.full((len(curves), k, 2), np.nan)
+        for i, cv in enumerate(curves):
+            cur[i, :len(cv)] = cv
+        save(name, pos=np.array((5 * Re, 0, 0)), v=v, pa=float(pa), mass=m_el, charge=-e, delta=0.4,
+             params=parjson(GCtimestep=0.05), traj=g.trajectory, mu=g.mu, step=3, Bm=Bm, eye=out, curves=cur,
+             npts=np.array([len(cv) for cv in curves]), simps_name_bound=patched)
+
+
 def case_units():
     """Field operators and utils helpers at seeded points (fields.py:76-280, utils.py:29-433)."""
     rng = np.random.default_rng(7)
@@ -403,7 +441,7 @@ def case_units():
 CASES = {
     "g1": case_g1, "g1b": case_g1b, "pfields": case_pfields, "g2": case_g2, "gcfields": case_gcfields,
     "g3": case_g3, "e4": case_e4, "adip": case_adaptive_dipole, "e2": case_e2, "e3": case_e3,
-    "e5": case_e5, "units": case_units,
+    "e5": case_e5, "units": case_units, "eye": case_eye,
 }
 
 if __name__ == "__main__":

@@ -215,8 +215,11 @@ class GuidingCenter:
                                          params["fieldlineresolution"])[0])
 
     def geteye(self, step=1):
-        raise NotImplementedError("the second invariant (flutils.eye) is off the advance hot path and is broken in "
-                                  "the reference (flutils.py:130); see DESIGN.md 'out of scope'")
+        """(time, second invariant I) for every `step`-th row (rapt/GuidingCenter.py:608-624, flutils.py:65-151):
+        all field lines are traced in one device call, the quadrature is the reference's."""
+        rows = self.trajectory[::step]
+        res = engine.eye(self.field, rows[:, :4], self.getBm()[::step])
+        return np.column_stack([rows[:, 0], res])
 
 
 def _column_getter(index, what):

@@ -223,3 +223,30 @@ def test_bounce_period_device_closed_form(eng, arith):
     ok = np.isfinite(bp[:64])
     assert np.max(np.abs(bp[:64][ok] / host[ok] - 1)) < 1e-4
     assert np.median(np.abs(bp[:64][ok] / host[ok] - 1)) < 2e-6
+
+
+@pytest.mark.parametrize("name", ["eye_pa80", "eye_pa45_simpson"])
+def test_geteye_matches_reference(eng, name):
+    """GuidingCenter.geteye (GuidingCenter.py:608-624): the second invariant along a trajectory, field lines
+    traced on the device.  The golden values are the reference's own (see the fixture's note on `simps`)."""
+    import rapt_b200 as R
+    from rapt_b200 import GuidingCenter, params
+    from rapt_b200.fields import EarthDipole
+    d, par = H.load(name)
+    old = params["GCtimestep"]
+    params["GCtimestep"] = par["GCtimestep"]
+    try:
+        g = GuidingCenter(pos=tuple(d["pos"]), v=float(d["v"]), pa=float(d["pa"]), mass=float(d["mass"]),
+                          charge=float(d["charge"]), field=EarthDipole())
+        g.advance(float(d["delta"]))
+    finally:
+        params["GCtimestep"] = old
+    assert g.trajectory.shape == d["traj"].shape
+    out = g.geteye(step=int(d["step"]))
+    assert out.shape == d["eye"].shape
+    assert np.allclose(out[:, 0], d["eye"][:, 0], rtol=0, atol=1e-12)
+    assert np.max(np.abs(out[:, 1] / d["eye"][:, 1] - 1)) < 1e-7
+    # the same from the reference's own rows: isolates the trace + quadrature from the advance
+    ref_rows = d["traj"][::int(d["step"])]
+    val = eng.eye(EarthDipole(), ref_rows[:, :4], d["Bm"])
+    assert np.max(np.abs(val / d["eye"][:, 1] - 1)) < 1e-8

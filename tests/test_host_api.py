@@ -149,6 +149,23 @@ def test_halfbouncepath_host_leg_matches_reference():
         assert (2 / float(d["bs_v"])) * hp == float(d["bs_period"])
 
 
+def test_second_invariant_host_leg_matches_reference():
+    """The host leg of GuidingCenter.geteye (flutils.py:65-151: trimming to one point beyond each mirror
+    point, Simpson + closed-form end intervals below 70 degrees, spline/brentq/quad above) on the reference's
+    own traced field lines gives the reference's I exactly.  eye_pa45_simpson was generated with the name
+    `simps` (undefined in the reference, flutils.py:130) bound to scipy.integrate.simpson -- see its flag."""
+    from rapt_b200 import engine
+    for name, bound in (("eye_pa80", False), ("eye_pa45_simpson", True)):
+        d, _ = H.load(name)
+        assert bool(d["simps_name_bound"]) == bound
+        for i in range(len(d["Bm"])):
+            cv = d["curves"][i, :d["npts"][i]]
+            assert engine.eye_from_curve(cv[:, 0], cv[:, 1], float(d["Bm"][i])) == d["eye"][i, 1], (name, i)
+    # no mirror point on the line / equatorial particle -> 0 (flutils.py:106-109)
+    s = np.linspace(0, 1, 9); b = 1 + (s - 0.5) ** 2
+    assert engine.eye_from_curve(s, b, 0.9) == 0.0 and engine.eye_from_curve(s, b, 1.0) == 0.0
+
+
 def test_nystrom_tables_are_consistent_with_the_tableau():
     """rapt_particle_rkn.cuh integrates in Nystrom form with A.A, b.A, er.A, w.A (tools/gen_coeffs.py):
     check the generated constants against the DOP853 tableau and the order conditions they must inherit."""

@@ -181,3 +181,17 @@ def test_edge_cases():
     pp = O.make_params(cyclotronresolution=1e-4)
     o = O.particle_advance(f, pp, d["traj"][0], float(d["mass"]), float(d["charge"]), 1e6, max_rows=4)
     assert o["status"][0] == -2 and o["nrows"][0] == 2
+
+
+@pytest.mark.parametrize("name", ["eye_pa80", "eye_pa45_simpson"])
+def test_oracle_full_fieldline_traces_of_geteye(name):
+    """Fieldline(row[:4], field, Bmax=Bm).trace() as GuidingCenter.geteye calls it (GuidingCenter.py:620-622):
+    the oracle's RKF45 trace reproduces the reference's s and |B| along every traced line bit for bit."""
+    d, _ = H.load(name)
+    f = O.make_field("EarthDipole")
+    rows = d["traj"][::int(d["step"])]
+    for i, row in enumerate(rows):
+        curve, B, ds = O.fieldline_trace(f, row[:4], float(d["Bm"][i]))
+        k = int(d["npts"][i])
+        assert len(curve) == k
+        assert np.array_equal(curve[:, 0], d["curves"][i, :k, 0]) and np.array_equal(B, d["curves"][i, :k, 1])
