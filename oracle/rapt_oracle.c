@@ -33,10 +33,18 @@
 #define EARTH_RE 6378137.0             /* rapt/__init__.py:10 */
 
 enum { F_EARTHDIPOLE = 0, F_DOUBLEDIPOLE = 1, F_UNIFORMBZ = 2, F_CROSSEDEB = 3, F_VARDIPOLE = 4,
-       F_PARABOLIC = 5, F_CHARGEDDIPOLE = 100 /* examples/Creating new fields.ipynb cell 10 */ };
+       F_PARABOLIC = 5, F_GRID = 6 /* fields.py:513-814 */, F_CHARGEDDIPOLE = 100 /* examples/Creating new fields.ipynb cell 10 */ };
 enum { EOM_TAOCHANBRIZARD = 0, EOM_BRIZARDCHAN = 1, EOM_NORTHROPTELLER = 2 };
-enum { ST_OK = 1, ST_NMAX = -2, ST_HSMALL = -3, ST_GCITER = -5 };
+enum { ST_OK = 1, ST_NMAX = -2, ST_HSMALL = -3, ST_GCITER = -5, ST_FIELD = -6 /* Grid: ValueError, point outside the grid */ };
 enum { MODE_PARTICLE = 0, MODE_GC = 1 };
+
+/* fields.Grid (fields.py:513-814): six components sampled on a rectilinear grid at nt = 1..n time
+ * points, each component a C-ordered [nt][nx][ny][nz] array exactly as _set_interpolator builds them */
+typedef struct {
+    int nt, nx, ny, nz;
+    const double *t, *x, *y, *z;
+    const double *B[3], *E[3];
+} ogrid_t;
 
 typedef struct {
     int kind;
@@ -44,7 +52,12 @@ typedef struct {
     double prm[8];
     double gradstep;      /* _Field.gradientstepsize  fields.py:39 */
     double tstep;         /* _Field.timederivstepsize fields.py:40 */
+    const ogrid_t *grid;  /* F_GRID only */
 } ofield_t;
+
+/* set when a Grid field is evaluated outside its bounds: the reference raises ValueError there
+ * (scipy RegularGridInterpolator, bounds_error=True) and the advance in progress is abandoned */
+static __thread int g_field_err = 0;
 
 typedef struct {
     double rtol, atol;              /* params["solvertolerances"] __init__.py:27 */
@@ -58,6 +71,55 @@ typedef struct {
 /* --------------------------------------------------------------------------------------------
  * Field models: fields.py:301-317, 344-362, 376-390, 413-427, 455-470, 506-511
  * ------------------------------------------------------------------------------------------ */
+/* scipy 1.18.1 interpolate/_poly_common.pxi find_interval_ascending: the interval i with
+ * x[i] <= v < x[i+1], closed on the right at the last node; -1 outside [x[0], x[n-1]] (or NaN). */
+static int grid_interval(const double *x, int n, double v)
+{
+    if (!(x[0] <= v && v <= x[n - 1])) return -1;
+    if (v == x[n - 1]) return n - 2;
+    int low = 0, high = n - 2;
+    if (v < x[low + 1]) high = low;
+    while (low < high) {
+        int mid = (high + low) / 2;
+        if (v < x[mid]) high = mid;
+        else if (v >= x[mid + 1]) low = mid + 1;
+        else { low = mid; break; }
+    }
+    return low;
+}
+
+/* Grid.Bgrid / Grid.Egrid (fields.py:707-772) = three scipy RegularGridInterpolator(method="linear") calls:
+ * _rgi.py find_indices (index + normalised distance per dimension) and _evaluate_linear (the 2^d vertices
+ * of the cell in itertools.product order, first dimension slowest; weight = ((1*w0)*w1)*...; value += v*weight).
+ * Dimensions are (t, x, y, z) for two or more time points and (x, y, z) for one. */
+static void grid_eval(const ogrid_t *g, const double *const comp[3], const double tp[4], double out[3])
+{
+    const double *ax[4]; int n[4], nd = 0, idx[4]; double yd[4], v[4];
+    if (g->nt >= 2) { ax[nd] = g->t; n[nd] = g->nt; v[nd] = tp[0]; nd++; }
+    ax[nd] = g->x; n[nd] = g->nx; v[nd] = tp[1]; nd++;
+    ax[nd] = g->y; n[nd] = g->ny; v[nd] = tp[2]; nd++;
+    ax[nd] = g->z; n[nd] = g->nz; v[nd] = tp[3]; nd++;
+    for (int d = 0; d < nd; d++) {
+        idx[d] = grid_interval(ax[d], n[d], v[d]);
+        if (idx[d] < 0) { g_field_err = 1; out[0] = out[1] = out[2] = NAN; return; }
+        yd[d] = (v[d] - ax[d][idx[d]]) / (ax[d][idx[d] + 1] - ax[d][idx[d]]);
+    }
+    for (int c = 0; c < 3; c++) {
+        double value = 0.0;
+        for (int corner = 0; corner < (1 << nd); corner++) {
+            double weight = 1.0; long off = 0;
+            for (int d = 0; d < nd; d++) {
+                int up = (corner >> (nd - 1 - d)) & 1;
+                weight = weight * (up ? yd[d] : 1 - yd[d]);
+                off = off * n[d] + idx[d] + up;
+            }
+            double term = comp[c][off] * weight;
+            value = value + term;
+        }
+        out[c] = value;
+    }
+}
+
 static void field_B(const ofield_t *f, const double tp[4], double B[3])
 {
     double t = tp[0], x = tp[1], y = tp[2], z = tp[3];
@@ -89,6 +151,7 @@ static void field_B(const ofield_t *f, const double tp[4], double B[3])
         else B[0] = (z > 0 ? 1.0 : (z < 0 ? -1.0 : 0.0)) * EARTH_B0;
         B[1] = 0; B[2] = f->prm[1];
         break;
+    case F_GRID: grid_eval(f->grid, f->grid->B, tp, B); break;      /* fields.py:774-794 */
     case F_CHARGEDDIPOLE: {         /* notebook field; prm = {B0, Q, k} */
         double p = pow(x * x + y * y + z * z, 5.0 / 2.0);
         B[0] = f->prm[0] * (3 * x * z) / p; B[1] = f->prm[0] * (3 * y * z) / p;
@@ -98,11 +161,12 @@ static void field_B(const ofield_t *f, const double tp[4], double B[3])
     }
 }
 
-static int field_has_E(const ofield_t *f) { return f->kind == F_CROSSEDEB || f->kind == F_CHARGEDDIPOLE; }
+static int field_has_E(const ofield_t *f) { return f->kind == F_CROSSEDEB || f->kind == F_CHARGEDDIPOLE || f->kind == F_GRID; }
 
 static void field_E(const ofield_t *f, const double tp[4], double E[3])
 {
     E[0] = E[1] = E[2] = 0;         /* fields.py:59-74 */
+    if (f->kind == F_GRID) { grid_eval(f->grid, f->grid->E, tp, E); return; }      /* fields.py:796-814 */
     if (f->kind == F_CROSSEDEB) E[1] = f->prm[1];      /* fields.py:427; prm = {Bz, Ey} */
     else if (f->kind == F_CHARGEDDIPOLE) {
         double x = tp[1], y = tp[2], z = tp[3];
@@ -267,6 +331,7 @@ static int dop853(int n, rhs_fn f, void *ctx, double *xio, double *y, double xen
     nfcn += 2;
     int idid;
     for (;;) {
+        if (g_field_err) { idid = ST_FIELD; break; }
         if (nstep > nmax) { idid = ST_NMAX; break; }
         if (0.1 * fabs(h) <= fabs(x) * uround) { idid = ST_HSMALL; break; }
         if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = 1; }
@@ -356,6 +421,7 @@ static int dopri5(int n, rhs_fn f, void *ctx, double *xio, double *y, double xen
     nfcn += 2;
     int idid;
     for (;;) {
+        if (g_field_err) { idid = ST_FIELD; break; }
         if (nstep > nmax) { idid = ST_NMAX; break; }
         if (0.1 * fabs(h) <= fabs(x) * uround) { idid = ST_HSMALL; break; }
         if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = 1; }
@@ -589,6 +655,7 @@ static int particle_advance_one(const ofield_t *f, const oparams_t *p, double st
         double label = x + dt, xend = x + dt;                                       /* :305 */
         ocount_t c1 = { 0, 0, 0, 0 };
         int idid = dop853(6, particle_eom, &ctx, &x, y, xend, p->rtol, p->atol, p->dop853_reject_rule, &c1);
+        if (g_field_err) return ST_FIELD;      /* ValueError out of r.integrate(): no row appended */
         if (cnt) { cnt->nfcn += c1.nfcn; cnt->nstep += c1.nstep; cnt->naccpt += c1.naccpt; cnt->nrejct += c1.nrejct; }
         if (percall && *ncalls < max_calls) {
             long *q = percall + 4 * (*ncalls); q[0] = c1.nfcn; q[1] = c1.nstep; q[2] = c1.naccpt; q[3] = c1.nrejct;
