@@ -371,6 +371,69 @@ def case_eye():
              npts=np.array([len(cv) for cv in curves]), simps_name_bound=patched)
 
 
+def synth_grid_class():
+    class SynthGrid(rf.Grid):
+        """fields.Grid with the synthetic parser of rapt_b200/synth.py ("file name" = time index)."""
+        def parsefile(self, filename):
+            return synth.dipole_grid_slice(int(filename))
+    return SynthGrid
+
+
+def grid_checksum(files):
+    import hashlib
+    h = hashlib.sha256()
+    for fn in files:
+        g = synth.dipole_grid_slice(int(fn))
+        for k in ("x", "y", "z", "Bx", "By", "Bz", "Ex", "Ey", "Ez"):
+            h.update(np.ascontiguousarray(g[k]).tobytes())
+    return np.array(h.hexdigest())
+
+
+def case_grid():
+    """fields.Grid (fields.py:513-814), UNMODIFIED reference, synthetic data files (4 time points, so the
+    rolling three-point window is updated once during the advance, fields.py:697-705 and :737-738)."""
+    SynthGrid = synth_grid_class()
+    files = ["0", "1", "2", "3"]
+    rng = np.random.default_rng(11)
+    # field operators at points with ascending time (the window forgets earlier times once it moves)
+    f = SynthGrid(files)
+    npt = 10
+    pts = np.column_stack([np.sort(rng.uniform(0, 2.9, npt)), rng.uniform(3.3, 7.7, npt) * Re,
+                           rng.uniform(-1.7, 1.7, npt) * Re, rng.uniform(-2.7, 2.7, npt) * Re])
+    pts[3, 1] = f.Bxt_interp.grid[1][5]          # exactly on a node plane
+    rec = {k: [] for k in ("B", "E", "magB", "unitb", "gradB", "curlb", "lengthscale")}
+    for tp in pts:
+        rec["B"].append(f.B(tp)); rec["E"].append(f.E(tp)); rec["magB"].append(f.magB(tp))
+        rec["unitb"].append(f.unitb(tp)); rec["gradB"].append(f.gradB(tp)); rec["curlb"].append(f.curlb(tp))
+        rec["lengthscale"].append(f.lengthscale(tp))
+    out = {"pts": pts, "gradstep": f.gradientstepsize, "static": f.static}
+    out.update({k: np.array(v, dtype=float) for k, v in rec.items()})
+    # Particle: 1 MeV proton, crosses t = 1.5 s (window update)
+    v = ru.speedfromKE(1e6, m_pr); pa = 40 * np.pi / 180
+    pos = (6 * Re, 0, 0); vel = (0, -v * np.sin(pa), v * np.cos(pa))
+    p, L = run_particle(pos, vel, m_pr, e, SynthGrid(files), 2.6, cyclotronresolution=10)
+    # GuidingCenter: 1 MeV electron, pa 60
+    ve = ru.speedfromKE(1e6, m_el)
+    g, Lg = run_gc(pos, ve, 60, m_el, -e, SynthGrid(files), 2.6, GCtimestep=0.05)
+    # leaving the grid: ValueError, rows before it are kept (Particle.py:304-307)
+    refshim.reset_params(rapt, cyclotronresolution=10)
+    pe = rapt.Particle(pos=(7.9 * Re, 0, 0), vel=(v * 0.6, 0, v * 0.8), t0=0, mass=m_pr, charge=e, field=SynthGrid(files))
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            pe.advance(5.0)
+        raised = False
+    except ValueError:
+        raised = True
+    save("grid_synthetic", files=np.array(files), checksum=grid_checksum(files),
+         p_pos=np.array(pos, float), p_vel=np.array(vel), p_mass=m_pr, p_charge=e, p_delta=2.6,
+         p_params=parjson(cyclotronresolution=10), p_traj=p.trajectory, p_counters=L, p_tcur=p.tcur,
+         g_pos=np.array(pos, float), g_v=ve, g_pa=60.0, g_mass=m_el, g_charge=-e, g_delta=2.6,
+         g_params=parjson(GCtimestep=0.05), g_traj=g.trajectory, g_counters=Lg, g_tcur=g.tcur, g_mu=g.mu,
+         oob_pos=np.array((7.9 * Re, 0, 0)), oob_vel=np.array((v * 0.6, 0, v * 0.8)), oob_raised=raised,
+         oob_traj=pe.trajectory, **{"ops_" + k: v_ for k, v_ in out.items()})
+
+
 def case_units():
     """Field operators and utils helpers at seeded points (fields.py:76-280, utils.py:29-433)."""
     rng = np.random.default_rng(7)
@@ -441,7 +504,7 @@ def case_units():
 CASES = {
     "g1": case_g1, "g1b": case_g1b, "pfields": case_pfields, "g2": case_g2, "gcfields": case_gcfields,
     "g3": case_g3, "e4": case_e4, "adip": case_adaptive_dipole, "e2": case_e2, "e3": case_e3,
-    "e5": case_e5, "units": case_units, "eye": case_eye,
+    "e5": case_e5, "units": case_units, "eye": case_eye, "grid": case_grid,
 }
 
 if __name__ == "__main__":

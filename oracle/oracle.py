@@ -22,9 +22,15 @@ KIND = {"EarthDipole": 0, "DoubleDipole": 1, "UniformBz": 2, "UniformCrossedEB":
 EOM = {"TaoChanBrizardEOM": 0, "BrizardChanEOM": 1, "NorthropTellerEOM": 2}
 
 
+class OGrid(C.Structure):
+    _fields_ = [("nt", C.c_int), ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int),
+                ("t", C.c_void_p), ("x", C.c_void_p), ("y", C.c_void_p), ("z", C.c_void_p),
+                ("B", C.c_void_p * 3), ("E", C.c_void_p * 3)]
+
+
 class OField(C.Structure):
     _fields_ = [("kind", C.c_int), ("is_static", C.c_int), ("prm", C.c_double * 8),
-                ("gradstep", C.c_double), ("tstep", C.c_double)]
+                ("gradstep", C.c_double), ("tstep", C.c_double), ("grid", C.c_void_p)]
 
 
 class OParams(C.Structure):
@@ -90,6 +96,28 @@ def make_field(name, *args, gradstep=None, tstep=1e-3, static=None):
     f.gradstep = gs if gradstep is None else gradstep
     f.tstep = tstep
     f.is_static = int(st if static is None else static)
+    return f
+
+
+def make_grid_field(t, x, y, z, B, E, static=True, gradstep=1e-3 * Re, tstep=1e-3):
+    """fields.Grid (fields.py:513-814) from parsed data: t (nt,), x, y, z node coordinates, B and E as three
+    arrays each of shape (nt, nx, ny, nz) (or (nx, ny, nz) for a single time point).  Defaults follow the
+    reference constructor (gradientstepsize 1e-3 Re, static left True, fields.py:577-579)."""
+    f = OField()
+    f.kind = 6; f.is_static = int(static); f.gradstep = gradstep; f.tstep = tstep
+    g = OGrid()
+    keep = []
+    def arr(a):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64)); keep.append(a); return a.ctypes.data
+    t = np.atleast_1d(np.asarray(t, dtype=np.float64))
+    g.nt, g.nx, g.ny, g.nz = len(t), len(x), len(y), len(z)
+    g.t, g.x, g.y, g.z = arr(t), arr(x), arr(y), arr(z)
+    for i in range(3):
+        assert np.asarray(B[i]).size == g.nt * g.nx * g.ny * g.nz
+        g.B[i] = arr(B[i]); g.E[i] = arr(E[i])
+    keep.append(g)
+    f.grid = C.addressof(g)
+    f._keep = keep                      # the C side holds raw pointers into these
     return f
 
 

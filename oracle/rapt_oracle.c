@@ -770,6 +770,7 @@ static int gc_advance_one(const ofield_t *f, const oparams_t *p, int eom, double
     while (ok && x < t0 + delta) {                                       /* :452 */
         ocount_t c1 = { 0, 0, 0, 0 };
         int idid = dopri5(4, gc_eom, &ctx, &x, y, x + dt, p->rtol, p->atol, &c1);   /* :453 */
+        if (g_field_err) return ST_FIELD;      /* ValueError out of r.integrate(): no row appended */
         if (cnt) { cnt->nfcn += c1.nfcn; cnt->nstep += c1.nstep; cnt->naccpt += c1.naccpt; cnt->nrejct += c1.nrejct; }
         if (percall && *ncalls < max_calls) {
             long *q = percall + 4 * (*ncalls); q[0] = c1.nfcn; q[1] = c1.nstep; q[2] = c1.naccpt; q[3] = c1.nrejct;
@@ -1034,6 +1035,7 @@ void oracle_particle_advance(const ofield_t *f, const oparams_t *p, long n,
     for (long i = 0; i < n; i++) {
         double st[7] = { t[i], x[i], y[i], z[i], px[i], py[i], pz[i] };
         ocount_t c = { 0, 0, 0, 0 };
+        g_field_err = 0;
         long ri = 0, ns = 0, nc = 0;
         double *r = rows ? rows + (size_t)i * max_rows * 8 : NULL;
         if (r && store_every > 0 && max_rows > 0) { memcpy(r, st, sizeof st); r[7] = 0; ns = 1; }
@@ -1067,6 +1069,7 @@ void oracle_gc_advance(const ofield_t *f, const oparams_t *p, int eom, long n,
     for (long i = 0; i < n; i++) {
         double st[5] = { t[i], x[i], y[i], z[i], ppar[i] };
         ocount_t c = { 0, 0, 0, 0 };
+        g_field_err = 0;
         long ri = 0, ns = 0, nc = 0;
         double *r = rows ? rows + (size_t)i * max_rows * 8 : NULL;
         if (r && store_every > 0 && max_rows > 0) { memcpy(r, st, sizeof st); r[5] = mu[i]; r[6] = 0; r[7] = 0; ns = 1; }

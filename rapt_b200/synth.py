@@ -122,3 +122,22 @@ def config5_belt(n, seed=20260501):
     v = speed_from_ke(ke, m_el)
     return dict(x=x, y=y, z=z, v=v, pa=pa, t0=np.zeros(n),
                 mass=np.full(n, m_el), charge=np.full(n, -e), ke_ev=ke)
+
+
+def dipole_grid_slice(k, nx=21, ny=17, nz=25):
+    """One synthetic "data file" for fields.Grid, in the dictionary form Grid.parsefile must return
+    (rapt/fields.py:553-562): a dipole scaled by (1 + 0.02 k) plus a dawn-dusk electric field, sampled on
+    x in [3, 8] Re, y in [-2, 2] Re, z in [-3, 3] Re at time k seconds.  Only IEEE basic operations and
+    sqrt, so every machine regenerates the same bits (the golden fixtures store a checksum)."""
+    from . import Re, B0
+    x = np.linspace(3.0, 8.0, nx) * Re
+    y = np.linspace(-2.0, 2.0, ny) * Re
+    z = np.linspace(-3.0, 3.0, nz) * Re
+    X, Y, Z = np.meshgrid(x, y, z, indexing="ij")
+    r2 = X * X + Y * Y + Z * Z
+    r5 = r2 * r2 * np.sqrt(r2)
+    s = -B0 * (Re * Re * Re) * (1.0 + 0.02 * k)
+    zero = np.zeros_like(X)
+    return {"time": float(k), "x": x, "y": y, "z": z,
+            "Bx": s * (3.0 * X * Z) / r5, "By": s * (3.0 * Y * Z) / r5, "Bz": s * (2.0 * Z * Z - X * X - Y * Y) / r5,
+            "Ex": zero.copy(), "Ey": 1e-4 * (1.0 + 0.1 * k) * (X / Re) / 6.0, "Ez": zero.copy()}

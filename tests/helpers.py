@@ -63,3 +63,20 @@ def gpu_field(name, args):
 def oracle_field(name, args):
     import oracle as O
     return O.make_field(name, *args)
+
+
+def synthetic_grid(files=("0", "1", "2", "3")):
+    """The parsed synthetic data files of the Grid fixtures (rapt_b200/synth.py:dipole_grid_slice), stacked
+    the way Grid._set_interpolator stacks them: t (nt,), x, y, z, B and E as 3 arrays (nt, nx, ny, nz);
+    plus the sha256 the golden generator recorded for the same arrays."""
+    import hashlib
+    from rapt_b200 import synth
+    gs = [synth.dipole_grid_slice(int(fn)) for fn in files]
+    h = hashlib.sha256()
+    for g in gs:
+        for k in ("x", "y", "z", "Bx", "By", "Bz", "Ex", "Ey", "Ez"):
+            h.update(np.ascontiguousarray(g[k]).tobytes())
+    t = np.array([g["time"] for g in gs])
+    B = [np.stack([g[k] for g in gs]) for k in ("Bx", "By", "Bz")]
+    E = [np.stack([g[k] for g in gs]) for k in ("Ex", "Ey", "Ez")]
+    return dict(t=t, x=gs[0]["x"], y=gs[0]["y"], z=gs[0]["z"], B=B, E=E, sha256=h.hexdigest(), slices=gs)

@@ -195,3 +195,42 @@ def test_oracle_full_fieldline_traces_of_geteye(name):
         k = int(d["npts"][i])
         assert len(curve) == k
         assert np.array_equal(curve[:, 0], d["curves"][i, :k, 0]) and np.array_equal(B, d["curves"][i, :k, 1])
+
+
+def test_grid_field_bit_exact():
+    """fields.Grid (fields.py:513-814; scipy RegularGridInterpolator, linear, 4-D) on synthetic data files:
+    field operators, a Particle and a GuidingCenter trajectory that cross the rolling window's update time, and
+    the ValueError of a tracer leaving the grid -- all against the unmodified reference."""
+    d, _ = H.load("grid_synthetic")
+    G = H.synthetic_grid([str(s) for s in d["files"]])
+    assert G["sha256"] == str(d["checksum"]), "synthetic grid must regenerate bit for bit"
+    f = O.make_grid_field(G["t"], G["x"], G["y"], G["z"], G["B"], G["E"])
+    assert f.gradstep == float(d["ops_gradstep"]) and bool(f.is_static) == bool(d["ops_static"])
+    ops = O.field_ops(f, d["ops_pts"])
+    for k in ("B", "E", "magB", "unitb", "gradB", "curlb", "lengthscale"):
+        assert np.array_equal(ops[k], d["ops_" + k]), k
+    import json
+    par = json.loads(str(d["p_params"]))
+    st0 = d["p_traj"][0]
+    o = O.particle_advance(f, O.make_params(**par), st0, float(d["p_mass"]), float(d["p_charge"]), float(d["p_delta"]),
+                           max_rows=len(d["p_traj"]) + 10, want_percall=True)
+    n = int(o["nstored"][0])
+    assert n == len(d["p_traj"]) and np.array_equal(o["rows"][0, :n, :7], d["p_traj"])
+    assert np.array_equal(o["percall"], d["p_counters"]) and o["tcur"][0] == float(d["p_tcur"])
+    par = json.loads(str(d["g_params"]))
+    traj = d["g_traj"]; mass, q, v = float(d["g_mass"]), float(d["g_charge"]), float(d["g_v"])
+    ppar, mu = O.gc_construct(f, traj[0, 0], d["g_pos"], v, float(d["g_pa"]), mass)
+    assert mu[0] == float(d["g_mu"]) and ppar[0] == traj[0, 4]
+    st0 = np.concatenate(([traj[0, 0]], d["g_pos"], ppar))
+    o = O.gc_advance(f, O.make_params(**par), st0, mu, v, mass, q, par["GCtimestep"], float(d["g_delta"]),
+                     max_rows=len(traj) + 10, want_percall=True)
+    n = int(o["nstored"][0])
+    assert n == len(traj) and np.array_equal(o["rows"][0, :n, :5], traj)
+    assert np.array_equal(o["percall"], d["g_counters"]) and o["tcur"][0] == float(d["g_tcur"])
+    # leaving the grid: the reference raises ValueError and keeps the rows appended so far
+    assert bool(d["oob_raised"])
+    from rapt_b200 import m_pr
+    gm = np.sqrt(m_pr ** 2 / (1 - np.dot(d["oob_vel"], d["oob_vel"]) / 299792458.0 ** 2))
+    st0 = np.concatenate(([0.0], d["oob_pos"], gm * d["oob_vel"]))
+    o = O.particle_advance(f, O.make_params(cyclotronresolution=10), st0, m_pr, float(d["p_charge"]), 5.0, max_rows=64)
+    assert int(o["status"][0]) == -6 and int(o["nstored"][0]) == len(d["oob_traj"])
