@@ -50,6 +50,7 @@ extern "C" {
 #define RAPT_FIELD_CROSSEDEB     3   /* fields.py:392-427  prm = {Bz, Ey}                         */
 #define RAPT_FIELD_VARDIPOLE     4   /* fields.py:429-470  prm = {amp, period}                    */
 #define RAPT_FIELD_PARABOLIC     5   /* fields.py:472-511  prm = {B0, Bn, d}                      */
+#define RAPT_FIELD_GRID          6   /* fields.py:513-814  gridded E/B; user_id = handle of rapt_b200_grid_create, prm unused */
 #define RAPT_FIELD_USER        100   /* NVRTC-compiled snippet (rapt_b200_field_nvrtc)            */
 
 /* ---- guiding-centre equations of motion: GuidingCenter.py:329-395, selected by advance(eom=...) :449 */
@@ -65,6 +66,7 @@ extern "C" {
 #define RAPT_ST_NMAX         -2   /* dop: more than nsteps=500 steps in one output interval        */
 #define RAPT_ST_HSMALL       -3   /* dop: step size underflow                                      */
 #define RAPT_ST_GCITER       -5   /* utils.guidingcenter did not converge (utils.py:326)           */
+#define RAPT_ST_FIELD        -6   /* fields.Grid evaluated outside the grid: scipy's ValueError (fields.py:735-740); rows so far are kept */
 #define RAPT_ST_ROWCAP      -10   /* adaptive: row buffer full before t0+delta                     */
 
 #define RAPT_MODE_PARTICLE 0
@@ -74,7 +76,7 @@ extern "C" {
 typedef struct rapt_field {
     int32_t kind;          /* RAPT_FIELD_*                                                       */
     int32_t is_static;     /* _Field.static            fields.py:41                               */
-    int32_t user_id;       /* handle returned by rapt_b200_field_nvrtc (kind == RAPT_FIELD_USER)  */
+    int32_t user_id;       /* handle returned by rapt_b200_field_nvrtc (RAPT_FIELD_USER) or rapt_b200_grid_create (RAPT_FIELD_GRID) */
     int32_t nprm;
     double  prm[16];       /* model parameters (constructor arguments, see RAPT_FIELD_*)          */
     double  gradstep;      /* _Field.gradientstepsize  fields.py:39                               */
@@ -112,6 +114,24 @@ int         rapt_b200_fp64_peak(int iters, double *tflops, double *sm_clock_mhz)
  * It is JIT-compiled with NVRTC for sm_100a into the same kernel templates as the built-ins and cached
  * by source hash.  On success *user_id receives the handle to put in rapt_field_t.user_id. */
 int rapt_b200_field_nvrtc(const char *cuda_src, int has_E, int *user_id, char *log, int loglen);
+
+/* rapt_b200_grid_create: replaces fields.Grid.__init__ / _set_interpolator / _update_interpolator
+ * (rapt/fields.py:566-705) -- the parsed data files of a Grid (the dictionaries Grid.parsefile returns,
+ * fields.py:553-562) become device-resident interpolation tables.
+ *   t[nt]                       time of every data file, ascending (nt == 1: time-independent, 3-D interpolation)
+ *   x[nx], y[ny], z[nz]         node coordinates, ascending, uniform spacing not required
+ *   Bx,By,Bz,Ex,Ey,Ez           [nt][nx][ny][nz] C-ordered, SI units; Ex,Ey,Ez may all be NULL (E == 0)
+ * All nt time points stay resident (the reference's rolling window of three, fields.py:697-705, exists to
+ * save host memory; the interpolated value does not depend on it).  Interpolation = scipy
+ * RegularGridInterpolator(method="linear", bounds_error=True) as Grid.Bgrid/Egrid call it (fields.py:707-772);
+ * a tracer that leaves the grid ends with RAPT_ST_FIELD where the reference raises ValueError.
+ * *grid_id receives the handle for rapt_field_t.user_id (kind = RAPT_FIELD_GRID, gradstep = 1e-3 Re as
+ * fields.py:578). rapt_b200_grid_destroy frees the tables. */
+int rapt_b200_grid_create(int64_t nt, int64_t nx, int64_t ny, int64_t nz,
+                          const double *t, const double *x, const double *y, const double *z,
+                          const double *Bx, const double *By, const double *Bz,
+                          const double *Ex, const double *Ey, const double *Ez, int32_t *grid_id);
+int rapt_b200_grid_destroy(int32_t grid_id);
 
 /* Field operators at npt points (tpos = npt x 4: t,x,y,z).  Any output pointer may be NULL.
  * Replaces _Field.B/E/unitb/magB/gradB/jacobianB/curlb/curvature/dBdt/dbdt/lengthscale/timescale

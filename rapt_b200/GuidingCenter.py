@@ -138,6 +138,8 @@ class GuidingCenter:
         if n > 1:
             self.tcur = float(o["tcur"][0])
         status = int(o["status"][0])
+        if status == -6:       # RAPT_ST_FIELD: scipy's ValueError inside Grid.Bgrid/Egrid; the rows so far are kept
+            raise ValueError("One of the requested xi is out of bounds: the tracer left the grid of the field")
         if status < 0:
             import warnings
             warnings.warn({-2: "dopri5: larger nsteps is needed", -3: "dopri5: step size becomes too small"}.get(

@@ -111,6 +111,8 @@ class Particle:
         if n > 1:
             self.tcur = float(o["tcur"][0])
         status = int(o["status"][0])
+        if status == -6:       # RAPT_ST_FIELD: scipy's ValueError inside Grid.Bgrid/Egrid; the rows so far are kept
+            raise ValueError("One of the requested xi is out of bounds: the tracer left the grid of the field")
         if status < 0:
             import warnings
             warnings.warn({-2: "dop853: larger nsteps is needed", -3: "dop853: step size becomes too small"}.get(

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("RAPT_B200_LIB", os.path.join(_HERE, "librapt_b200.so"
 
 RAPT_OK = 0
 FIELD_KIND = {"EarthDipole": 0, "DoubleDipole": 1, "UniformBz": 2, "UniformCrossedEB": 3,
-              "VarEarthDipole": 4, "Parabolic": 5, "User": 100}
+              "VarEarthDipole": 4, "Parabolic": 5, "Grid": 6, "User": 100}
 EOM_KIND = {"TaoChanBrizardEOM": 0, "BrizardChanEOM": 1, "NorthropTellerEOM": 2}
 ST_OK, ST_ADIABATIC, ST_NONADIABATIC = 1, 2, 3
 

@@ -88,11 +88,31 @@ cudaError_t down(void *h, DevBuf &d, size_t bytes, cudaStream_t s)
     return cudaMemcpyAsync(h, d.p, bytes, cudaMemcpyDeviceToHost, s);
 }
 
-void fill_common(rapt::AdvArgs &a, const rapt_field_t *f, const rapt_params_t *p)
+// fields.Grid tables resident on the device (rapt_b200_grid_create)
+struct GridEntry { rapt::GridP g; bool live = false; void *mem[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; };
+std::vector<GridEntry> g_grids;
+std::mutex g_grid_mu;
+
+// rapt_field_t -> FieldP; a gridded field gets its table block placed in prm
+int resolve_field(const rapt_field_t *f, rapt::FieldP *out)
+{
+    memcpy(out, f, sizeof *out);
+    if (f->kind == RAPT_FIELD_GRID) {
+        std::lock_guard<std::mutex> lk(g_grid_mu);
+        if (f->user_id < 0 || f->user_id >= (int)g_grids.size() || !g_grids[f->user_id].live)
+            return fail(RAPT_E_ARG, "rapt_field_t.user_id %d is not a live grid handle (rapt_b200_grid_create)", f->user_id);
+        memset(out->prm, 0, sizeof out->prm);
+        memcpy(out->prm, &g_grids[f->user_id].g, sizeof(rapt::GridP));
+    }
+    return RAPT_OK;
+}
+#define RESOLVE(dst, f) do { if (int rc_ = resolve_field((f), &(dst))) return rc_; } while (0)
+
+int fill_common(rapt::AdvArgs &a, const rapt_field_t *f, const rapt_params_t *p)
 {
     memset(&a, 0, sizeof a);
-    memcpy(&a.f, f, sizeof a.f);
     memcpy(&a.p, p, sizeof a.p);
+    return resolve_field(f, &a.f);
 }
 
 
@@ -252,7 +272,7 @@ int check_field(const rapt_field_t *f)
         if (f->user_id < 0 || f->user_id >= (int)g_user.size()) return fail(RAPT_E_ARG, "unknown user field id %d", f->user_id);
         return RAPT_OK;
     }
-    if (f->kind < 0 || f->kind > 5) return fail(RAPT_E_ARG, "unknown field kind %d", f->kind);
+    if (f->kind < 0 || f->kind > RAPT_FIELD_GRID) return fail(RAPT_E_ARG, "unknown field kind %d", f->kind);
     return RAPT_OK;
 }
 
@@ -403,6 +423,78 @@ int rapt_b200_field_nvrtc(const char *cuda_src, int has_E, int *user_id, char *l
     return RAPT_OK;
 }
 
+int rapt_b200_grid_create(int64_t nt, int64_t nx, int64_t ny, int64_t nz,
+                          const double *t, const double *x, const double *y, const double *z,
+                          const double *Bx, const double *By, const double *Bz,
+                          const double *Ex, const double *Ey, const double *Ez, int32_t *grid_id)
+{
+    if (int rc = ensure_init()) return rc;
+    if (nt < 1 || nx < 2 || ny < 2 || nz < 2 || !x || !y || !z || !Bx || !By || !Bz || !grid_id || (nt > 1 && !t))
+        return fail(RAPT_E_ARG, "rapt_b200_grid_create: need nt >= 1, nx, ny, nz >= 2 and the coordinate and B arrays");
+    if ((Ex || Ey || Ez) && !(Ex && Ey && Ez)) return fail(RAPT_E_ARG, "rapt_b200_grid_create: give all of Ex, Ey, Ez or none");
+    const double *axes[4] = {t, x, y, z};
+    const int64_t len[4] = {nt, nx, ny, nz};
+    for (int a = (nt > 1 ? 0 : 1); a < 4; a++)
+        for (int64_t i = 1; i < len[a]; i++)
+            if (!(axes[a][i] > axes[a][i - 1])) return fail(RAPT_E_ARG, "rapt_b200_grid_create: axis %d is not strictly ascending", a);
+    GridEntry e;
+    rapt::GridP &g = e.g;
+    memset(&g, 0, sizeof g);
+    g.nt = (int)nt; g.nx = (int)nx; g.ny = (int)ny; g.nz = (int)nz;
+    // coordinates
+    const double **dst[4] = {&g.t, &g.x, &g.y, &g.z};
+    for (int a = 0; a < 4; a++) {
+        if (a == 0 && nt == 1 && !t) continue;
+        CK(cudaMalloc(&e.mem[a], len[a] * sizeof(double)));
+        CK(cudaMemcpy(e.mem[a], axes[a], len[a] * sizeof(double), cudaMemcpyHostToDevice));
+        *dst[a] = static_cast<const double *>(e.mem[a]);
+    }
+    // uniform axes get a direct index (made exact against the node array on the device)
+    double *u0[3] = {&g.x0, &g.y0, &g.z0}, *ui[3] = {&g.xinv, &g.yinv, &g.zinv};
+    for (int a = 1; a < 4; a++) {
+        const double *v = axes[a]; const int64_t n = len[a];
+        const double d = (v[n - 1] - v[0]) / (double)(n - 1);
+        bool uniform = true;
+        for (int64_t i = 0; i < n && uniform; i++) uniform = fabs(v[i] - (v[0] + d * (double)i)) <= 1e-9 * fabs(d);
+        *u0[a - 1] = v[0]; *ui[a - 1] = uniform ? 1.0 / d : 0.0;
+    }
+    // node tables: [nt][nx][ny][nz] x (c0, c1, c2, pad), staged one time point at a time
+    const size_t nodes = (size_t)nx * ny * nz;
+    bool hasE = false;
+    if (Ex) for (size_t i = 0; i < nodes * (size_t)nt && !hasE; i++) hasE = (Ex[i] != 0.0) || (Ey[i] != 0.0) || (Ez[i] != 0.0);
+    std::vector<double> stage(nodes * 4);
+    const double *comp[2][3] = {{Bx, By, Bz}, {Ex, Ey, Ez}};
+    for (int w = 0; w < 2; w++) {
+        if (w == 1 && !hasE) break;
+        CK(cudaMalloc(&e.mem[4 + w], nodes * (size_t)nt * 4 * sizeof(double)));
+        for (int64_t it = 0; it < nt; it++) {
+            const size_t off = (size_t)it * nodes;
+            for (size_t i = 0; i < nodes; i++) {
+                stage[4 * i] = comp[w][0][off + i]; stage[4 * i + 1] = comp[w][1][off + i];
+                stage[4 * i + 2] = comp[w][2][off + i]; stage[4 * i + 3] = 0.0;
+            }
+            CK(cudaMemcpy(static_cast<double *>(e.mem[4 + w]) + off * 4, stage.data(), nodes * 4 * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
+    g.B = static_cast<const double *>(e.mem[4]);
+    g.E = static_cast<const double *>(e.mem[5]);
+    e.live = true;
+    std::lock_guard<std::mutex> lk(g_grid_mu);
+    g_grids.push_back(e);
+    *grid_id = (int32_t)g_grids.size() - 1;
+    return RAPT_OK;
+}
+
+int rapt_b200_grid_destroy(int32_t grid_id)
+{
+    std::lock_guard<std::mutex> lk(g_grid_mu);
+    if (grid_id < 0 || grid_id >= (int)g_grids.size() || !g_grids[grid_id].live)
+        return fail(RAPT_E_ARG, "rapt_b200_grid_destroy: %d is not a live grid handle", grid_id);
+    for (void *&m : g_grids[grid_id].mem) { if (m) cudaFree(m); m = nullptr; }
+    g_grids[grid_id].live = false;
+    return RAPT_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Particle.advance
 // ------------------------------------------------------------------------------------------------
@@ -423,7 +515,7 @@ int rapt_b200_particle_advance_dev(const rapt_field_t *f, const rapt_params_t *p
     if (n == 0) return RAPT_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rapt::AdvArgs a;
-    fill_common(a, f, p);
+    if (int rc = fill_common(a, f, p)) return rc;
     a.nwork = n; a.order = nullptr; a.queue = next_queue(s);
     a.t = t; a.s1 = x; a.s2 = y; a.s3 = z; a.s4 = px; a.s5 = py; a.s6 = pz;
     a.mass = mass; a.charge = charge; a.delta = delta;
@@ -498,7 +590,7 @@ int rapt_b200_gc_advance_dev(const rapt_field_t *f, const rapt_params_t *p, int 
     if (n == 0) return RAPT_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rapt::AdvArgs a;
-    fill_common(a, f, p);
+    if (int rc = fill_common(a, f, p)) return rc;
     a.nwork = n; a.order = nullptr; a.queue = next_queue(s);
     a.t = t; a.s1 = x; a.s2 = y; a.s3 = z; a.s4 = ppar;
     a.mass = mass; a.charge = charge; a.mu = mu; a.v = v; a.dtin = dt; a.delta = delta; a.eom = eom;
@@ -569,7 +661,7 @@ int rapt_b200_field_ops(const rapt_field_t *f, int arith, int64_t npt, const dou
     for (int k = 0; k < 12; k++) if (host[k]) CK(o[k].alloc(npt * width[k] * sizeof(double)));
     rapt::OpsArgs a;
     memset(&a, 0, sizeof a);
-    memcpy(&a.f, f, sizeof a.f);
+    RESOLVE(a.f, f);
     a.n = npt; a.tpos = dpos.as<double>();
     a.B = o[0].as<double>(); a.E = o[1].as<double>(); a.unitb = o[2].as<double>(); a.magB = o[3].as<double>();
     a.gradB = o[4].as<double>(); a.jac = o[5].as<double>(); a.curlb = o[6].as<double>(); a.curv = o[7].as<double>();
@@ -597,7 +689,7 @@ int rapt_b200_gc_construct(const rapt_field_t *f, int arith, int64_t n, const do
     CK(o0.alloc(nb)); CK(o1.alloc(nb));
     rapt::MiscArgs a;
     memset(&a, 0, sizeof a);
-    memcpy(&a.f, f, sizeof a.f);
+    RESOLVE(a.f, f);
     a.n = n; a.op = 0;
     a.a0 = in[0].as<double>(); a.a1 = in[1].as<double>(); a.a2 = in[2].as<double>(); a.a3 = in[3].as<double>();
     a.a4 = in[4].as<double>(); a.a5 = in[5].as<double>(); a.a6 = in[6].as<double>();
@@ -623,7 +715,7 @@ int rapt_b200_switch_p2g(const rapt_field_t *f, int arith, int64_t n, const doub
     CK(og.alloc(5 * nb)); CK(omu.alloc(nb)); CK(ov.alloc(nb)); CK(ost.alloc(n * sizeof(int)));
     rapt::MiscArgs a;
     memset(&a, 0, sizeof a);
-    memcpy(&a.f, f, sizeof a.f);
+    RESOLVE(a.f, f);
     a.n = n; a.op = 1;
     a.a0 = dp.as<double>(); a.a1 = dm.as<double>(); a.a2 = dq.as<double>();
     a.o0 = og.as<double>(); a.o1 = omu.as<double>(); a.o2 = ov.as<double>(); a.io = ost.as<int>();
@@ -648,7 +740,7 @@ int rapt_b200_switch_g2p(const rapt_field_t *f, int arith, int64_t n, const doub
     CK(op.alloc(7 * nb));
     rapt::MiscArgs a;
     memset(&a, 0, sizeof a);
-    memcpy(&a.f, f, sizeof a.f);
+    RESOLVE(a.f, f);
     a.n = n; a.op = 2; a.t_eval = t_eval;
     a.a0 = dg.as<double>(); a.a1 = dmu.as<double>(); a.a2 = dm.as<double>(); a.a3 = dq.as<double>();
     a.o0 = op.as<double>();
@@ -674,7 +766,7 @@ int rapt_b200_isadiabatic(const rapt_field_t *f, const rapt_params_t *p, int mod
     CK(up(dm, mass, nb, s)); CK(up(dq, charge, nb, s)); CK(oo.alloc(n * sizeof(int)));
     rapt::MiscArgs a;
     memset(&a, 0, sizeof a);
-    memcpy(&a.f, f, sizeof a.f); memcpy(&a.p, p, sizeof a.p);
+    RESOLVE(a.f, f); memcpy(&a.p, p, sizeof a.p);
     a.n = n; a.op = 3; a.mode = mode; a.stride = row_stride;
     a.a0 = dr.as<double>(); a.a1 = dmu.as<double>(); a.a2 = dm.as<double>(); a.a3 = dq.as<double>(); a.io = oo.as<int>();
     if (int rc = launch_any(f, p->arith == 1, UK_MISC, &a, n, 0, s)) return rc;
@@ -739,7 +831,7 @@ static int bounce_impl(const rapt_field_t *f, int arith, double fieldlineresolut
     CK(ocv.alloc((size_t)n * max_pts * 5 * sizeof(double))); CK(scr.alloc((size_t)n * max_pts * 4 * sizeof(double)));
     rapt::BounceArgs a;
     memset(&a, 0, sizeof a);
-    memcpy(&a.f, f, sizeof a.f);
+    RESOLVE(a.f, f);
     a.flres = fieldlineresolution; a.n = n; a.max_pts = max_pts;
     a.t = in[0].as<double>(); a.x = in[1].as<double>(); a.y = in[2].as<double>(); a.z = in[3].as<double>();
     a.ppar = in[4].as<double>(); a.mu = in[5].as<double>(); a.mass = in[6].as<double>();
@@ -804,7 +896,7 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
     }
     rapt::AdaptArgs sw;
     memset(&sw, 0, sizeof sw);
-    memcpy(&sw.f, f, sizeof sw.f); memcpy(&sw.p, p, sizeof sw.p);
+    RESOLVE(sw.f, f); memcpy(&sw.p, p, sizeof sw.p);
     sw.n = n; sw.delta = delta;
     sw.x0 = in[0].as<double>(); sw.y0 = in[1].as<double>(); sw.z0 = in[2].as<double>();
     sw.vx0 = in[3].as<double>(); sw.vy0 = in[4].as<double>(); sw.vz0 = in[5].as<double>(); sw.t0 = in[6].as<double>();
@@ -851,7 +943,7 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
         CK(cudaStreamSynchronize(s0));
         if (cnt[0] > 0) {
             rapt::AdvArgs a;
-            fill_common(a, f, &pc);
+            if (int rc = fill_common(a, f, &pc)) return rc;
             a.nwork = cnt[0]; a.order = sw.listP; a.queue = next_queue(s1);
             a.t = sw.pt; a.s1 = sw.px; a.s2 = sw.py; a.s3 = sw.pz; a.s4 = sw.ppx; a.s5 = sw.ppy; a.s6 = sw.ppz;
             a.mass = sw.mass; a.charge = sw.charge; a.delta = 0; a.delta_arr = sw.rem;
@@ -864,7 +956,7 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
         }
         if (cnt[1] > 0) {
             rapt::AdvArgs a;
-            fill_common(a, f, &pc);
+            if (int rc = fill_common(a, f, &pc)) return rc;
             a.nwork = cnt[1]; a.order = sw.listG; a.queue = next_queue(s2);
             a.t = sw.gt; a.s1 = sw.gx; a.s2 = sw.gy; a.s3 = sw.gz; a.s4 = sw.gpp;
             a.mass = sw.mass; a.charge = sw.charge; a.mu = sw.mu; a.v = sw.v; a.dtin = ddtg.as<double>();

@@ -32,6 +32,7 @@ cudaError_t launch_particle(const rapt::AdvArgs &a, int grid, cudaStream_t s)
     case 3: return go_particle<3>(a, grid, s);
     case 4: return go_particle<4>(a, grid, s);
     case 5: return go_particle<5>(a, grid, s);
+    case 6: return go_particle<6>(a, grid, s);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -73,6 +74,7 @@ cudaError_t launch_gc(const rapt::AdvArgs &a, int grid, cudaStream_t s)
     case 3: return go_gc<3>(a, grid, s);
     case 4: return go_gc<4>(a, grid, s);
     case 5: return go_gc<5>(a, grid, s);
+    case 6: return go_gc<6>(a, grid, s);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -111,6 +113,7 @@ __global__ void k_particle_dt(const rapt::AdvArgs a, double *key, int *idx)
     case 0: CALL(0); break; case 1: CALL(1); break;    \
     case 2: CALL(2); break; case 3: CALL(3); break;    \
     case 4: CALL(4); break; case 5: CALL(5); break;    \
+    case 6: CALL(6); break;                            \
     default: return cudaErrorInvalidValue;             \
     }
 cudaError_t launch_particle_dt(const rapt::AdvArgs &a, double *key, int *idx, cudaStream_t s)

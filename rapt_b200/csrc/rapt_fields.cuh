@@ -19,6 +19,7 @@
 #define RAPT_EARTH_B0 3.07e-5              /* rapt/__init__.py:9  */
 #define RAPT_EARTH_RE 6378137.0            /* rapt/__init__.py:10 */
 #define RAPT_PI 3.141592653589793
+#define RAPT_NAN __longlong_as_double(0x7ff8000000000000LL)
 
 #define RAPT_DEV __device__ __forceinline__
 
@@ -27,6 +28,7 @@
 namespace RAPT_NS {
 
 using rapt::FieldP;
+using rapt::GridP;
 
 // np.dot on 3-vectors as executed by the reference's numpy: fma(a2,b2, fma(a1,b1, a0*b0))
 RAPT_DEV double dot3(double ax, double ay, double az, double bx, double by, double bz)
@@ -107,6 +109,81 @@ __device__ void rapt_user_E(double t, double x, double y, double z, const double
 #endif
 
 // ------------------------------------------------------------------------------------------
+// fields.Grid (fields.py:513-814): multilinear interpolation of gridded E/B in (t, x, y, z), or (x, y, z)
+// for a single time point -- scipy's RegularGridInterpolator(method="linear") as Grid.Bgrid/Egrid call it:
+// interval search per axis (x[i] <= v < x[i+1], closed on the right at the last node), normalised distance
+// (v - x[i]) / (x[i+1] - x[i]), then the 2^d cell vertices in itertools.product order (first axis slowest)
+// with weight ((w0 w1) w2) w3 and value += node * weight.  The strict flavour executes exactly those
+// operations (bit-identical to scipy on the same tables).  Outside the grid the reference raises
+// ValueError; here the field is NaN and the advance kernels stop the tracer with RAPT_ST_FIELD.
+// The reference keeps a rolling window of three time points on the host (fields.py:697-705); linear
+// interpolation between the two bracketing time points does not depend on the window, so all time points
+// stay resident in HBM and the window is the bracketing pair.
+// ------------------------------------------------------------------------------------------
+RAPT_DEV const GridP &grid_of(const FieldP &f) { return *reinterpret_cast<const GridP *>(f.prm); }
+
+RAPT_DEV bool grid_locate(const double *__restrict__ g, int n, double g0, double ginv, double v, int &idx, double &w)
+{
+    if (!(__ldg(g) <= v && v <= __ldg(g + n - 1))) return false;
+    int k;
+    if (ginv != 0.0) {                               // uniform axis: direct index, then make it exact
+        k = (int)((v - g0) * ginv);
+        k = max(0, min(k, n - 2));
+        while (k > 0 && v < __ldg(g + k)) k--;
+        while (k < n - 2 && v >= __ldg(g + k + 1)) k++;
+    } else {                                         // binary search
+        int low = 0, high = n - 2;
+        if (v == __ldg(g + n - 1)) low = high;
+        while (low < high) {
+            const int mid = (high + low) >> 1;
+            if (v < __ldg(g + mid)) high = mid;
+            else if (v >= __ldg(g + mid + 1)) low = mid + 1;
+            else { low = mid; break; }
+        }
+        k = low;
+    }
+    const double a = __ldg(g + k), b = __ldg(g + k + 1);
+    w = (v - a) / (b - a);
+    idx = k;
+    return true;
+}
+
+RAPT_DEV void grid_eval(const GridP &g, const double *__restrict__ tab, double t, double x, double y, double z,
+                        double &o0, double &o1, double &o2)
+{
+    int it = 0, ix, iy, iz;
+    double wt = 0, wx, wy, wz;
+    bool ok = grid_locate(g.x, g.nx, g.x0, g.xinv, x, ix, wx);
+    ok = grid_locate(g.y, g.ny, g.y0, g.yinv, y, iy, wy) && ok;
+    ok = grid_locate(g.z, g.nz, g.z0, g.zinv, z, iz, wz) && ok;
+    const int ntp = (g.nt >= 2) ? 2 : 1;
+    if (ntp == 2) ok = grid_locate(g.t, g.nt, 0.0, 0.0, t, it, wt) && ok;
+    if (!ok) { o0 = o1 = o2 = RAPT_NAN; return; }
+    const size_t sy = (size_t)g.nz, sx = sy * g.ny, st = sx * g.nx;
+    const double2 *__restrict__ node = reinterpret_cast<const double2 *>(tab) + 2 * ((it * st + ix * sx) + iy * sy + iz);
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+        if (a >= ntp) break;
+        const double ft = (ntp == 2) ? (a ? wt : 1 - wt) : 1.0;
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            const double fx = (ntp == 2) ? ft * (b ? wx : 1 - wx) : (b ? wx : 1 - wx);
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const double fy = fx * (c ? wy : 1 - wy);
+                const double2 *q = node + 2 * (a * st + b * sx + c * sy);      // two z-neighbours: 64 contiguous bytes
+                const double2 lxy = __ldg(q), lz = __ldg(q + 1), hxy = __ldg(q + 2), hz = __ldg(q + 3);
+                const double w0 = fy * (1 - wz), w1 = fy * wz;
+                v0 = v0 + lxy.x * w0; v1 = v1 + lxy.y * w0; v2 = v2 + lz.x * w0;
+                v0 = v0 + hxy.x * w1; v1 = v1 + hxy.y * w1; v2 = v2 + hz.x * w1;
+            }
+        }
+    }
+    o0 = v0; o1 = v1; o2 = v2;
+}
+
+// ------------------------------------------------------------------------------------------
 // Field models.  KIND is a compile-time constant so every kernel contains exactly one model.
 // ------------------------------------------------------------------------------------------
 template <int KIND> struct Field {
@@ -114,9 +191,10 @@ template <int KIND> struct Field {
 #ifdef RAPT_USER_FIELD
         (KIND == 100) ? (RAPT_USER_HAS_E != 0) :
 #endif
-        (KIND == 3);
-    static constexpr bool TIME_DEP = (KIND == 4) || (KIND == 100);
+        (KIND == 3) || (KIND == 6);
+    static constexpr bool TIME_DEP = (KIND == 4) || (KIND == 6) || (KIND == 100);
     static constexpr bool UNIFORM = (KIND == 2) || (KIND == 3);
+    static constexpr bool CAN_FAIL = (KIND == 6);      // gridded data: NaN outside the grid
     // B(t, x) = tfactor(t) * Bspace(x): lets the guiding-centre stencil evaluate the time factor once per
     // right-hand side instead of once per stencil point (fast flavour; VarEarthDipole, fields.py:469-470)
     static constexpr bool SEPARABLE = (KIND == 4) && !RAPT_STRICT;
@@ -181,6 +259,9 @@ template <int KIND> struct Field {
             if (fabs(z) <= 1.0) bx = f.prm[0] * z / f.prm[2];
             else bx = sgn(z) * RAPT_EARTH_B0;
             by = 0; bz = f.prm[1];
+        } else if (KIND == 6) {             // Grid.B -> Grid.Bgrid, fields.py:707-741, 774-794
+            const GridP &g = grid_of(f);
+            grid_eval(g, g.B, t, x, y, z, bx, by, bz);
         }
 #ifdef RAPT_USER_FIELD
         else if (KIND == 100) {
@@ -216,6 +297,10 @@ template <int KIND> struct Field {
     {
         ex = 0; ey = 0; ez = 0;             // fields.py:59-74
         if (KIND == 3) ey = f.prm[1];       // fields.py:427
+        if (KIND == 6) {                    // Grid.E -> Grid.Egrid, fields.py:743-772, 796-814
+            const GridP &g = grid_of(f);
+            if (g.E) grid_eval(g, g.E, t, x, y, z, ex, ey, ez);
+        }
 #if defined(RAPT_USER_FIELD) && RAPT_USER_HAS_E
         if (KIND == 100) {
             double o[3];

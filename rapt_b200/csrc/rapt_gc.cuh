@@ -498,6 +498,7 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
                 reject = true;
                 if (naccpt_row >= 1) nrejct++;
                 last = false;
+                if (F::CAN_FAIL && !(err == err)) { st = RAPT_ST_FIELD; need_row = true; }   // left the grid: keep the last row
             }
         }
     }

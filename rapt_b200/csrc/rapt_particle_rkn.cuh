@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
             reject = true;
             if (naccpt_row >= 1) nrejct++;
             last = false;
+            if (F::CAN_FAIL && !(err == err)) { st = RAPT_ST_FIELD; need_row = true; }   // left the grid: keep the last row
         }
         }   // st == ST_OK
         }   // have && !need_row

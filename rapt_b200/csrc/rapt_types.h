@@ -11,6 +11,19 @@ struct FieldP {
     double gradstep, tstep;
 };
 
+// fields.Grid (rapt/fields.py:513-814) on the device.  The host side of the C ABI resolves
+// rapt_field_t.user_id (the handle of rapt_b200_grid_create) into this block and places it in FieldP::prm,
+// so every kernel receives the table pointers as kernel parameters.
+// Tables: B and E as [nt][nx][ny][nz] nodes of 4 doubles (x, y, z component + pad): the two z-neighbours
+// of a cell edge are one aligned 64-byte segment.  E == nullptr: the electric field is identically zero.
+struct GridP {
+    const double *t, *x, *y, *z;       // node coordinates (t: nt >= 2 time points, unused when nt == 1)
+    const double *B, *E;
+    int nt, nx, ny, nz;
+    double x0, xinv, y0, yinv, z0, zinv;   // uniform axis: first node and 1/spacing (inv == 0: not uniform)
+};
+static_assert(sizeof(GridP) <= 16 * sizeof(double), "GridP must fit FieldP::prm");
+
 struct ParamsP {
     double rtol, atol, cyclotronresolution, epss, epst;
     int enforce_equatorial, check_adiabaticity, dop853_reject_rule, arith, sort_by_work;
@@ -114,5 +127,6 @@ struct AdaptArgs {
 #define RAPT_ST_NMAX (-2)
 #define RAPT_ST_HSMALL (-3)
 #define RAPT_ST_GCITER (-5)
+#define RAPT_ST_FIELD (-6)         /* Grid field evaluated outside its bounds (the reference raises ValueError) */
 #define RAPT_ST_ROWCAP (-10)
 #endif

@@ -35,6 +35,23 @@ def _field_desc(field):
     return field if isinstance(field, FieldT) else field.device_descriptor()
 
 
+def create_grid(t, x, y, z, B, E):
+    """Upload the parsed data of a fields.Grid (rapt_b200_grid_create); returns the grid handle.
+    t (nt,), x, y, z node coordinates, B and E: three arrays each of shape (nt, nx, ny, nz)."""
+    t = np.ascontiguousarray(np.atleast_1d(t), dtype=np.float64)
+    x, y, z = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z))
+    shape = (len(t), len(x), len(y), len(z))
+    comps = [np.ascontiguousarray(a, dtype=np.float64).reshape(shape) for a in list(B) + list(E)]
+    gid = C.c_int32(-1)
+    check(_lib.load().rapt_b200_grid_create(C.c_int64(shape[0]), C.c_int64(shape[1]), C.c_int64(shape[2]), C.c_int64(shape[3]),
+                                            ptr(t), ptr(x), ptr(y), ptr(z), *[ptr(a) for a in comps], C.byref(gid)))
+    return gid.value
+
+
+def destroy_grid(grid_id):
+    check(_lib.load().rapt_b200_grid_destroy(C.c_int32(grid_id)))
+
+
 def compile_user_field(source, has_E):
     """NVRTC-compile a user field snippet (cached by source); returns the user_id handle."""
     key = (source, bool(has_E))

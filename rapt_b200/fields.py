@@ -250,8 +250,127 @@ class Parabolic(_Field):
 
 
 class Grid(_Field):
-    """Gridded-data fields (rapt/fields.py:513-814) are outside the device hot path."""
+    """Fields sampled on a Cartesian (rectilinear) grid (rapt/fields.py:513-814).
 
-    def __init__(self, *a, **k):
-        raise NotImplementedError("fields.Grid is not part of the B200 hot path (analytic fields and NVRTC "
-                                  "snippets only); see DESIGN.md 'out of scope'")
+    Not for direct use: subclass and override `parsefile(filename)`, which must return a dictionary with
+    "time" (float), "x", "y", "z" (1-D node coordinates, uniform spacing not required) and the 3-D arrays
+    "Bx", "By", "Bz", "Ex", "Ey", "Ez" (SI units) -- the reference's contract (fields.py:553-562).
+
+    `Grid(filelist)` takes the data files in time order.  Two or more files: linear interpolation in
+    (t, x, y, z); one file: time-independent, interpolation in (x, y, z).  Differences from the reference,
+    both consequences of running on a B200:
+
+    * every file is parsed at construction and all time points are uploaded to HBM
+      (`rapt_b200_grid_create`).  The reference keeps a rolling window of three files on the host to save
+      memory (fields.py:697-705) and therefore "forgets" earlier times; the interpolated values are the same
+      (linear interpolation between the two bracketing time points) but a second tracer started at an
+      earlier time works here.
+    * the single-file case works (the reference sets `self.time_indep` but tests `self._time_indep`,
+      fields.py:593 vs :733, and then calls a 3-D interpolator with four coordinates).
+
+    Outside the grid `B`/`E` raise ValueError like scipy's RegularGridInterpolator does in the reference;
+    a tracer that leaves the grid during `advance` keeps the rows computed so far and raises ValueError.
+    `static` stays True as in the reference (fields.py:41 is never overridden by Grid): set it to False on the
+    instance when dB/dt or E matter for gamma.  Overriding `B`/`E` in a subclass (e.g. to add a dipole) has
+    no device counterpart; such a subclass cannot be advanced.
+    """
+    _device_kind = "Grid"
+
+    def __init__(self, filelist):
+        assert len(filelist) > 0
+        _Field.__init__(self)
+        self.gradientstepsize = 1e-3 * Re                     # fields.py:578
+        self.files = []                                        # nothing left to load (reference: remaining file names)
+        grids = [self.parsefile(fn) for fn in filelist]
+        g0 = grids[0]
+        self._t = np.array([float(g["time"]) for g in grids])
+        self._x, self._y, self._z = (np.ascontiguousarray(g0[k], dtype=np.float64) for k in ("x", "y", "z"))
+        shape = (len(self._x), len(self._y), len(self._z))
+        for g in grids:
+            for k in ("Bx", "By", "Bz", "Ex", "Ey", "Ez"):
+                if np.shape(g[k]) != shape:
+                    raise ValueError(f"{k} has shape {np.shape(g[k])}, expected {shape}: the grid must be the same in all files")
+        self._B = [np.ascontiguousarray(np.stack([g[k] for g in grids]), dtype=np.float64) for k in ("Bx", "By", "Bz")]
+        self._E = [np.ascontiguousarray(np.stack([g[k] for g in grids]), dtype=np.float64) for k in ("Ex", "Ey", "Ez")]
+        self._time_indep = len(grids) == 1
+        self.t0 = self._t[0]
+        if len(grids) > 1:
+            self.t1 = self._t[1]
+        if len(grids) > 2:
+            self.t2 = self._t[2]
+        self._grid_id = None
+
+    def parsefile(self, filename):
+        """Parse one data file (one time point); override in the subclass (fields.py:596-622)."""
+        return dict()
+
+    # ---- device side
+    def device_descriptor(self):
+        if type(self).B is not Grid.B or type(self).E is not Grid.E:
+            raise NotImplementedError(f"{type(self).__name__} overrides B/E of fields.Grid; only the interpolated grid "
+                                      "field has a device implementation (rapt_b200 has no CPU fallback)")
+        if self._grid_id is None:
+            from . import engine
+            self._grid_id = engine.create_grid(self._t, self._x, self._y, self._z, self._B, self._E)
+        f = FieldT()
+        f.kind = FIELD_KIND["Grid"]
+        f.user_id = self._grid_id
+        f.nprm = 0
+        f.is_static = int(bool(self.static))
+        f.gradstep = float(self.gradientstepsize)
+        f.tstep = float(self.timederivstepsize)
+        return f
+
+    def __del__(self):
+        gid = getattr(self, "_grid_id", None)
+        if gid is not None:
+            try:
+                from . import engine
+                engine.destroy_grid(gid)
+            except Exception:
+                pass
+
+    # ---- host side: scipy's linear RegularGridInterpolator restated for one point (the reference builds six
+    # of them, fields.py:643-694); used by the host-side API only, never by advance()
+    @staticmethod
+    def _interval(g, v, axis):
+        if not (g[0] <= v <= g[-1]):
+            raise ValueError(f"One of the requested xi is out of bounds in dimension {axis}")
+        i = int(np.searchsorted(g, v, side="right")) - 1
+        return min(max(i, 0), len(g) - 2)
+
+    def _interp(self, comps, tpos):
+        axes = ([] if self._time_indep else [self._t]) + [self._x, self._y, self._z]
+        vals = list(tpos[1:]) if self._time_indep else list(tpos)
+        idx, w = [], []
+        for d, (g, v) in enumerate(zip(axes, vals)):
+            i = self._interval(g, float(v), d)
+            idx.append(i); w.append((float(v) - g[i]) / (g[i + 1] - g[i]))
+        nd = len(axes)
+        out = np.zeros(3)
+        for c in range(3):
+            arr = comps[c][0] if self._time_indep else comps[c]
+            value = 0.0
+            for corner in range(1 << nd):
+                weight = 1.0; ii = []
+                for d in range(nd):
+                    up = (corner >> (nd - 1 - d)) & 1
+                    weight = weight * (w[d] if up else 1 - w[d])
+                    ii.append(idx[d] + up)
+                value = value + arr[tuple(ii)] * weight
+            out[c] = value
+        return out
+
+    def Bgrid(self, tpos):
+        """Interpolated magnetic field vector (fields.py:707-741)."""
+        return self._interp(self._B, np.asarray(tpos, dtype=float))
+
+    def Egrid(self, tpos):
+        """Interpolated electric field vector (fields.py:743-772)."""
+        return self._interp(self._E, np.asarray(tpos, dtype=float))
+
+    def B(self, tpos):
+        return self.Bgrid(tpos)
+
+    def E(self, tpos):
+        return self.Egrid(tpos)

@@ -166,6 +166,30 @@ def test_second_invariant_host_leg_matches_reference():
     assert engine.eye_from_curve(s, b, 0.9) == 0.0 and engine.eye_from_curve(s, b, 1.0) == 0.0
 
 
+def test_grid_host_interpolation_matches_reference():
+    """fields.Grid host side (Bgrid/Egrid and the derived operators of _Field) on the synthetic data files
+    equals the reference's values bit for bit; outside the grid it raises ValueError like scipy."""
+    from rapt_b200 import fields, synth, Re
+    d, _ = H.load("grid_synthetic")
+    files = [str(s) for s in d["files"]]
+
+    class SynthGrid(fields.Grid):
+        def parsefile(self, filename):
+            return synth.dipole_grid_slice(int(filename))
+    f = SynthGrid(files)
+    assert f.gradientstepsize == float(d["ops_gradstep"]) and f.static == bool(d["ops_static"])
+    for i, tp in enumerate(d["ops_pts"]):
+        assert np.array_equal(f.B(tp), d["ops_B"][i]) and np.array_equal(f.E(tp), d["ops_E"][i])
+        assert f.magB(tp) == d["ops_magB"][i] and np.array_equal(f.gradB(tp), d["ops_gradB"][i])
+        assert np.array_equal(f.curlb(tp), d["ops_curlb"][i])
+    with pytest.raises(ValueError):
+        f.B([0.5, 9 * Re, 0, 0])
+    with pytest.raises(ValueError):
+        f.E([3.5, 5 * Re, 0, 0])          # time beyond the last data file
+    one = SynthGrid(files[:1])            # single file: time-independent, any t
+    assert np.array_equal(one.B([123.0, 5 * Re, 0.1 * Re, 0.2 * Re]), f.B([0.0, 5 * Re, 0.1 * Re, 0.2 * Re]))
+
+
 def test_nystrom_tables_are_consistent_with_the_tableau():
     """rapt_particle_rkn.cuh integrates in Nystrom form with A.A, b.A, er.A, w.A (tools/gen_coeffs.py):
     check the generated constants against the DOP853 tableau and the order conditions they must inherit."""
