@@ -89,7 +89,7 @@ cudaError_t down(void *h, DevBuf &d, size_t bytes, cudaStream_t s)
 }
 
 // fields.Grid tables resident on the device (rapt_b200_grid_create)
-struct GridEntry { rapt::GridP g; bool live = false; void *mem[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; };
+struct GridEntry { rapt::GridP g; bool live = false; void *mem[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; };   // mem[6]: device copy of g
 std::vector<GridEntry> g_grids;
 std::mutex g_grid_mu;
 
@@ -102,7 +102,10 @@ int resolve_field(const rapt_field_t *f, rapt::FieldP *out)
         if (f->user_id < 0 || f->user_id >= (int)g_grids.size() || !g_grids[f->user_id].live)
             return fail(RAPT_E_ARG, "rapt_field_t.user_id %d is not a live grid handle (rapt_b200_grid_create)", f->user_id);
         memset(out->prm, 0, sizeof out->prm);
-        memcpy(out->prm, &g_grids[f->user_id].g, sizeof(rapt::GridP));
+        const void *dev = g_grids[f->user_id].mem[6];
+        memcpy(&out->prm[0], &dev, sizeof dev);                       // prm[0]: device address of the GridP block
+        out->prm[1] = g_grids[f->user_id].g.E ? 1.0 : 0.0;            // prm[1]: has an electric-field table
+        out->prm[2] = (double)g_grids[f->user_id].g.nt;               // prm[2]: number of time points (launchers size the cell cache)
     }
     return RAPT_OK;
 }
@@ -478,6 +481,8 @@ int rapt_b200_grid_create(int64_t nt, int64_t nx, int64_t ny, int64_t nz,
     }
     g.B = static_cast<const double *>(e.mem[4]);
     g.E = static_cast<const double *>(e.mem[5]);
+    CK(cudaMalloc(&e.mem[6], sizeof g));
+    CK(cudaMemcpy(e.mem[6], &g, sizeof g, cudaMemcpyHostToDevice));
     e.live = true;
     std::lock_guard<std::mutex> lk(g_grid_mu);
     g_grids.push_back(e);

@@ -4,6 +4,15 @@
 #include <cstdlib>
 #include "rapt_launch.h"
 
+// gridded field: dynamic shared memory for the per-thread cell cache (prm[2] = number of time points)
+template <class K> static size_t grid_cache_bytes(const rapt::AdvArgs &a, K kernel, int threads)
+{
+    if (a.f.kind != 6) return 0;
+    const size_t bytes = (size_t)threads * 8 * (1 + 24 * (a.f.prm[2] >= 2.0 ? 2 : 1));
+    if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return bytes;
+}
+
 #ifdef RAPT_TU_PARTICLE
 #include "rapt_particle.cuh"
 #if !RAPT_STRICT
@@ -17,10 +26,11 @@ static bool use_rkn(const rapt::AdvArgs &a) { return a.f.is_static && !a.p.enfor
 template <int KIND> static cudaError_t go_particle(const rapt::AdvArgs &a, int grid, cudaStream_t s)
 {
 #if !RAPT_STRICT
-    if (use_rkn(a)) k_particle_rkn<Field<KIND>><<<(grid * 128 + RAPT_RKN_THREADS - 1) / RAPT_RKN_THREADS, RAPT_RKN_THREADS, 0, s>>>(a);
+    if (use_rkn(a)) k_particle_rkn<Field<KIND>><<<(grid * 128 + RAPT_RKN_THREADS - 1) / RAPT_RKN_THREADS, RAPT_RKN_THREADS,
+                                                  grid_cache_bytes(a, k_particle_rkn<Field<KIND>>, RAPT_RKN_THREADS), s>>>(a);
     else
 #endif
-    k_particle_dop853<Field<KIND>><<<grid, 128, 0, s>>>(a);
+    k_particle_dop853<Field<KIND>><<<grid, 128, grid_cache_bytes(a, k_particle_dop853<Field<KIND>>, 128), s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_particle(const rapt::AdvArgs &a, int grid, cudaStream_t s)
@@ -60,9 +70,9 @@ namespace RAPT_NS {
 static int gc_minb() { const char *e = getenv("RAPT_B200_GC_BLOCKS"); return e ? atoi(e) : RAPT_GC_DEFAULT_BLOCKS; }
 template <int KIND> static cudaError_t go_gc(const rapt::AdvArgs &a, int grid, cudaStream_t s)
 {
-    if (gc_minb() >= 4) k_gc_dopri5<Field<KIND>, 4><<<grid, 128, 0, s>>>(a);
-    else if (gc_minb() == 3) k_gc_dopri5<Field<KIND>, 3><<<grid, 128, 0, s>>>(a);
-    else k_gc_dopri5<Field<KIND>, 2><<<grid, 128, 0, s>>>(a);
+    if (gc_minb() >= 4) k_gc_dopri5<Field<KIND>, 4><<<grid, 128, grid_cache_bytes(a, k_gc_dopri5<Field<KIND>, 4>, 128), s>>>(a);
+    else if (gc_minb() == 3) k_gc_dopri5<Field<KIND>, 3><<<grid, 128, grid_cache_bytes(a, k_gc_dopri5<Field<KIND>, 3>, 128), s>>>(a);
+    else k_gc_dopri5<Field<KIND>, 2><<<grid, 128, grid_cache_bytes(a, k_gc_dopri5<Field<KIND>, 2>, 128), s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_gc(const rapt::AdvArgs &a, int grid, cudaStream_t s)

@@ -120,10 +120,25 @@ __device__ void rapt_user_E(double t, double x, double y, double z, const double
 // interpolation between the two bracketing time points does not depend on the window, so all time points
 // stay resident in HBM and the window is the bracketing pair.
 // ------------------------------------------------------------------------------------------
-RAPT_DEV const GridP &grid_of(const FieldP &f) { return *reinterpret_cast<const GridP *>(f.prm); }
+// FieldP::prm[0] carries the device address of the grid's GridP block (read as a value: taking the address of a
+// kernel parameter would force a local copy of the whole argument struct)
+RAPT_DEV const GridP *grid_of(const FieldP &f) { return reinterpret_cast<const GridP *>(__double_as_longlong(f.prm[0])); }
+struct GridVec { double x, y, z; };
 
 RAPT_DEV bool grid_locate(const double *__restrict__ g, int n, double g0, double ginv, double v, int &idx, double &w)
 {
+#if !RAPT_STRICT
+    if (ginv != 0.0) {
+        // fast flavour, uniform axis: index and normalised distance from the arithmetic node positions
+        // g0 + k/ginv -- no table look-ups, no division; differs from the stored nodes by their rounding
+        // (~1e-13 of a cell)
+        const double u = (v - g0) * ginv;
+        if (!(u >= 0.0 && u <= (double)(n - 1))) return false;
+        const int k0 = min((int)u, n - 2);
+        idx = k0; w = u - (double)k0;
+        return true;
+    }
+#endif
     if (!(__ldg(g) <= v && v <= __ldg(g + n - 1))) return false;
     int k;
     if (ginv != 0.0) {                               // uniform axis: direct index, then make it exact
@@ -148,9 +163,32 @@ RAPT_DEV bool grid_locate(const double *__restrict__ g, int n, double g0, double
     return true;
 }
 
-RAPT_DEV void grid_eval(const GridP &g, const double *__restrict__ tab, double t, double x, double y, double z,
-                        double &o0, double &o1, double &o2)
+// one shared copy per kernel (the unrolled particle kernel has 13 call sites: inlined, its hot loop no longer
+// fits the instruction cache -- profiles/r1_grid_field.md)
+// Per-thread cell cache in dynamic shared memory (advance kernels of a gridded field are launched with
+// blockDim * 8 * (1 + 24 * min(nt, 2)) bytes): slot 0 = index of the cached cell, then the 8 (16 with time
+// interpolation) vertices of that cell, 3 components each, entry k of thread i at word k * blockDim + i
+// (conflict-free).  Consecutive evaluations of one tracer -- the RK stages of a step, the 7 stencil points
+// of the guiding-centre right-hand side -- almost always fall in the same cell, so the 16 gathers of 32-byte
+// sectors through L1/L2 happen once per cell instead of once per evaluation (profiles/r1_grid_field.md).
+RAPT_DEV unsigned grid_dynamic_smem()
 {
+    unsigned n;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(n));
+    return n;
+}
+RAPT_DEV void grid_cache_reset()
+{
+    extern __shared__ double rapt_grid_cache[];
+    if (grid_dynamic_smem() >= blockDim.x * 8u) rapt_grid_cache[threadIdx.x] = __longlong_as_double(-1LL);
+}
+
+static __device__ __noinline__ GridVec grid_eval(const GridP *__restrict__ gp, int which, double t, double x, double y, double z)
+{
+    extern __shared__ double rapt_grid_cache[];
+    const GridP g = *gp;                             // uniform loads, L1-resident
+    const double *__restrict__ tab = which ? g.E : g.B;
+    GridVec r;
     int it = 0, ix, iy, iz;
     double wt = 0, wx, wy, wz;
     bool ok = grid_locate(g.x, g.nx, g.x0, g.xinv, x, ix, wx);
@@ -158,10 +196,29 @@ RAPT_DEV void grid_eval(const GridP &g, const double *__restrict__ tab, double t
     ok = grid_locate(g.z, g.nz, g.z0, g.zinv, z, iz, wz) && ok;
     const int ntp = (g.nt >= 2) ? 2 : 1;
     if (ntp == 2) ok = grid_locate(g.t, g.nt, 0.0, 0.0, t, it, wt) && ok;
-    if (!ok) { o0 = o1 = o2 = RAPT_NAN; return; }
+    if (!ok) { r.x = r.y = r.z = RAPT_NAN; return r; }
     const size_t sy = (size_t)g.nz, sx = sy * g.ny, st = sx * g.nx;
-    const double2 *__restrict__ node = reinterpret_cast<const double2 *>(tab) + 2 * ((it * st + ix * sx) + iy * sy + iz);
+    const size_t cell = (it * st + ix * sx) + iy * sy + iz;
+    const double2 *__restrict__ node = reinterpret_cast<const double2 *>(tab) + 2 * cell;
+    const unsigned nthr = blockDim.x;
+    const bool cached = (which == 0) && grid_dynamic_smem() >= nthr * 8u * (1u + 24u * ntp);
+    double *my = rapt_grid_cache + threadIdx.x;
+    if (cached && __double_as_longlong(my[0]) != (long long)cell) {
+        // refill: vertex pairs in evaluation order, 6 doubles each (x, y, z of the lower and the upper z-node)
+        int k = 1;
+        for (int a = 0; a < ntp; a++)
+            for (int b = 0; b < 2; b++)
+                for (int c = 0; c < 2; c++) {
+                    const double2 *q = node + 2 * (a * st + b * sx + c * sy);
+                    const double2 lxy = __ldg(q), lz = __ldg(q + 1), hxy = __ldg(q + 2), hz = __ldg(q + 3);
+                    my[(k + 0) * nthr] = lxy.x; my[(k + 1) * nthr] = lxy.y; my[(k + 2) * nthr] = lz.x;
+                    my[(k + 3) * nthr] = hxy.x; my[(k + 4) * nthr] = hxy.y; my[(k + 5) * nthr] = hz.x;
+                    k += 6;
+                }
+        my[0] = __longlong_as_double((long long)cell);
+    }
     double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+    int k = 1;
 #pragma unroll
     for (int a = 0; a < 2; a++) {
         if (a >= ntp) break;
@@ -172,15 +229,24 @@ RAPT_DEV void grid_eval(const GridP &g, const double *__restrict__ tab, double t
 #pragma unroll
             for (int c = 0; c < 2; c++) {
                 const double fy = fx * (c ? wy : 1 - wy);
-                const double2 *q = node + 2 * (a * st + b * sx + c * sy);      // two z-neighbours: 64 contiguous bytes
-                const double2 lxy = __ldg(q), lz = __ldg(q + 1), hxy = __ldg(q + 2), hz = __ldg(q + 3);
+                double lx, ly, lzz, hx, hy, hzz;
+                if (cached) {
+                    lx = my[(k + 0) * nthr]; ly = my[(k + 1) * nthr]; lzz = my[(k + 2) * nthr];
+                    hx = my[(k + 3) * nthr]; hy = my[(k + 4) * nthr]; hzz = my[(k + 5) * nthr];
+                    k += 6;
+                } else {
+                    const double2 *q = node + 2 * (a * st + b * sx + c * sy);      // two z-neighbours: 64 contiguous bytes
+                    const double2 lxy = __ldg(q), lz = __ldg(q + 1), hxy = __ldg(q + 2), hz = __ldg(q + 3);
+                    lx = lxy.x; ly = lxy.y; lzz = lz.x; hx = hxy.x; hy = hxy.y; hzz = hz.x;
+                }
                 const double w0 = fy * (1 - wz), w1 = fy * wz;
-                v0 = v0 + lxy.x * w0; v1 = v1 + lxy.y * w0; v2 = v2 + lz.x * w0;
-                v0 = v0 + hxy.x * w1; v1 = v1 + hxy.y * w1; v2 = v2 + hz.x * w1;
+                v0 = v0 + lx * w0; v1 = v1 + ly * w0; v2 = v2 + lzz * w0;
+                v0 = v0 + hx * w1; v1 = v1 + hy * w1; v2 = v2 + hzz * w1;
             }
         }
     }
-    o0 = v0; o1 = v1; o2 = v2;
+    r.x = v0; r.y = v1; r.z = v2;
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -260,8 +326,8 @@ template <int KIND> struct Field {
             else bx = sgn(z) * RAPT_EARTH_B0;
             by = 0; bz = f.prm[1];
         } else if (KIND == 6) {             // Grid.B -> Grid.Bgrid, fields.py:707-741, 774-794
-            const GridP &g = grid_of(f);
-            grid_eval(g, g.B, t, x, y, z, bx, by, bz);
+            const GridVec r = grid_eval(grid_of(f), 0, t, x, y, z);
+            bx = r.x; by = r.y; bz = r.z;
         }
 #ifdef RAPT_USER_FIELD
         else if (KIND == 100) {
@@ -298,8 +364,10 @@ template <int KIND> struct Field {
         ex = 0; ey = 0; ez = 0;             // fields.py:59-74
         if (KIND == 3) ey = f.prm[1];       // fields.py:427
         if (KIND == 6) {                    // Grid.E -> Grid.Egrid, fields.py:743-772, 796-814
-            const GridP &g = grid_of(f);
-            if (g.E) grid_eval(g, g.E, t, x, y, z, ex, ey, ez);
+            if (f.prm[1] != 0.0) {          // the grid has an electric field table
+                const GridVec r = grid_eval(grid_of(f), 1, t, x, y, z);
+                ex = r.x; ey = r.y; ez = r.z;
+            }
         }
 #if defined(RAPT_USER_FIELD) && RAPT_USER_HAS_E
         if (KIND == 100) {

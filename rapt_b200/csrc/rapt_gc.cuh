@@ -230,6 +230,7 @@ RAPT_DEV bool gc_isadiabatic(const FieldP &f, const ParamsP &p, double t, const 
 template <class F, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
 {
+    if (F::CAN_FAIL) grid_cache_reset();     // gridded field: per-thread cell cache (rapt_fields.cuh)
     const double rtol = a.p.rtol, atol = a.p.atol;
     const int eqf = a.p.enforce_equatorial, eom = a.eom;
     const double beta = 0.04, safe = 0.9, fac1 = 0.2, fac2 = 10.0, uround = 2.3e-16;

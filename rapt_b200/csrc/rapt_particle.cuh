@@ -112,6 +112,7 @@ RAPT_DEV bool particle_isadiabatic(const FieldP &f, const ParamsP &p, double t, 
 template <class F>
 __global__ void __launch_bounds__(128, 2) k_particle_dop853(const AdvArgs a)
 {
+    if (F::CAN_FAIL) grid_cache_reset();     // gridded field: per-thread cell cache (rapt_fields.cuh)
     const double rtol = a.p.rtol, atol = a.p.atol;
     const int eqf = a.p.enforce_equatorial;
     const double beta = 0.1, safe = 0.9, fac1 = 0.3, fac2 = 6.0, uround = 2.3e-16;

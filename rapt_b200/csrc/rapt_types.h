@@ -12,8 +12,8 @@ struct FieldP {
 };
 
 // fields.Grid (rapt/fields.py:513-814) on the device.  The host side of the C ABI resolves
-// rapt_field_t.user_id (the handle of rapt_b200_grid_create) into this block and places it in FieldP::prm,
-// so every kernel receives the table pointers as kernel parameters.
+// rapt_field_t.user_id (the handle of rapt_b200_grid_create) into the device address of this block
+// (FieldP::prm[0]; prm[1] != 0: the grid has an electric-field table).
 // Tables: B and E as [nt][nx][ny][nz] nodes of 4 doubles (x, y, z component + pad): the two z-neighbours
 // of a cell edge are one aligned 64-byte segment.  E == nullptr: the electric field is identically zero.
 struct GridP {
@@ -22,7 +22,6 @@ struct GridP {
     int nt, nx, ny, nz;
     double x0, xinv, y0, yinv, z0, zinv;   // uniform axis: first node and 1/spacing (inv == 0: not uniform)
 };
-static_assert(sizeof(GridP) <= 16 * sizeof(double), "GridP must fit FieldP::prm");
 
 struct ParamsP {
     double rtol, atol, cyclotronresolution, epss, epst;

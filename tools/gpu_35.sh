@@ -1,0 +1,5 @@
+python tools/bench_grid.py 1048576 1.0 1 129 fast 2>&1 | tail -1
+python tools/bench_grid.py 1048576 1.0 2 129 fast 2>&1 | tail -1
+python tools/bench_grid.py 1048576 1.0 1 257 fast 2>&1 | tail -1
+ncu --set full --clock-control none --import-source on -k regex:k_particle_rkn -c 1 -o gpurun_out/prof_grid_r1a python tools/bench_grid.py 262144 0.5 1 129 fast > gpurun_out/ncu_grid.log 2>&1
+tail -2 gpurun_out/ncu_grid.log | cut -c1-300
