@@ -401,11 +401,11 @@ def main():
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this configuration, one
-                         # launch, from `ncu --set full` (profiles/r1_particle_v6_bench_kernel_ncu_summary.txt):
-                         # 522 MB + 310 MB.  4.6x the algorithmic state I/O because tracers are fetched in
-                         # longest-first order, i.e. as scattered 8-byte accesses (32-byte sectors); at 0.36 s
-                         # per launch that is 2 GB/s and irrelevant to this compute-bound kernel.
-                         "traffic": 831857152 if (n == N_PER_GPU and args.delta == DELTA and not is_gc) else None,
+                         # launch, from `ncu --set full` (profiles/r1_particle_v8_bench_kernel_ncu_summary.txt):
+                         # 452 MB + 289 MB.  4x the algorithmic state I/O because tracers are fetched in
+                         # longest-first order, i.e. as scattered 8-byte accesses (32-byte sectors); at 0.27 s
+                         # per launch that is 3 GB/s and irrelevant to this compute-bound kernel.
+                         "traffic": 740606720 if (n == N_PER_GPU and args.delta == DELTA and not is_gc) else None,
                          "peak_source": "FP64 DFMA microbenchmark measured in this run (rapt_b200_fp64_peak); "
                                         "MEASURED_PEAKS.json has HBM and bf16 only",
                          "algorithmic_flop_per_step": flops / nstep,
