@@ -108,8 +108,8 @@ def test_spline_matches_interp1d(hc):
         assert np.max(np.abs(out - B(x)) / np.abs(B(x))) < 5e-15
 
 
-@pytest.mark.parametrize("pa_eq", [72, 80, 85, 89])
-@pytest.mark.parametrize("n", [48, 61, 150])
+@pytest.mark.parametrize("pa_eq", [72, 80, 85, 88])
+@pytest.mark.parametrize("n", [61, 150, 400])
 def test_halfbounce_and_eye_match_the_reference_route(hc, pa_eq, n):
     """flutils.halfbouncepath / eye's scipy route (interp1d + brentq + quad epsrel 1e-4) on synthetic curves."""
     rng = np.random.default_rng(100 * pa_eq + n)
