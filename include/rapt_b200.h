@@ -67,6 +67,7 @@ extern "C" {
 #define RAPT_ST_HSMALL       -3   /* dop: step size underflow                                      */
 #define RAPT_ST_GCITER       -5   /* utils.guidingcenter did not converge (utils.py:326)           */
 #define RAPT_ST_FIELD        -6   /* fields.Grid evaluated outside the grid: scipy's ValueError (fields.py:735-740); rows so far are kept */
+#define RAPT_ST_TRACE        -7   /* bounce centre: a field line could not be traced between its mirror points (the reference raises: flutils.py:117,311) */
 #define RAPT_ST_ROWCAP      -10   /* adaptive: row buffer full before t0+delta                     */
 
 #define RAPT_MODE_PARTICLE 0
@@ -197,13 +198,48 @@ int rapt_b200_bounce_setup(const rapt_field_t *f, int arith, double fieldlineres
                            double *Bm, double *v, double *ds, int32_t *npts, int64_t max_pts, double *curve);
 
 /* ---- GuidingCenter.bounceperiod entirely on the device: the trace above followed by
- * flutils.halfbouncepath (flutils.py:274-316) with scipy's quadratic interpolating spline rebuilt per thread
- * and the mirror points and the integral of 1/sqrt(1 - B(s)/Bm) taken in closed form span by span.  The
- * result equals the reference's up to the error of its own QUADPACK call (epsrel 1e-4 requested; 1e-7 typical, up to 2e-5 observed).
+ * flutils.halfbouncepath (flutils.py:274-316) with scipy's quadratic interpolating spline rebuilt per thread.
+ *   quadrature = RAPT_QUAD_QUADPACK: the reference's own route -- brentq for the two mirror points and QUADPACK
+ *     QAGS (epsabs 1.49e-8, epsrel 1e-4, limit 50) on 1/sqrt(1 - B(s)/Bm), both restated per thread; equals
+ *     the reference's value to ~1e-9 (the integrand is evaluated within 1e-10 of its singularities);
+ *   quadrature = RAPT_QUAD_CLOSED: mirror points and integral in closed form span by span; no quadrature error,
+ *     so it differs from the reference by QUADPACK's own error (1e-7 typical, up to 2e-5 observed).
  * period[i] = NaN if the trace did not bracket both mirror points.  npts may be NULL.  HOST pointers. */
-int rapt_b200_bounce_period(const rapt_field_t *f, int arith, double fieldlineresolution, int64_t n,
+#define RAPT_QUAD_CLOSED   0
+#define RAPT_QUAD_QUADPACK 1
+int rapt_b200_bounce_period(const rapt_field_t *f, int arith, int quadrature, double fieldlineresolution, int64_t n,
                             const double *t, const double *x, const double *y, const double *z, const double *ppar,
                             const double *mu, const double *mass, double *period, int32_t *npts);
+
+/* ---- BounceCenter.advance (rapt/BounceCenter.py:206-251) for n bounce centres.
+ * State in/out: t (the row label = BounceCenter.tcur), x, y, z.  mu, v (speed), mass, charge per tracer.
+ * Each tracer: dt = bctimestep * bounceperiod(last row) (params["BCtimestep"], BounceCenter.py:228-229; or
+ * dt_in[i] when dt_in != NULL), then len(np.arange(tcur, tcur+delta, dt)) rows, each one scipy "dopri5" call over
+ * dt (rtol, atol = params["solvertolerances"]) on dR/dt = gamma m v^2/(q S_b B^2) gradI x B, where S_b =
+ * flutils.halfbouncepath (:254-316) and gradI = flutils.gradI (:153-229, step eyegradientstep =
+ * params["eyegradientstep"]) trace five field lines per evaluation (fieldlineresolution =
+ * params["fieldlineresolution"]).  As in the reference the label of a row is the START time of its step.
+ * rows[(i*max_rows + k)*4 + c], c = t, x, y, z (every store_every-th row, row 0 = first computed row);
+ * counters = n x 4 int32 (nfcn, nstep, naccpt, nrejct of dopri5, summed over rows); status: RAPT_ST_OK,
+ * RAPT_ST_NMAX / RAPT_ST_HSMALL (scipy warns and the reference carries on with the unfinished row; here the
+ * tracer stops), RAPT_ST_TRACE.  dt_out (optional) receives the step.  Only static fields (the reference's
+ * constructor raises otherwise, BounceCenter.py:104-105); gridded fields are RAPT_E_UNSUPPORTED.  HOST pointers. */
+int rapt_b200_bounce_center_advance(const rapt_field_t *f, int arith, int quadrature, int64_t n,
+                                    double *t, double *x, double *y, double *z,
+                                    const double *mu, const double *v, const double *mass, const double *charge,
+                                    const double *dt_in, double bctimestep, double delta,
+                                    double rtol, double atol, double fieldlineresolution, double eyegradientstep,
+                                    int64_t store_every, int64_t max_rows, double *rows,
+                                    int32_t *nrows, int32_t *nstored, int32_t *counters, int32_t *status, double *dt_out);
+
+/* ---- the pieces of that right-hand side at n points, for callers of flutils.halfbouncepath / eye / gradI
+ * (rapt/flutils.py:65-316; rapt/__init__.py:42 exports them): out[i*8 + c], c = S_b, I, gradI_x, gradI_y, gradI_z,
+ * and BounceCenter.advance's deriv_x, deriv_y, deriv_z (needs v, mass, charge; pass NULL to get NaN there).
+ * Bm per point (mirror field).  status[i] as above.  HOST pointers. */
+int rapt_b200_bounce_center_terms(const rapt_field_t *f, int arith, int quadrature, int64_t n,
+                                  const double *t, const double *x, const double *y, const double *z, const double *Bm,
+                                  const double *v, const double *mass, const double *charge,
+                                  double fieldlineresolution, double eyegradientstep, double *out, int32_t *status);
 
 /* ---- Adaptive.__init__ + Adaptive.advance (Adaptive.py:70-104, 187-222) for an ensemble.
  * In: particle position/velocity (as the Adaptive constructor takes them), t0, mass, charge.

@@ -501,10 +501,63 @@ def case_units():
     save("units", **out)
 
 
+def case_bc():
+    """BounceCenter.advance (BounceCenter.py:206-251) and the flutils integrals behind it (flutils.py:65-316), from
+    the UNMODIFIED reference.  Pitch angles are chosen so that the equatorial pitch angle is >= 70 degrees: below
+    that the reference stops with NameError (`simps`, flutils.py:130).  NB the constructor feeds the pitch angle in
+    degrees to a radian cosine (BounceCenter.py:114): pa = 80 means cos(80 rad) = -0.110, i.e. 96.3 degrees."""
+    from rapt import flutils as rfu
+    from scipy.integrate import simpson
+    cases = [
+        ("bc_dipole_electron", rf.EarthDipole(), "EarthDipole", (6 * Re, 0, 0.1 * Re), ru.speedfromKE(1e6, m_el), 80, m_el, -e, 0.3, 0.2),
+        ("bc_dipole_proton", rf.EarthDipole(), "EarthDipole", (3 * Re, 2.5 * Re, -0.15 * Re), ru.speedfromKE(1e7, m_pr), 30, m_pr, e, 0.8, 0.0),
+        ("bc_doubledipole_electron", rf.DoubleDipole(), "DoubleDipole", (-5 * Re, 4 * Re, 0.2 * Re), ru.speedfromKE(3e5, m_el), 80, m_el, -e, 0.35, 0.0),
+    ]
+    for name, f, fname, pos, v, pa, mass, charge, delta, delta2 in cases:
+        refshim.reset_params(rapt)
+        refshim.SOLVER_LOG.clear()
+        b = rapt.BounceCenter(pos=pos, v=v, t0=0, pa=pa, mass=mass, charge=charge, field=f)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            b.advance(delta)
+            n1 = len(b.trajectory)
+            if delta2:
+                b.advance(delta2)            # second call: restarts from the last row LABEL (BounceCenter.py:247,250)
+        log = take_log()
+        gamma = 1.0 / np.sqrt(1 - (v / c) ** 2)
+        Bm = mass * gamma ** 2 * v ** 2 / (2 * b.mu)
+        # the pieces at the first, a middle and the last row
+        pts = b.trajectory[[0, len(b.trajectory) // 2, -1]]
+        Sb = np.array([rfu.halfbouncepath(r, f, Bm) for r in pts])
+        I = np.array([rfu.eye(r, f, Bm) for r in pts])
+        gI = np.array([rfu.gradI(r, f, Bm) for r in pts])
+        save(name, field=fname, pos=np.array(pos), v=v, pa=float(pa), mass=mass, charge=charge, delta=delta, delta2=delta2,
+             nrows_first_call=n1, traj=b.trajectory, mu=b.mu, Bm=Bm, solver_log=log, pts=pts, Sb=Sb, I=I, gradI=gI)
+    # flutils on its own, including the cases BounceCenter cannot reach in the reference:
+    #  * forward/backward differences in gradI when a displaced field line lies beyond the mirror field (flutils.py:212-215)
+    #  * the Simpson branch (eqpa < 70) with the missing name bound to scipy's simpson (fixture says so)
+    f = rf.EarthDipole()
+    refshim.reset_params(rapt)
+    rows = []
+    for L, zz, eqpa in ((5.0, 0.0, 89.0), (5.0, 0.05, 88.0), (4.0, 0.3, 75.0), (6.5, -0.2, 80.0)):
+        tpos = np.array([0.0, L * Re * np.cos(0.3), L * Re * np.sin(0.3), zz * Re])
+        Bm = f.magB(np.array([0.0, L * Re * np.cos(0.3), L * Re * np.sin(0.3), 0.0])) / np.sin(np.radians(eqpa)) ** 2
+        rows.append((tpos, Bm, rfu.halfbouncepath(tpos, f, Bm), rfu.eye(tpos, f, Bm), rfu.gradI(tpos, f, Bm), 0))
+    rfu.simps = lambda y, x: simpson(y, x=x)
+    for L, zz, eqpa in ((5.0, 0.2, 45.0), (3.0, -0.1, 60.0)):
+        tpos = np.array([0.0, L * Re * np.cos(1.3), L * Re * np.sin(1.3), zz * Re])
+        Bm = f.magB(np.array([0.0, L * Re * np.cos(1.3), L * Re * np.sin(1.3), 0.0])) / np.sin(np.radians(eqpa)) ** 2
+        rows.append((tpos, Bm, rfu.halfbouncepath(tpos, f, Bm), rfu.eye(tpos, f, Bm), rfu.gradI(tpos, f, Bm), 1))
+    del rfu.simps
+    save("bc_flutils", field="EarthDipole", tpos=np.array([r[0] for r in rows]), Bm=np.array([r[1] for r in rows]),
+         Sb=np.array([r[2] for r in rows]), I=np.array([r[3] for r in rows]), gradI=np.array([r[4] for r in rows]),
+         simps_name_bound=np.array([r[5] for r in rows]))
+
+
 CASES = {
     "g1": case_g1, "g1b": case_g1b, "pfields": case_pfields, "g2": case_g2, "gcfields": case_gcfields,
     "g3": case_g3, "e4": case_e4, "adip": case_adaptive_dipole, "e2": case_e2, "e3": case_e3,
-    "e5": case_e5, "units": case_units, "eye": case_eye, "grid": case_grid,
+    "e5": case_e5, "units": case_units, "eye": case_eye, "grid": case_grid, "bc": case_bc,
 }
 
 if __name__ == "__main__":

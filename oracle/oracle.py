@@ -362,3 +362,119 @@ def adaptive_c(f, par, pos, vel, t0, mass, charge, delta, max_rows=1 << 16, max_
                                      C.c_double(charge), C.c_double(delta), _p(rows), C.c_long(max_rows), C.byref(nrows),
                                      _p(seglog), C.c_long(max_segs), _p(cnt))
     return nseg, rows[:nrows.value], seglog[:max(nseg, 0)], cnt
+
+
+# ---------------------------------------------------------------- BounceCenter
+def eye_from_curve(s, b, Bm):
+    """flutils.eye (flutils.py:95-151) on a traced curve.  scipy's interp1d / brentq / quad as the reference calls
+    them; the eqpa < 70 branch calls `simps`, which the reference never imports (NameError) -- evaluated with
+    scipy.integrate.simpson(y, x=x), the function its import line (flutils.py:18) provides."""
+    from scipy.interpolate import interp1d
+    from scipy.optimize import brentq
+    from scipy.integrate import quad, simpson
+    s = np.array(s, dtype=float); b = np.array(b, dtype=float)
+    n = len(b)
+    Bmin = np.min(b)
+    if Bmin > Bm:
+        return 0
+    if abs(Bmin - Bm) / Bm < 1e-12:
+        return 0
+    inside = np.where(b < Bm)[0]
+    drop = list(range(0, inside[0] - 1)) + list(range(inside[-1] + 2, n))
+    b = np.delete(b, drop); s = np.delete(s, drop)
+    assert b[0] > Bm and b[1] < Bm and b[-2] < Bm and b[-1] > Bm
+    eqpa = np.arcsin(np.sqrt(Bmin / Bm)) * 180 / np.pi
+    if eqpa < 70:
+        sm1 = (Bm - b[0]) * (s[1] - s[0]) / (b[1] - b[0]) + s[0]
+        sm2 = (Bm - b[-2]) * (s[-1] - s[-2]) / (b[-1] - b[-2]) + s[-2]
+        s[0], s[-1] = sm1, sm2
+        b[0], b[-1] = Bm, Bm
+        bi = np.sqrt(1 - b[1:-1] / Bm)
+        I = simpson(bi, x=s[1:-1])
+        d = s[-1] - s[-2]
+        I += (2 / 3) * d * np.sqrt((Bm - b[-2]) / Bm)
+        d = s[1] - s[0]
+        I += (2 / 3) * d * np.sqrt((Bm - b[1]) / Bm)
+        return I
+    B = interp1d(s, b, kind='quadratic', assume_sorted=True)
+    sm1 = brentq(lambda x: B(x) - Bm, s[0], s[1])
+    if B(s[-2]) == Bm:
+        sm2 = s[-2]
+    else:
+        sm2 = brentq(lambda x: B(x) - Bm, s[-2], s[-1])
+    return quad(lambda x: np.sqrt(1 - B(x) / Bm), sm1, sm2, epsrel=1e-4)[0]
+
+
+def eye(f, tpos, Bm, fieldlineresolution=50):
+    curve, B, _ = fieldline_trace(f, tpos, Bm, fieldlineresolution)
+    return eye_from_curve(curve[:, 0], B, Bm)
+
+
+def halfbouncepath(f, tpos, Bm, fieldlineresolution=50):
+    curve, B, _ = fieldline_trace(f, tpos, Bm, fieldlineresolution)
+    return halfbouncepath_from_curve(curve[:, 0], B, Bm)
+
+
+def gradI(f, tpos, Bm, d=0.03 * Re, fieldlineresolution=50):
+    """flutils.gradI (flutils.py:183-229)."""
+    tpos = np.array(tpos, dtype=float)
+    x, y = tpos[1], tpos[2]
+    r = np.array((x, y, 0)) / max((abs(x), abs(y)))
+    b = field_ops(f, tpos)["unitb"][0]
+    r = r - np.dot(r, b) * b
+    r = r / np.sqrt(np.dot(r, r))
+    v1 = np.zeros(4); v1[1:4] = r
+    v2 = np.zeros(4); v2[1:4] = np.cross(b, r)
+    I = lambda p: eye(f, p, Bm, fieldlineresolution)
+    out = []
+    for v in (v1, v2):
+        I1 = I(tpos + d * v); I2 = I(tpos - d * v)
+        if I1 == 0:
+            out.append((I(tpos) - I2) / d)
+        elif I2 == 0:
+            out.append((I1 - I(tpos)) / d)
+        else:
+            out.append((I1 - I2) / (2 * d))
+    return out[0] * v1[1:] + out[1] * v2[1:]
+
+
+def bc_mirror_field(mu, v, mass):
+    """BounceCenter.py:226-227"""
+    gamma = 1.0 / np.sqrt(1 - (v / 299792458) ** 2)
+    return mass * gamma ** 2 * v ** 2 / (2 * mu), gamma
+
+
+def bc_deriv(f, t, Y, Bm, gamma, v, mass, charge, d=0.03 * Re, fieldlineresolution=50):
+    """BounceCenter.advance.deriv (BounceCenter.py:232-243)."""
+    tpos = np.concatenate(([t], Y))
+    Bvec = field_ops(f, tpos)["B"][0]
+    magBsq = np.dot(Bvec, Bvec)
+    Sb = halfbouncepath(f, tpos, Bm, fieldlineresolution)
+    gI = gradI(f, tpos, Bm, d, fieldlineresolution)
+    return gamma * mass * v * v / (charge * Sb * magBsq) * np.cross(gI, Bvec)
+
+
+def bounce_center_advance(f, row, mu, v, mass, charge, delta, bctimestep=0.1, tol=(1.49012e-8, 1.49012e-8),
+                          d=0.03 * Re, fieldlineresolution=50):
+    """BounceCenter.advance (BounceCenter.py:206-251) for one tracer from its last row (t, x, y, z): the reference's
+    control flow, the C dopri5 of this oracle on the Python right-hand side above.  Returns (rows (k,4), counters, dt)."""
+    row = np.array(row, dtype=float)
+    Bm, gamma = bc_mirror_field(mu, v, mass)
+    dt = bctimestep * (2 / v) * halfbouncepath(f, row[:4], Bm, fieldlineresolution)
+    CB = C.CFUNCTYPE(None, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+    def rhs(t, yp, dyp):
+        Y = np.array([yp[0], yp[1], yp[2]])
+        out = bc_deriv(f, t, Y, Bm, gamma, v, mass, charge, d, fieldlineresolution)
+        dyp[0], dyp[1], dyp[2] = out[0], out[1], out[2]
+    cb = CB(rhs)
+    x = C.c_double(row[0]); y = row[1:4].copy(); cnt = np.zeros(4, dtype=np.int64)
+    rows = []
+    tcur = row[0]
+    for t in np.arange(tcur, tcur + delta, dt):
+        idid = lib().oracle_dopri5_callback(C.c_int(3), cb, C.byref(x), _p(y), C.c_double(x.value + dt),
+                                            C.c_double(tol[0]), C.c_double(tol[1]), _p(cnt))
+        if idid != 1:
+            break
+        rows.append(np.concatenate(([t], y)))
+    return np.array(rows).reshape(-1, 4), cnt, dt

@@ -1020,6 +1020,20 @@ int oracle_test_solver(int which_solver, int which_ode, double x0, double xend, 
     return idid;
 }
 
+/* dopri5 on a caller-supplied right-hand side (BounceCenter.advance, BounceCenter.py:246-249: the RHS there is
+ * scipy quadrature over field-line traces, which oracle.py evaluates with scipy itself, as the reference does) */
+typedef void (*cb_rhs_fn)(double t, const double *y, double *dy);
+typedef struct { cb_rhs_fn fn; } cb_ctx_t;
+static void cb_rhs(double t, const double *y, double *dy, void *ctx) { ((cb_ctx_t *)ctx)->fn(t, y, dy); }
+int oracle_dopri5_callback(int n, cb_rhs_fn fn, double *x, double *y, double xend, double rtol, double atol, long *counters)
+{
+    ocount_t c = { 0, 0, 0, 0 }; cb_ctx_t ctx = { fn };
+    g_field_err = 0;
+    int idid = dopri5(n, cb_rhs, &ctx, x, y, xend, rtol, atol, &c);
+    counters[0] += c.nfcn; counters[1] += c.nstep; counters[2] += c.naccpt; counters[3] += c.nrejct;
+    return idid;
+}
+
 /* Particle ensemble.  In/out SoA state t,x,y,z,px,py,pz (n each); mass, charge per particle.
  * rows: n x max_rows x 8 (row 0 of each particle = initial state) or NULL.
  * Outputs per particle: nrows (1 + output intervals), nstored, counters[4], status, tcur, dt.

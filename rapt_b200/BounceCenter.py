@@ -1,15 +1,22 @@
-"""BounceCenter: API surface only (rapt/BounceCenter.py:74-316).
+"""BounceCenter (rapt/BounceCenter.py:17-316): the bounce-averaged drift tracer, SURVEY.md §8f N4.
 
-The bounce-averaged drift tracer is outside the B200 hot path: its
-right-hand side is host-side quadrature and root finding over five field-line traces per evaluation,
-the reference's implementation depends on the broken `flutils.eye` (`simps` undefined,
-flutils.py:130), and its author deprecates it (BounceCenter.py:59-70).  The constructor, `setpa`,
-`save`/`load` and the getters keep the reference's behaviour; `advance` raises.
+`advance` runs on the device (rapt_b200/csrc/rapt_bc.cuh): scipy's dopri5 per output row on
+dR/dt = gamma m v^2/(q S_b B^2) gradI x B, every right-hand side tracing five field lines and running the
+reference's spline / brentq / QUADPACK route on them, one thread per tracer.  Reference behaviour kept: the
+constructor takes cos() of the pitch angle as given (BounceCenter.py:114 -- degrees fed to a radian cosine), rows are
+labelled with the START time of their step (BounceCenter.py:248-249), only static fields are accepted.
+Two reference defects are not reproduced: equatorial pitch angles below 70 degrees stop with NameError in
+flutils.eye (`simps`, flutils.py:130) -- here that branch runs with scipy.integrate.simpson's rule, the function the
+reference imports; and `isequatorial = True` indexes a 3-vector as a 4-vector (BounceCenter.py:235) -- not offered.
+For many tracers use rapt_b200.ensemble.BounceCenterEnsemble.
 """
 import pickle
+import warnings
+
 import numpy as np
 
 from . import utils as ru
+from . import engine, params
 
 
 class BounceCenter:
@@ -37,8 +44,34 @@ class BounceCenter:
         self.__init__(self.pos, self.v, self.t0, pa, self.mass, self.charge, self.field)
 
     def advance(self, delta):
-        raise NotImplementedError("BounceCenter.advance is outside the B200 hot path (SURVEY.md §8f N4); use "
-                                  "GuidingCenter.advance for bounce + drift motion")
+        """Advance the bounce centre by `delta` seconds (rapt/BounceCenter.py:206-251) on the device."""
+        if self.isequatorial:
+            raise NotImplementedError("BounceCenter.isequatorial: the reference's branch cannot run (BounceCenter.py:235)")
+        last = self.trajectory[-1, :4]
+        # rows needed: len(np.arange(tcur, tcur+delta, dt)); dt comes from the device, so size the buffer in two passes
+        probe = engine.bounce_center_terms(self.field, last, self._mirror_field(), params=params)
+        if probe["status"][0] != 1 or not np.isfinite(probe["Sb"][0]):
+            raise RuntimeError("BounceCenter.advance: the field line through the current position could not be traced "
+                               "between its mirror points")
+        dt = params["BCtimestep"] * (2 / self.v) * probe["Sb"][0]
+        nrows = len(np.arange(self.tcur, self.tcur + delta, dt))
+        res = engine.bounce_center_advance(self.field, last, self.mu, self.v, self.mass, self.charge, delta,
+                                           store_every=1, max_rows=max(nrows, 1), params=params)
+        k = int(res["nstored"][0])
+        if k:
+            self.trajectory = np.vstack((self.trajectory, res["rows"][0, :k]))
+        st = int(res["status"][0])
+        if st != 1:
+            warnings.warn(f"BounceCenter.advance stopped after {k} of {nrows} rows (status {st}: "
+                          f"{ {-2: 'dopri5: larger nsteps is needed', -3: 'dopri5: step size becomes too small', -7: 'field line not traceable between mirror points'}.get(st, 'error')})",
+                          UserWarning)
+        self.tcur = self.trajectory[-1, 0]
+
+    def _mirror_field(self):
+        # BounceCenter.py:226-227
+        from . import c
+        gamma = 1.0 / np.sqrt(1 - (self.v / c) ** 2)
+        return self.mass * gamma ** 2 * self.v ** 2 / (2 * self.mu)
 
     def save(self, filename):
         with open(filename, "wb") as f:

@@ -211,10 +211,10 @@ class GuidingCenter:
         return np.where(g - 1 < 1e-6, self.mu * B + 0.5 * pp ** 2 / self.mass, (g - 1) * self.mass * c * c)
 
     def bounceperiod(self):
-        """Bounce period at the current position (rapt/GuidingCenter.py:593-606): device field-line trace
-        (RKF45, rapt_b200/csrc/rapt_aux.cuh) + the reference's scipy quadrature over the traced curve."""
-        return float(engine.bounceperiod(self.field, self.trajectory[-1], self.mu, self.mass,
-                                         params["fieldlineresolution"])[0])
+        """Bounce period at the current position (rapt/GuidingCenter.py:593-606), all on the device: field-line
+        trace (RKF45, rapt_aux.cuh), then scipy's spline / brentq / QUADPACK route restated per thread (rapt_quad.cuh)."""
+        return float(engine.bounceperiod_device(self.field, self.trajectory[-1], self.mu, self.mass,
+                                                params["fieldlineresolution"], quadrature="quadpack")[0])
 
     def geteye(self, step=1):
         """(time, second invariant I) for every `step`-th row (rapt/GuidingCenter.py:608-624, flutils.py:65-151):

@@ -49,4 +49,6 @@ from .GuidingCenter import GuidingCenter     # noqa: E402
 from .Adaptive import Adaptive               # noqa: E402
 from .BounceCenter import BounceCenter       # noqa: E402
 from .fieldline import Fieldline             # noqa: E402
-from .ensemble import ParticleEnsemble, GuidingCenterEnsemble, AdaptiveEnsemble   # noqa: E402
+from .ensemble import ParticleEnsemble, GuidingCenterEnsemble, AdaptiveEnsemble, BounceCenterEnsemble   # noqa: E402
+from . import flutils                        # noqa: E402
+from .flutils import eye, gradI, halfbouncepath   # noqa: E402  (rapt/__init__.py:42)

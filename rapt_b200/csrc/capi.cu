@@ -126,7 +126,7 @@ int fill_common(rapt::AdvArgs &a, const rapt_field_t *f, const rapt_params_t *p)
 // (source, arithmetic flavour); the cubin is loaded with cudaLibraryLoadData.  libnvrtc is dlopen'ed on
 // first use so that the library itself loads on machines without the CUDA toolkit's NVRTC.
 // ------------------------------------------------------------------------------------------------
-enum { UK_PARTICLE = 0, UK_GC, UK_PARTICLE_DT, UK_FIELD_OPS, UK_MISC, UK_BOUNCE, UK_ADAPT, UK_COUNT };
+enum { UK_PARTICLE = 0, UK_GC, UK_PARTICLE_DT, UK_FIELD_OPS, UK_MISC, UK_BOUNCE, UK_ADAPT, UK_BC, UK_COUNT };
 const char *const k_user_kernel_exprs[UK_COUNT] = {
     "rapt_user::k_particle_dop853<rapt_user::Field<100> >",
     "rapt_user::k_gc_dopri5<rapt_user::Field<100>, 2>",
@@ -135,6 +135,7 @@ const char *const k_user_kernel_exprs[UK_COUNT] = {
     "rapt_user::k_misc<rapt_user::Field<100> >",
     "rapt_user::k_bounce_setup<rapt_user::Field<100> >",
     "rapt_user::k_adaptive_switch<rapt_user::Field<100> >",
+    "rapt_user::k_bounce_center<rapt_user::Field<100> >",
 };
 struct UserModule { bool built = false; cudaLibrary_t lib = nullptr; cudaKernel_t k[UK_COUNT] = {}; };
 struct UserField { std::string src; int has_E = 0; UserModule mod[2]; };
@@ -177,7 +178,7 @@ int nvrtc_compile(const UserField &uf, bool strict, std::string &cubin, std::str
     src += std::string("#define RAPT_USER_HAS_E ") + (uf.has_E ? "1" : "0") + "\n";
     src += std::string("#define RAPT_STRICT ") + (strict ? "1" : "0") + "\n";
     src += "#define RAPT_NS rapt_user\n";
-    src += "#include \"rapt_aux.cuh\"\n";
+    src += "#include \"rapt_bc.cuh\"\n";
     src += "namespace rapt_user {\n"
            "template <class F> __global__ void k_particle_dt(const rapt::AdvArgs a, double *key, int *idx) {\n"
            "  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; if (i >= a.nwork) return;\n"
@@ -251,6 +252,7 @@ int launch_any(const rapt_field_t *f, bool strict, int which, const void *args, 
         if (which == UK_PARTICLE_DT) { block = 256; grid = (int)((n + 255) / 256); }
         else if (which == UK_ADAPT) { block = 256; grid = (int)((n + 255) / 256); }
         else if (which == UK_FIELD_OPS || which == UK_MISC || which == UK_BOUNCE) grid = (int)((n + 127) / 128);
+        else if (which == UK_BC) block = 64;
         void *kargs[3] = {const_cast<void *>(args), &key, &idx};
         CK(cudaLaunchKernel((const void *)m->k[which], dim3(grid), dim3(block), kargs, 0, s));
         return RAPT_OK;
@@ -263,6 +265,7 @@ int launch_any(const rapt_field_t *f, bool strict, int which, const void *args, 
     case UK_MISC: CK(FLAVOUR(strict, launch_misc, args, s)); break;
     case UK_BOUNCE: CK(FLAVOUR(strict, launch_bounce, args, s)); break;
     case UK_ADAPT: CK(FLAVOUR(strict, launch_adaptive_switch, args, s)); break;
+    case UK_BC: CK(FLAVOUR(strict, launch_bounce_center, args, grid, s)); break;
     default: return fail(RAPT_E_ARG, "bad kernel family");
     }
     return RAPT_OK;
@@ -784,7 +787,8 @@ int rapt_b200_isadiabatic(const rapt_field_t *f, const rapt_params_t *p, int mod
 static int bounce_impl(const rapt_field_t *f, int arith, double fieldlineresolution, int64_t n,
                        const double *t, const double *x, const double *y, const double *z, const double *ppar,
                        const double *mu, const double *mass,
-                       double *Bm, double *v, double *ds, int32_t *npts, int64_t max_pts, double *curve, double *period);
+                       double *Bm, double *v, double *ds, int32_t *npts, int64_t max_pts, double *curve, double *period,
+                       int quadrature = 0);
 
 int rapt_b200_bounce_setup(const rapt_field_t *f, int arith, double fieldlineresolution, int64_t n,
                            const double *t, const double *x, const double *y, const double *z, const double *ppar,
@@ -795,7 +799,7 @@ int rapt_b200_bounce_setup(const rapt_field_t *f, int arith, double fieldlineres
     return bounce_impl(f, arith, fieldlineresolution, n, t, x, y, z, ppar, mu, mass, Bm, v, ds, npts, max_pts, curve, nullptr);
 }
 
-int rapt_b200_bounce_period(const rapt_field_t *f, int arith, double fieldlineresolution, int64_t n,
+int rapt_b200_bounce_period(const rapt_field_t *f, int arith, int quadrature, double fieldlineresolution, int64_t n,
                             const double *t, const double *x, const double *y, const double *z, const double *ppar,
                             const double *mu, const double *mass, double *period, int32_t *npts)
 {
@@ -806,7 +810,7 @@ int rapt_b200_bounce_period(const rapt_field_t *f, int arith, double fieldlinere
     int32_t *np_out = npts ? npts : np_local.data();
     for (int64_t max_pts = 128; max_pts <= 8192; max_pts *= 4) {
         int rc = bounce_impl(f, arith, fieldlineresolution, n, t, x, y, z, ppar, mu, mass, Bm.data(), v.data(), ds.data(),
-                             np_out, max_pts, nullptr, period);
+                             np_out, max_pts, nullptr, period, quadrature);
         if (rc) return rc;
         int32_t mx = 0;
         for (int64_t i = 0; i < n; i++) mx = std::max(mx, np_out[i]);
@@ -818,7 +822,8 @@ int rapt_b200_bounce_period(const rapt_field_t *f, int arith, double fieldlinere
 static int bounce_impl(const rapt_field_t *f, int arith, double fieldlineresolution, int64_t n,
                        const double *t, const double *x, const double *y, const double *z, const double *ppar,
                        const double *mu, const double *mass,
-                       double *Bm, double *v, double *ds, int32_t *npts, int64_t max_pts, double *curve, double *period)
+                       double *Bm, double *v, double *ds, int32_t *npts, int64_t max_pts, double *curve, double *period,
+                       int quadrature)
 {
     if (int rc = ensure_init()) return rc;
     if (int rc = check_field(f)) return rc;
@@ -843,12 +848,131 @@ static int bounce_impl(const rapt_field_t *f, int arith, double fieldlineresolut
     a.Bm = oBm.as<double>(); a.v = ov.as<double>(); a.ds = ods.as<double>(); a.npts = onp.as<int>();
     a.curve = ocv.as<double>(); a.scratch = scr.as<double>();
     if (period) { CK(oper.alloc(nb)); a.period = oper.as<double>(); }
+    a.quadrature = quadrature;
     if (int rc = launch_any(f, arith == 1, UK_BOUNCE, &a, n, 0, s)) return rc;
     g_launches++;
     CK(down(Bm, oBm, nb, s)); if (v) CK(down(v, ov, nb, s)); CK(down(ds, ods, nb, s)); CK(down(npts, onp, n * sizeof(int), s));
     if (curve) CK(down(curve, ocv, (size_t)n * max_pts * 5 * sizeof(double), s));
     if (period) CK(down(period, oper, nb, s));
     CK(cudaStreamSynchronize(s));
+    return RAPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BounceCenter.advance and the flutils pieces behind it (rapt_bc.cuh).  One lane per tracer up to
+// 148 SMs x 4 blocks x 64 threads; every lane owns a scratch curve of max_pts points, grown on overflow.
+// ------------------------------------------------------------------------------------------------
+static int bc_run(const rapt_field_t *f, int arith, rapt::BCArgs &a, int64_t n, int32_t *status_host, DevBuf &dstatus, cudaStream_t s)
+{
+    if (f->kind == RAPT_FIELD_GRID)
+        return fail(RAPT_E_UNSUPPORTED, "bounce centre: analytic fields only (built-in or NVRTC user fields)");
+    if (!f->is_static) return fail(RAPT_E_ARG, "BounceCenter does not work with nonstatic fields or electric fields.");
+    const long long lanes_max = (long long)g_sms * 4 * 64;
+    const long long lanes = std::min<long long>(n, lanes_max);
+    const int grid = (int)((lanes + 63) / 64);
+    (void)status_host; (void)dstatus;
+    DevBuf cv, bw;
+    CK(cv.alloc((size_t)grid * 64 * a.max_pts * 5 * sizeof(double)));
+    CK(bw.alloc((size_t)grid * 64 * a.max_pts * 4 * sizeof(double)));
+    a.curve = cv.as<double>(); a.scratch = bw.as<double>();
+    if (int rc = launch_any(f, arith == 1, UK_BC, &a, n, grid, s)) return rc;
+    g_launches++;
+    CK(cudaStreamSynchronize(s));
+    return RAPT_OK;
+}
+
+int rapt_b200_bounce_center_advance(const rapt_field_t *f, int arith, int quadrature, int64_t n,
+                                    double *t, double *x, double *y, double *z,
+                                    const double *mu, const double *v, const double *mass, const double *charge,
+                                    const double *dt_in, double bctimestep, double delta,
+                                    double rtol, double atol, double fieldlineresolution, double eyegradientstep,
+                                    int64_t store_every, int64_t max_rows, double *rows,
+                                    int32_t *nrows, int32_t *nstored, int32_t *counters, int32_t *status, double *dt_out)
+{
+    if (int rc = ensure_init()) return rc;
+    if (int rc = check_field(f)) return rc;
+    if (n < 0 || (n > 0 && (!t || !x || !y || !z || !mu || !v || !mass || !charge || !nrows || !nstored || !counters || !status)))
+        return fail(RAPT_E_ARG, "bounce_center_advance: null argument");
+    if (!(fieldlineresolution > 0) || !(eyegradientstep > 0) || !(rtol > 0) || !(atol >= 0))
+        return fail(RAPT_E_ARG, "bounce_center_advance: bad parameter");
+    if (!dt_in && !(bctimestep > 0)) return fail(RAPT_E_ARG, "bounce_center_advance: BCtimestep must be > 0");
+    if (n == 0) return RAPT_OK;
+    cudaStream_t s = 0;
+    const size_t nb = (size_t)n * sizeof(double), ni = (size_t)n * sizeof(int);
+    const bool want_rows = rows && max_rows > 0 && store_every > 0;
+    for (int64_t max_pts = 256; max_pts <= 16384; max_pts *= 4) {
+        DevBuf st[4], in[4], ddt, dodt, drows, dnr, dns, dcnt, dstat;
+        double *hs[4] = {t, x, y, z};
+        const double *hi[4] = {mu, v, mass, charge};
+        for (int k = 0; k < 4; k++) { CK(up(st[k], hs[k], nb, s)); CK(up(in[k], hi[k], nb, s)); }
+        if (dt_in) CK(up(ddt, dt_in, nb, s));
+        CK(dodt.alloc(nb)); CK(dnr.alloc(ni)); CK(dns.alloc(ni)); CK(dcnt.alloc(4 * ni)); CK(dstat.alloc(ni));
+        if (want_rows) CK(drows.alloc((size_t)n * max_rows * 4 * sizeof(double)));
+        rapt::BCArgs a;
+        memset(&a, 0, sizeof a);
+        RESOLVE(a.f, f);
+        a.op = 0; a.quadrature = quadrature; a.rtol = rtol; a.atol = atol; a.flres = fieldlineresolution;
+        a.eyestep = eyegradientstep; a.bctimestep = bctimestep; a.delta = delta;
+        a.n = n; a.max_pts = max_pts; a.store_every = want_rows ? store_every : 0; a.max_rows = want_rows ? max_rows : 0;
+        a.t = st[0].as<double>(); a.x = st[1].as<double>(); a.y = st[2].as<double>(); a.z = st[3].as<double>();
+        a.mu = in[0].as<double>(); a.v = in[1].as<double>(); a.mass = in[2].as<double>(); a.charge = in[3].as<double>();
+        a.dtin = dt_in ? ddt.as<double>() : nullptr; a.dt_out = dodt.as<double>();
+        a.rows = want_rows ? drows.as<double>() : nullptr;
+        a.nrows = dnr.as<int>(); a.nstored = dns.as<int>(); a.counters = dcnt.as<int>(); a.status = dstat.as<int>();
+        if (int rc = bc_run(f, arith, a, n, status, dstat, s)) return rc;
+        CK(down(status, dstat, ni, s));
+        CK(cudaStreamSynchronize(s));
+        bool overflow = false;
+        for (int64_t i = 0; i < n; i++) if (status[i] == RAPT_ST_ROWCAP) { overflow = true; break; }
+        if (overflow && max_pts < 16384) continue;          // a field line needed more points: rerun with larger scratch
+        for (int k = 0; k < 4; k++) CK(down(hs[k], st[k], nb, s));
+        CK(down(nrows, dnr, ni, s)); CK(down(nstored, dns, ni, s)); CK(down(counters, dcnt, 4 * ni, s));
+        if (dt_out) CK(down(dt_out, dodt, nb, s));
+        if (want_rows) CK(down(rows, drows, (size_t)n * max_rows * 4 * sizeof(double), s));
+        CK(cudaStreamSynchronize(s));
+        return RAPT_OK;
+    }
+    return RAPT_OK;
+}
+
+int rapt_b200_bounce_center_terms(const rapt_field_t *f, int arith, int quadrature, int64_t n,
+                                  const double *t, const double *x, const double *y, const double *z, const double *Bm,
+                                  const double *v, const double *mass, const double *charge,
+                                  double fieldlineresolution, double eyegradientstep, double *out, int32_t *status)
+{
+    if (int rc = ensure_init()) return rc;
+    if (int rc = check_field(f)) return rc;
+    if (n < 0 || (n > 0 && (!t || !x || !y || !z || !Bm || !out || !status)))
+        return fail(RAPT_E_ARG, "bounce_center_terms: null argument");
+    if (!(fieldlineresolution > 0) || !(eyegradientstep > 0)) return fail(RAPT_E_ARG, "bounce_center_terms: bad parameter");
+    if (n == 0) return RAPT_OK;
+    cudaStream_t s = 0;
+    const size_t nb = (size_t)n * sizeof(double), ni = (size_t)n * sizeof(int);
+    std::vector<double> nanv;
+    if (!v || !mass || !charge) nanv.assign((size_t)n, std::nan(""));
+    for (int64_t max_pts = 256; max_pts <= 16384; max_pts *= 4) {
+        DevBuf in[8], dout, dstat;
+        const double *hi[8] = {t, x, y, z, Bm, v ? v : nanv.data(), mass ? mass : nanv.data(), charge ? charge : nanv.data()};
+        for (int k = 0; k < 8; k++) CK(up(in[k], hi[k], nb, s));
+        CK(dout.alloc(8 * nb)); CK(dstat.alloc(ni));
+        rapt::BCArgs a;
+        memset(&a, 0, sizeof a);
+        RESOLVE(a.f, f);
+        a.op = 1; a.quadrature = quadrature; a.flres = fieldlineresolution; a.eyestep = eyegradientstep;
+        a.n = n; a.max_pts = max_pts;
+        a.t = in[0].as<double>(); a.x = in[1].as<double>(); a.y = in[2].as<double>(); a.z = in[3].as<double>();
+        a.Bm = in[4].as<double>(); a.v = in[5].as<double>(); a.mass = in[6].as<double>(); a.charge = in[7].as<double>();
+        a.out = dout.as<double>(); a.status = dstat.as<int>();
+        if (int rc = bc_run(f, arith, a, n, status, dstat, s)) return rc;
+        CK(down(status, dstat, ni, s));
+        CK(cudaStreamSynchronize(s));
+        bool overflow = false;
+        for (int64_t i = 0; i < n; i++) if (status[i] == RAPT_ST_ROWCAP) { overflow = true; break; }
+        if (overflow && max_pts < 16384) continue;
+        CK(down(out, dout, 8 * nb, s));
+        CK(cudaStreamSynchronize(s));
+        return RAPT_OK;
+    }
     return RAPT_OK;
 }
 

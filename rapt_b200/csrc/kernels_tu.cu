@@ -1,5 +1,5 @@
 // kernels_tu.cu -- one translation unit per (arithmetic flavour, kernel family); see Makefile.
-//   -DRAPT_STRICT=0|1 -DRAPT_NS=rapt_fast|rapt_strict -DRAPT_TU_PARTICLE | -DRAPT_TU_GC | -DRAPT_TU_AUX
+//   -DRAPT_STRICT=0|1 -DRAPT_NS=rapt_fast|rapt_strict -DRAPT_TU_PARTICLE | -DRAPT_TU_GC | -DRAPT_TU_AUX | -DRAPT_TU_BC
 #include <cuda_runtime.h>
 #include <cstdlib>
 #include "rapt_launch.h"
@@ -173,6 +173,24 @@ cudaError_t launch_bounce(const void *args, cudaStream_t s)
 #define CALL(K) k_bounce_setup<Field<K>><<<grid, 128, 0, s>>>(a)
     RAPT_KIND_SWITCH(CALL)
 #undef CALL
+    return cudaGetLastError();
+}
+}  // namespace RAPT_NS
+#endif
+
+#ifdef RAPT_TU_BC
+#include "rapt_bc.cuh"
+namespace RAPT_NS {
+cudaError_t launch_bounce_center(const void *args, int grid, cudaStream_t s)
+{
+    const BCArgs &a = *static_cast<const BCArgs *>(args);
+    const int kind = a.f.kind;
+    switch (kind) {
+#define CALL(K) case K: k_bounce_center<Field<K>><<<grid, 64, 0, s>>>(a); break
+    CALL(0); CALL(1); CALL(2); CALL(3); CALL(4); CALL(5);
+#undef CALL
+    default: return cudaErrorInvalidValue;      // gridded fields: not offered (per-lane cell cache + curve scratch)
+    }
     return cudaGetLastError();
 }
 }  // namespace RAPT_NS

@@ -7,6 +7,7 @@
 #include "rapt_fields.cuh"
 #include "rapt_particle.cuh"
 #include "rapt_gc.cuh"
+#include "rapt_quad.cuh"
 
 namespace RAPT_NS {
 using rapt::OpsArgs;
@@ -266,122 +267,54 @@ RAPT_DEV long long rkf_chunk(const FieldP &f, double time, double sign, const do
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// flutils.halfbouncepath (flutils.py:274-316) on the device.  Trimming and the equatorial 3-point
-// formula are the reference's.  For the general case the reference builds scipy's quadratic
-// interpolating spline B(s) (make_interp_spline k=2: knots at the interior midpoints, tridiagonal
-// collocation), finds the two mirror points with brentq and integrates 1/sqrt(1 - B(s)/Bm) with
-// QUADPACK (epsrel 1e-4).  Here the SAME spline is built (agrees with scipy to 4e-16) but, B being a
-// quadratic on every knot span, both the mirror points and the integral are taken in closed form
-// (asin / log primitives): no quadrature error.  It differs from the reference's value only by
-// QUADPACK's own error (epsrel 1e-4 requested; 1e-7 typical, up to 2e-5 observed, tests/test_gpu_gc.py).
-// Returns NaN when the trace does not bracket both mirror points.
-// ------------------------------------------------------------------------------------------------
-struct SplineView {
-    const double *cv;     // curve rows (stride 5): s at [0], |B| at [4]
-    double *w;            // work rows (stride 4): [0] spline coefficient c, [1], [2] Thomas scratch
-    long long i1;         // first kept point
-    int m;                // number of kept points
-    RAPT_DEV double s(int j) const { return cv[5 * (i1 + j)]; }
-    RAPT_DEV double b(int j) const { return cv[5 * (i1 + j) + 4]; }
-    // knot vector of make_interp_spline(k=2): s0 x3, interior midpoints (without first and last), s_{m-1} x3
-    RAPT_DEV double knot(int k) const
-    {
-        if (k <= 2) return s(0);
-        if (k >= m) return s(m - 1);
-        return 0.5 * (s(k - 2) + s(k - 1));
-    }
-    RAPT_DEV double &c(int j) const { return w[4 * j]; }
-    // the three non-zero quadratic B-splines of span l = p + 2 at x (columns p, p+1, p+2)
-    RAPT_DEV void basis(int p, double x, double &nlo, double &nmid, double &nhi) const
-    {
-        const int l = p + 2;
-        const double tl1 = knot(l - 1), tl = knot(l), tr = knot(l + 1), tr2 = knot(l + 2);
-        nlo = (tr - x) * (tr - x) / ((tr - tl1) * (tr - tl));
-        nhi = (x - tl) * (x - tl) / ((tr2 - tl) * (tr - tl));
-        nmid = 1 - nlo - nhi;
-    }
-    RAPT_DEV double eval(int p, double x) const
-    {
-        double a, bm, h; basis(p, x, a, bm, h);
-        return a * c(p) + bm * c(p + 1) + h * c(p + 2);
-    }
-};
-
-// primitive of 1/sqrt(al + be u + ga u^2)
-RAPT_DEV double invsqrt_quadratic_primitive(double al, double be, double ga, double u)
+// Fieldline(tpos, field, Bmax=Bm).trace() + getB() (fieldline.py:13-105, 123-127) for one thread: the curve
+// (s, x, y, z, |B|) goes to cv (stride 5, room for cap points); bw is scratch for the backward half (stride 4,
+// cap points).  Returns the number of points, or cap + 1 when the line does not fit.
+template <class F>
+RAPT_DEV long long fieldline_trace(const FieldP &f, double t, double x, double y, double z, double Bm, double flres,
+                                   double *cv, double *bw, long long cap, double &ds_out)
 {
-    const double q = fmax(al + be * u + ga * u * u, 0.0);
-    if (ga == 0) return 2 * sqrt(q) / be;
-    const double disc = be * be - 4 * al * ga;
-    if (ga < 0) return -asin(fmax(-1.0, fmin(1.0, (2 * ga * u + be) / sqrt(disc)))) / sqrt(-ga);
-    return log(fabs(2 * ga * u + be + 2 * sqrt(ga) * sqrt(q))) / sqrt(ga);
-}
-
-RAPT_DEV double halfbouncepath_device(const double *cv, double *work, long long n, double Bm)
-{
-    long long first = -1, last = -1;
-    for (long long k = 0; k < n; k++) if (cv[5 * k + 4] <= Bm) { if (first < 0) first = k; last = k; }
-    long long i1, i2;
-    if (first < 0) { i1 = (n - 3) / 2; i2 = (n + 1) / 2; }          // flutils.py:281-283
-    else { i1 = first - 1; i2 = last + 1; }
-    if (i1 < 0 || i2 > n - 1) return nan("");
-    const int m = (int)(i2 - i1 + 1);
-    if (m < 3) return nan("");
-    if (m == 3) {                                                    // flutils.py:295-305
-        const double s1 = cv[5 * i1], s2 = cv[5 * (i1 + 1)], s3 = cv[5 * (i1 + 2)];
-        const double B1 = cv[5 * i1 + 4], B2 = cv[5 * (i1 + 1) + 4], B3 = cv[5 * (i1 + 2) + 4];
-        const double s12 = s1 - s2, s23 = s2 - s3, s13 = s1 - s3;
-        const double B2s = 2 * (B1 * s23 - B2 * s13 + B3 * s12) / (s12 * s13 * s23);
-        return RAPT_PI * sqrt(2 * Bm / B2s);
-    }
-    SplineView sp = {cv, work, i1, m};
-    // tridiagonal collocation system (row j: columns j-1, j, j+1), Thomas algorithm
-    sp.w[1] = 0.0; sp.w[2] = sp.b(0);                                // row 0: c_0 = b_0
-    for (int j = 1; j <= m - 2; j++) {
-        double lo, mid, hi; sp.basis(j - 1, sp.s(j), lo, mid, hi);
-        const double den = mid - lo * sp.w[4 * (j - 1) + 1];
-        sp.w[4 * j + 1] = hi / den;
-        sp.w[4 * j + 2] = (sp.b(j) - lo * sp.w[4 * (j - 1) + 2]) / den;
-    }
-    sp.c(m - 1) = sp.b(m - 1);                                       // last row: c_{m-1} = b_{m-1}
-    for (int j = m - 2; j >= 0; j--) sp.c(j) = sp.w[4 * j + 2] - sp.w[4 * j + 1] * sp.c(j + 1);
-    // mirror points: B(s) = Bm in [s_0, s_1] and in [s_{m-2}, s_{m-1}]  (flutils.py:311-313)
-    double sm[2] = {nan(""), nan("")};
-    for (int side = 0; side < 2; side++) {
-        const double lo = side ? sp.s(m - 2) : sp.s(0), hi = side ? sp.s(m - 1) : sp.s(1);
-        for (int p = 0; p <= m - 3; p++) {
-            const double sl = sp.knot(p + 2), sr = sp.knot(p + 3);
-            const double L = fmax(sl, lo), R = fmin(sr, hi);
-            if (!(L < R)) continue;
-            const double hh = sr - sl, f0 = sp.eval(p, sl), f1 = sp.eval(p, 0.5 * (sl + sr)), f2 = sp.eval(p, sr);
-            const double cc = 2 * (f2 - 2 * f1 + f0) / (hh * hh), bb = (f2 - f0) / hh - cc * hh, aa = f0 - Bm;
-            double r0, r1;
-            if (cc == 0) { r0 = r1 = -aa / bb; }
-            else {
-                const double d = bb * bb - 4 * cc * aa;
-                if (d < 0) continue;
-                const double qq = -0.5 * (bb + copysign(sqrt(d), bb));
-                r0 = qq / cc; r1 = (qq != 0) ? aa / qq : nan("");
-            }
-            const double eps = 1e-9 * hh;
-            if (r0 >= L - sl - eps && r0 <= R - sl + eps) { sm[side] = sl + r0; break; }
-            if (r1 >= L - sl - eps && r1 <= R - sl + eps) { sm[side] = sl + r1; break; }
+    const double ds = 1 / F::curvature(f, t, x, y, z) / flres;          // fieldline.py:31-35
+    ds_out = ds;
+    double *fw = cv;                                   // forward half staged in the output buffer (stride 4)
+    long long nf = 1, nb = 1;
+    fw[0] = 0; fw[1] = x; fw[2] = y; fw[3] = z;
+    bw[0] = 0; bw[1] = x; bw[2] = y; bw[3] = z;
+    for (int dir = 0; dir < 2; dir++) {
+        double *arr = dir ? bw : fw;
+        long long np_ = 1;
+        const double sign = dir ? -1.0 : 1.0, tol = dir ? 1e-4 : 1e-3;
+        double cur[4] = {0, x, y, z}, nxt[4];
+        for (;;) {
+            if (np_ >= cap) { np_ = cap + 1; break; }
+            long long m = rkf_chunk<F>(f, t, sign, cur, ds, tol, ds, 1e-6, arr + 4 * np_, cap - np_, nxt);
+            if (m < 0) break;
+            if (np_ + m > cap) { np_ = cap + 1; break; }
+            np_ += m;
+#pragma unroll
+            for (int k = 0; k < 4; k++) cur[k] = nxt[k];
+            if (!(F::magB(f, t, cur[1], cur[2], cur[3]) <= Bm)) break;      // |B| > Bm, or NaN outside a grid
         }
+        if (dir) nb = np_; else nf = np_;
     }
-    if (!(sm[0] == sm[0]) || !(sm[1] == sm[1])) return nan("");
-    // S_b = integral_{sm1}^{sm2} ds / sqrt(1 - B(s)/Bm), span by span in closed form
-    double tot = 0;
-    for (int p = 0; p <= m - 3; p++) {
-        const double sl = sp.knot(p + 2), sr = sp.knot(p + 3);
-        const double L = fmax(sl, sm[0]), R = fmin(sr, sm[1]);
-        if (!(L < R)) continue;
-        const double hh = sr - sl, f0 = sp.eval(p, sl), f1 = sp.eval(p, 0.5 * (sl + sr)), f2 = sp.eval(p, sr);
-        const double cc = 2 * (f2 - 2 * f1 + f0) / (hh * hh), bb = (f2 - f0) / hh - cc * hh;
-        const double al = 1 - f0 / Bm, be = -bb / Bm, ga = -cc / Bm;
-        tot += invsqrt_quadratic_primitive(al, be, ga, R - sl) - invsqrt_quadratic_primitive(al, be, ga, L - sl);
+    if (nf > cap || nb > cap || (nb - 1) + nf > cap) return cap + 1;
+    const long long n = (nb - 1) + nf;
+    // assemble curve = reversed(backward[1:]) + forward, in place: move the forward half up first
+    for (long long k = nf - 1; k >= 0; k--) {
+        double s = fw[4 * k], px = fw[4 * k + 1], py = fw[4 * k + 2], pz = fw[4 * k + 3];
+        double *o = cv + 5 * ((nb - 1) + k);
+        o[0] = s; o[1] = px; o[2] = py; o[3] = pz;
     }
-    return tot;
+    for (long long k = 0; k < nb - 1; k++) {
+        const double *q = bw + 4 * (nb - 1 - k);
+        double *o = cv + 5 * k;
+        o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3];
+    }
+    for (long long k = 0; k < n; k++) {
+        double *o = cv + 5 * k;
+        o[4] = F::magB(f, t, o[1], o[2], o[3]);        // Fieldline.getB, fieldline.py:123-127
+    }
+    return n;
 }
 
 template <class F>
@@ -406,53 +339,17 @@ __global__ void __launch_bounds__(128) k_bounce_setup(const BounceArgs a)
             v = p / mass / gamma;
         }
     } else Bm = a.Bm[i];                                     // Fieldline(tpos, field, Bmax=Bm)
-    const double ds = 1 / F::curvature(a.f, t, x, y, z) / a.flres;      // fieldline.py:31-35
-    a.Bm[i] = Bm; a.v[i] = v; a.ds[i] = ds;
-
     const long long cap = a.max_pts;
-    double *fw = a.curve + (size_t)i * cap * 5;       // forward half staged in the output buffer (stride 4)
-    double *bw = a.scratch + (size_t)i * cap * 4;
-    long long nf = 1, nb = 1;
-    fw[0] = 0; fw[1] = x; fw[2] = y; fw[3] = z;
-    bw[0] = 0; bw[1] = x; bw[2] = y; bw[3] = z;
-    for (int dir = 0; dir < 2; dir++) {
-        double *arr = dir ? bw : fw;
-        long long np_ = 1;
-        const double sign = dir ? -1.0 : 1.0, tol = dir ? 1e-4 : 1e-3;
-        double cur[4] = {0, x, y, z}, nxt[4];
-        for (;;) {
-            if (np_ >= cap) { np_ = cap + 1; break; }
-            long long m = rkf_chunk<F>(a.f, t, sign, cur, ds, tol, ds, 1e-6, arr + 4 * np_, cap - np_, nxt);
-            if (m < 0) break;
-            if (np_ + m > cap) { np_ = cap + 1; break; }
-            np_ += m;
-#pragma unroll
-            for (int k = 0; k < 4; k++) cur[k] = nxt[k];
-            if (F::magB(a.f, t, cur[1], cur[2], cur[3]) > Bm) break;
-        }
-        if (dir) nb = np_; else nf = np_;
-    }
-    if (nf > cap || nb > cap || (nb - 1) + nf > cap) { a.npts[i] = (int)(cap + 1); if (a.period) a.period[i] = nan(""); return; }
-    const long long n = (nb - 1) + nf;
-    // assemble curve = reversed(backward[1:]) + forward, in place: move the forward half up first
     double *cv = a.curve + (size_t)i * cap * 5;
-    for (long long k = nf - 1; k >= 0; k--) {
-        double s = fw[4 * k], px = fw[4 * k + 1], py = fw[4 * k + 2], pz = fw[4 * k + 3];
-        double *o = cv + 5 * ((nb - 1) + k);
-        o[0] = s; o[1] = px; o[2] = py; o[3] = pz;
-    }
-    for (long long k = 0; k < nb - 1; k++) {
-        const double *q = bw + 4 * (nb - 1 - k);
-        double *o = cv + 5 * k;
-        o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3];
-    }
-    for (long long k = 0; k < n; k++) {
-        double *o = cv + 5 * k;
-        o[4] = F::magB(a.f, t, o[1], o[2], o[3]);        // Fieldline.getB, fieldline.py:123-127
-    }
+    double *bw = a.scratch + (size_t)i * cap * 4;
+    double ds;
+    const long long n = fieldline_trace<F>(a.f, t, x, y, z, Bm, a.flres, cv, bw, cap, ds);
+    a.Bm[i] = Bm; a.v[i] = v; a.ds[i] = ds;
     a.npts[i] = (int)n;
-    // flutils.bounceperiod (flutils.py:252): tau_b = (2/v) S_b
-    if (a.period) a.period[i] = (2 / v) * halfbouncepath_device(cv, bw, n, Bm);
+    if (n > cap) { if (a.period) a.period[i] = nan(""); return; }
+    // flutils.bounceperiod (flutils.py:252): tau_b = (2/v) S_b.  quadrature 1: brentq + QUADPACK as the reference;
+    // 0: mirror points and integral in closed form on the same spline (rapt_quad.cuh)
+    if (a.period) a.period[i] = (2 / v) * halfbouncepath_curve(cv, bw, n, Bm, a.quadrature);
 }
 
 

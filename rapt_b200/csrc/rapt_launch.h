@@ -14,6 +14,7 @@
     cudaError_t launch_misc(const void *args, cudaStream_t s);                            \
     cudaError_t launch_bounce(const void *args, cudaStream_t s);                          \
     cudaError_t launch_adaptive_switch(const void *args, cudaStream_t s);                 \
+    cudaError_t launch_bounce_center(const void *args, int grid, cudaStream_t s);         \
     }
 RAPT_DECLARE_FLAVOUR(rapt_fast)
 RAPT_DECLARE_FLAVOUR(rapt_strict)

@@ -15,8 +15,10 @@
 //
 // A curve is rows of stride 5: s at [0], x,y,z at [1..3], |B| at [4] (k_bounce_setup's layout).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <math.h>
 #include <float.h>
+#endif
 
 #ifndef RAPT_NS
 #define RAPT_NS rapt_fast

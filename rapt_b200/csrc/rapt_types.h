@@ -91,7 +91,26 @@ struct BounceArgs {
     int *npts;
     double *curve;            // [n][max_pts][5] : s, x, y, z, |B|
     double *scratch;          // [n][max_pts][4] : backward half before reversal; then spline work arrays
-    double *period;           // optional: bounce period by closed-form quadrature of the quadratic spline
+    double *period;           // optional: bounce period (flutils.bounceperiod) from the traced curve
+    int quadrature;           // 0: closed form on the quadratic spline, 1: brentq + QUADPACK QAGS as the reference
+};
+
+// BounceCenter.advance (rapt/BounceCenter.py:206-251) and its pieces (flutils.halfbouncepath / eye / gradI)
+struct BCArgs {
+    FieldP f;
+    int op;                   // 0: advance; 1: out[i] = (S_b, I, gradI[3], deriv[3]) at the given points
+    int quadrature;           // halfbouncepath: 1 brentq + QAGS as the reference, 0 closed form
+    double rtol, atol, flres, eyestep, bctimestep, delta;
+    long long n, max_pts, store_every, max_rows;
+    double *t, *x, *y, *z;    // last row, in/out (t = row label, BounceCenter.py:248-250)
+    const double *mu, *Bm;    // mirror field from mu (BounceCenter.py:227) unless Bm is given
+    const double *v, *mass, *charge;
+    const double *dtin;       // output step per tracer, or NULL: BCtimestep * bounce period
+    double *dt_out, *tsolver; // optional
+    double *rows;             // [n][max_rows][4] or NULL
+    int *nrows, *nstored, *counters, *status;
+    double *out;              // op 1: [n][8]
+    double *curve, *scratch;  // per LANE: [lanes][max_pts][5], [lanes][max_pts][4]
 };
 
 // Adaptive: per-tracer state of both modes + the epoch bookkeeping (rapt/Adaptive.py:70-104, 187-222)

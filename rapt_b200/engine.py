@@ -313,11 +313,16 @@ def bounceperiod(field, state, mu, mass, fieldlineresolution=None, arith="strict
     return out
 
 
-def bounceperiod_device(field, state, mu, mass, fieldlineresolution=None, arith="strict"):
+QUADRATURE = {"closed": 0, "quadpack": 1, 0: 0, 1: 1}
+
+
+def bounceperiod_device(field, state, mu, mass, fieldlineresolution=None, arith="strict", quadrature="quadpack"):
     """GuidingCenter.bounceperiod for n guiding centres entirely on the device: field-line trace + scipy's
-    quadratic spline rebuilt per thread + closed-form mirror points and integral (no host loop).  Equals the
-    reference's value up to the error of its QUADPACK call (epsrel 1e-4 requested; 1e-7 typical, 2e-5 worst seen); use `bounceperiod` for the
-    reference's exact host quadrature."""
+    quadratic spline rebuilt per thread, then
+      quadrature="quadpack": brentq + QUADPACK QAGS restated per thread (flutils.py:308-314 as the reference runs
+                             them; the reference's value to ~1e-9),
+      quadrature="closed":   mirror points and integral in closed form (no quadrature error: differs from the
+                             reference by its own QUADPACK error, 1e-7 typical, 2e-5 worst seen)."""
     from . import params as gp
     f = _field_desc(field)
     st = np.asarray(state, dtype=np.float64).reshape(-1, 5)
@@ -326,9 +331,58 @@ def bounceperiod_device(field, state, mu, mass, fieldlineresolution=None, arith=
     cols = [np.ascontiguousarray(st[:, i]).copy() for i in range(5)]
     mu, mass = _col(mu, n), _col(mass, n)
     period = np.zeros(n)
-    check(_lib.load().rapt_b200_bounce_period(C.byref(f), C.c_int(1 if arith in ("strict", 1) else 0), C.c_double(flr),
+    check(_lib.load().rapt_b200_bounce_period(C.byref(f), C.c_int(1 if arith in ("strict", 1) else 0),
+                                              C.c_int(QUADRATURE[quadrature]), C.c_double(flr),
                                               C.c_int64(n), *[ptr(c_) for c_ in cols], ptr(mu), ptr(mass), ptr(period), None))
     return period
+
+
+def bounce_center_advance(field, state, mu, v, mass, charge, delta, dt=None, store_every=1, max_rows=0, params=None,
+                          arith="strict", quadrature="quadpack"):
+    """BounceCenter.advance (rapt/BounceCenter.py:206-251) for n bounce centres; state (n,4) = t, x, y, z of the
+    last rows.  dt None: BCtimestep * bounce period per tracer, computed on the device.  Returns a dict with the
+    new last rows, stored rows (n, max_rows, 4), nrows, nstored, counters (n,4), status, dt."""
+    from . import params as gp
+    src = dict(gp if params is None else params)
+    f = _field_desc(field)
+    st = np.asarray(state, dtype=np.float64).reshape(-1, 4)
+    n = len(st)
+    cols = [np.ascontiguousarray(st[:, i]).copy() for i in range(4)]
+    mu, v, mass, charge = _col(mu, n), _col(v, n), _col(mass, n), _col(charge, n)
+    dtin = None if dt is None else _col(dt, n)
+    want = store_every > 0 and max_rows > 0
+    rows = np.zeros((n, max_rows, 4)) if want else None
+    nrows = np.zeros(n, np.int32); nstored = np.zeros(n, np.int32); counters = np.zeros((n, 4), np.int32)
+    status = np.zeros(n, np.int32); dt_out = np.zeros(n)
+    rtol, atol = src["solvertolerances"]
+    check(_lib.load().rapt_b200_bounce_center_advance(
+        C.byref(f), C.c_int(1 if arith in ("strict", 1) else 0), C.c_int(QUADRATURE[quadrature]), C.c_int64(n),
+        *[ptr(c_) for c_ in cols], ptr(mu), ptr(v), ptr(mass), ptr(charge), ptr(dtin),
+        C.c_double(float(src["BCtimestep"])), C.c_double(float(delta)), C.c_double(float(rtol)), C.c_double(float(atol)),
+        C.c_double(float(src["fieldlineresolution"])), C.c_double(float(src["eyegradientstep"])),
+        C.c_int64(store_every if want else 0), C.c_int64(max_rows if want else 0), ptr(rows),
+        ptr(nrows), ptr(nstored), ptr(counters), ptr(status), ptr(dt_out)))
+    return dict(state=np.column_stack(cols), rows=rows, nrows=nrows, nstored=nstored, counters=counters, status=status,
+                dt=dt_out)
+
+
+def bounce_center_terms(field, tpos, Bm, v=None, mass=None, charge=None, params=None, arith="strict", quadrature="quadpack"):
+    """flutils.halfbouncepath / eye / gradI (rapt/flutils.py:65-316) and BounceCenter.advance's right-hand side at n
+    points tpos (n,4) with mirror fields Bm: dict of Sb (n,), I (n,), gradI (n,3), deriv (n,3), status."""
+    from . import params as gp
+    src = dict(gp if params is None else params)
+    f = _field_desc(field)
+    tp = np.asarray(tpos, dtype=np.float64).reshape(-1, 4)
+    n = len(tp)
+    cols = [np.ascontiguousarray(tp[:, i]).copy() for i in range(4)]
+    Bm = _col(Bm, n)
+    opt = [None if a is None else _col(a, n) for a in (v, mass, charge)]
+    out = np.zeros((n, 8)); status = np.zeros(n, np.int32)
+    check(_lib.load().rapt_b200_bounce_center_terms(
+        C.byref(f), C.c_int(1 if arith in ("strict", 1) else 0), C.c_int(QUADRATURE[quadrature]), C.c_int64(n),
+        *[ptr(c_) for c_ in cols], ptr(Bm), *[ptr(a) for a in opt],
+        C.c_double(float(src["fieldlineresolution"])), C.c_double(float(src["eyegradientstep"])), ptr(out), ptr(status)))
+    return dict(Sb=out[:, 0], I=out[:, 1], gradI=out[:, 2:5], deriv=out[:, 5:8], status=status)
 
 
 def switch_p2g(field, prow, mass, charge, arith="strict"):

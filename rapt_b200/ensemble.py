@@ -147,16 +147,17 @@ class GuidingCenterEnsemble:
 
     HOST_QUADRATURE_MAX = 4096
 
-    def bounceperiod(self, method=None):
-        """GuidingCenter.bounceperiod of every member.  method "scipy": device field-line traces + the
-        reference's scipy quadrature in a host loop (the reference's exact value, ~5 ms per member);
-        "closed-form": everything on the device (within the error of the reference's QUADPACK call: 1e-7 typical, 2e-5 worst seen).  Default:
-        scipy up to HOST_QUADRATURE_MAX members, closed-form above."""
-        if method is None:
-            method = "scipy" if self.n <= self.HOST_QUADRATURE_MAX else "closed-form"
+    def bounceperiod(self, method="quadpack"):
+        """GuidingCenter.bounceperiod of every member (rapt/GuidingCenter.py:593-606).
+        "quadpack" (default): all on the device -- field-line trace, scipy's spline, brentq and QUADPACK QAGS
+            restated per thread: the reference's value to ~1e-9;
+        "closed-form": all on the device, mirror points and integral in closed form (within the error of the
+            reference's QUADPACK call: 1e-7 typical, 2e-5 worst seen);
+        "scipy": device traces + scipy's own interp1d/brentq/quad in a host loop (~5 ms per member; kept as a cross-check)."""
         if method == "scipy":
             return engine.bounceperiod(self.field, self.state, self.mu, self.mass, params["fieldlineresolution"])
-        return engine.bounceperiod_device(self.field, self.state, self.mu, self.mass, params["fieldlineresolution"])
+        return engine.bounceperiod_device(self.field, self.state, self.mu, self.mass, params["fieldlineresolution"],
+                                          quadrature="closed" if method == "closed-form" else "quadpack")
 
     def _dt(self):
         if params["GCtimestep"] != 0:                                # GuidingCenter.py:443-446
@@ -213,6 +214,45 @@ class GuidingCenterEnsemble:
         mc = self.mass * c
         g = np.sqrt(1 + 2 * self.mu * Bm / (mc * c) + (self.state[:, 4] / mc) ** 2)
         return np.where(g - 1 < 1e-6, self.mu * Bm + 0.5 * self.state[:, 4] ** 2 / self.mass, (g - 1) * mc * c)
+
+
+class BounceCenterEnsemble:
+    """n bounce centres: BounceCenter(pos, v, t0, pa, mass, charge, field) with array arguments
+    (rapt/BounceCenter.py:74-115).  `state` is (n,4): t (row label), x, y, z.  As in the reference the magnetic moment
+    uses cos(pa) of the pitch angle as given (BounceCenter.py:114)."""
+
+    def __init__(self, pos, v, t0=0.0, pa=None, mass=None, charge=None, field=None):
+        if not field.static:
+            raise RuntimeError("BounceCenter does not work with nonstatic fields or electric fields.")
+        pos = np.asarray(pos, dtype=np.float64).reshape(-1, 3)
+        n = len(pos)
+        self.n = n
+        self.v = _arr(v, n); self.mass = _arr(mass, n); self.charge = _arr(charge, n); self.pa = _arr(pa, n)
+        self.field = field
+        t0 = _arr(t0, n)
+        g = 1 / np.sqrt(1 - (self.v / c) ** 2)
+        Bmag = engine.field_ops(field, np.column_stack([t0, pos]), which=["magB"])["magB"]
+        vpar = self.v * np.cos(self.pa)
+        self.mu = g ** 2 * self.mass * (self.v - vpar) * (self.v + vpar) / (2 * Bmag)       # utils.py:214-216
+        self.state = np.column_stack([t0, pos])
+        self.tcur = t0.copy()
+        self.counters = np.zeros((n, 4), dtype=np.int64)
+        self.status = np.ones(n, dtype=np.int32)
+        self.trajectory = None; self.nstored = None; self.nrows = None; self.dt = None
+
+    def advance(self, delta, store_every=0, max_rows=0, dt=None, **over):
+        """BounceCenter.advance(delta) for every member (rapt/BounceCenter.py:206-251)."""
+        o = engine.bounce_center_advance(self.field, self.state, self.mu, self.v, self.mass, self.charge, float(delta), dt=dt,
+                                         store_every=store_every, max_rows=max_rows, **over)
+        self.state = o["state"]; self.tcur = o["state"][:, 0].copy(); self.status = o["status"]
+        self.last_counters = o["counters"].astype(np.int64)
+        self.counters += self.last_counters
+        self.nrows = o["nrows"].astype(np.int64); self.dt = o["dt"]
+        self.trajectory = o["rows"]; self.nstored = o["nstored"]
+        return self
+
+    def member_trajectory(self, i):
+        return self.trajectory[i, :self.nstored[i], :4]
 
 
 class AdaptiveEnsemble:

@@ -1,0 +1,203 @@
+"""GPU parity: BounceCenter.advance (rapt/BounceCenter.py:206-251) and the field-line integrals behind it
+(rapt/flutils.py:65-316) on the B200 vs golden vectors from the unmodified reference and vs the CPU oracle.
+
+Tolerances.  The device restates the reference's whole route (RKF45 trace, scipy's spline, brentq, QUADPACK QAGS,
+dopri5); differences are round-off only, amplified where the reference's own value is ill-conditioned:
+  * the trace step ds = 1/(50 curvature) is a finite difference over 6.4 m (EarthDipole.gradientstepsize): CUDA's
+    pow() vs glibc's moves it by ~1e-9, and every sample point of the curve with it;
+  * I (second invariant) and S_b therefore agree to ~1e-8 (asserted 1e-7); S_b also samples 1/sqrt(1 - B/Bm) within
+    1e-10 of its singularities;
+  * gradI is a central difference of two I values over 2 x 0.03 Re: |I| / |I1 - I2| ~ 50 times the noise of I (1e-5);
+  * positions: <= 1e-8 relative (north_star's tolerance), solver counters equal.
+The measured values are printed (pytest -rA shows them).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+BC_CASES = ("bc_dipole_electron", "bc_dipole_proton", "bc_doubledipole_electron")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from rapt_b200 import engine, _lib
+    _lib.init(0)
+    return engine
+
+
+def _gold(name):
+    return np.load(os.path.join(H.GOLDEN, name + ".npz"))
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+@pytest.mark.parametrize("name", BC_CASES)
+def test_flutils_terms_vs_reference(eng, name, arith):
+    d = _gold(name)
+    f = H.gpu_field(str(d["field"]), ())
+    r = eng.bounce_center_terms(f, d["pts"], float(d["Bm"]), v=float(d["v"]), mass=float(d["mass"]), charge=float(d["charge"]),
+                                arith=arith)
+    assert np.all(r["status"] == 1)
+    print(name, arith, "Sb", H.relerr(r["Sb"], d["Sb"]), "I", H.relerr(r["I"], d["I"]), "gradI", H.vec_relerr(r["gradI"], d["gradI"]))
+    assert H.relerr(r["Sb"], d["Sb"]) < 1e-7
+    assert H.relerr(r["I"], d["I"]) < 1e-7
+    assert H.vec_relerr(r["gradI"], d["gradI"]) < 1e-5
+    # the right-hand side itself against the oracle's (reference formula on the reference's pieces)
+    import oracle as O
+    of = O.make_field(str(d["field"]))
+    Bm, gamma = O.bc_mirror_field(float(d["mu"]), float(d["v"]), float(d["mass"]))
+    assert Bm == float(d["Bm"])
+    ref = O.bc_deriv(of, d["pts"][0, 0], d["pts"][0, 1:], Bm, gamma, float(d["v"]), float(d["mass"]), float(d["charge"]))
+    print(name, arith, "deriv", H.vec_relerr(r["deriv"][:1], ref[None]))
+    assert H.vec_relerr(r["deriv"][:1], ref[None]) < 1e-5
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_flutils_special_branches(eng, arith):
+    """One-sided differences in gradI (flutils.py:212-215) and the Simpson branch of eye (eqpa < 70)."""
+    d = _gold("bc_flutils")
+    f = H.gpu_field("EarthDipole", ())
+    r = eng.bounce_center_terms(f, d["tpos"], d["Bm"], arith=arith)
+    assert np.all(r["status"] == 1)
+    print(arith, "Sb", np.abs(r["Sb"] / d["Sb"] - 1), "I", np.abs(r["I"] / d["I"] - 1),
+          "gradI", np.linalg.norm(r["gradI"] - d["gradI"], axis=1) / np.linalg.norm(d["gradI"], axis=1))
+    assert H.relerr(r["Sb"], d["Sb"]) < 1e-7
+    assert H.relerr(r["I"], d["I"]) < 1e-7
+    assert H.vec_relerr(r["gradI"], d["gradI"]) < 1e-5
+    assert np.all(np.isnan(r["deriv"]))              # v, mass, charge not given
+
+
+def test_flutils_module_matches_reference_call_shapes(eng):
+    """rapt.eye / gradI / halfbouncepath (rapt/__init__.py:42): scalar and 3-vector returns for one tpos."""
+    import rapt_b200 as rb
+    d = _gold("bc_flutils")
+    f = rb.fields.EarthDipole()
+    tp, Bm = d["tpos"][2], float(d["Bm"][2])
+    assert isinstance(rb.halfbouncepath(tp, f, Bm), float) and rb.halfbouncepath(tp, f, Bm) == pytest.approx(d["Sb"][2], rel=1e-7)
+    assert rb.eye(tp, f, Bm) == pytest.approx(d["I"][2], rel=1e-7)
+    g = rb.gradI(tp, f, Bm)
+    assert g.shape == (3,) and H.vec_relerr(g[None], d["gradI"][2][None]) < 1e-5
+    v = 2.5e8
+    assert rb.flutils.bounceperiod(tp, f, Bm, v) == pytest.approx(2 / v * d["Sb"][2], rel=1e-7)
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+@pytest.mark.parametrize("name", BC_CASES)
+def test_advance_vs_reference(eng, name, arith):
+    d = _gold(name)
+    f = H.gpu_field(str(d["field"]), ())
+    n1 = int(d["nrows_first_call"])
+    traj = d["traj"]
+    o = eng.bounce_center_advance(f, traj[0], float(d["mu"]), float(d["v"]), float(d["mass"]), float(d["charge"]),
+                                  float(d["delta"]), store_every=1, max_rows=n1 + 4, arith=arith)
+    assert o["status"][0] == 1
+    k = int(o["nstored"][0])
+    assert k == n1 - 1 == int(o["nrows"][0])
+    rows = o["rows"][0, :k]
+    print(name, arith, "labels", H.relerr(rows[1:, 0], traj[2:n1, 0]), "pos", H.vec_relerr(rows[:, 1:], traj[1:n1, 1:]),
+          "counters", o["counters"][0], d["solver_log"][:n1 - 1].sum(0))
+    assert np.allclose(rows[:, 0], traj[1:n1, 0], rtol=1e-7, atol=0)              # labels: k * dt, dt = 0.1 tau_b
+    assert rows[0, 0] == traj[0, 0]                                                # the START-time label quirk
+    assert H.vec_relerr(rows[:, 1:], traj[1:n1, 1:]) < 1e-8
+    # displacement itself (the drift is ~1e-3 of |r| per row): relative to the distance travelled
+    disp = np.linalg.norm(rows[:, 1:] - traj[0, 1:], axis=1); ref_disp = np.linalg.norm(traj[1:n1, 1:] - traj[0, 1:], axis=1)
+    print(name, arith, "displacement", np.max(np.abs(disp / ref_disp - 1)))
+    assert np.max(np.abs(disp / ref_disp - 1)) < 1e-5
+    assert np.array_equal(o["counters"][0], d["solver_log"][:n1 - 1].sum(0))
+    assert np.array_equal(o["state"][0], rows[-1])
+    if float(d["delta2"]):
+        # second advance(): restarts from the last row label (BounceCenter.py:247, 250)
+        o2 = eng.bounce_center_advance(f, o["state"][0], float(d["mu"]), float(d["v"]), float(d["mass"]), float(d["charge"]),
+                                       float(d["delta2"]), store_every=1, max_rows=len(traj), arith=arith)
+        k2 = int(o2["nstored"][0])
+        assert k2 == len(traj) - n1
+        assert H.vec_relerr(o2["rows"][0, :k2, 1:], traj[n1:, 1:]) < 1e-8
+        assert np.allclose(o2["rows"][0, :k2, 0], traj[n1:, 0], rtol=1e-7, atol=0)
+
+
+def test_bounce_center_class_matches_reference(eng):
+    """The reference-shaped class: constructor quirk (cos of degrees), advance twice, getters."""
+    import rapt_b200 as rb
+    d = _gold("bc_dipole_electron")
+    b = rb.BounceCenter(pos=tuple(d["pos"]), v=float(d["v"]), t0=0, pa=float(d["pa"]), mass=float(d["mass"]),
+                        charge=float(d["charge"]), field=rb.fields.EarthDipole())
+    assert b.mu == pytest.approx(float(d["mu"]), rel=1e-14)
+    b.advance(float(d["delta"]))
+    n1 = int(d["nrows_first_call"])
+    assert b.trajectory.shape == (n1, 4)
+    b.advance(float(d["delta2"]))
+    assert b.trajectory.shape == d["traj"].shape
+    assert H.vec_relerr(b.trajectory[:, 1:], d["traj"][:, 1:]) < 1e-8
+    assert b.tcur == pytest.approx(d["traj"][-1, 0], rel=1e-7)
+    assert np.array_equal(b.getx(), b.trajectory[:, 1]) and b.getr().shape == (len(b.trajectory),)
+    with pytest.raises(RuntimeError):
+        rb.BounceCenter(pos=(1, 1, 1), v=1.0, pa=80, mass=1.0, charge=1.0, field=rb.fields.VarEarthDipole())
+
+
+def test_ensemble_vs_oracle_and_dipole_invariants(eng):
+    """BounceCenterEnsemble: (i) two seeded members against the oracle (the reference's algorithm on scipy);
+    (ii) 2048 members: in a dipole the bounce-averaged drift conserves z of the starting plane's field line (the drift is
+    azimuthal): L = r^3 / (x^2 + y^2) constant, and electrons and protons drift in opposite directions."""
+    import oracle as O
+    import rapt_b200 as rb
+    from rapt_b200 import Re, m_el, m_pr, e, c
+    rng = np.random.default_rng(20261017)
+    n = 2048
+    L = rng.uniform(3, 7, n); phi = rng.uniform(0, 2 * np.pi, n)
+    pos = np.column_stack([L * Re * np.cos(phi), L * Re * np.sin(phi), rng.uniform(-0.05, 0.05, n) * Re])
+    proton = rng.uniform(size=n) < 0.5
+    mass = np.where(proton, m_pr, m_el); charge = np.where(proton, e, -e)
+    ke = np.exp(rng.uniform(np.log(1e5), np.log(5e6), n)) * e
+    g = 1 + ke / (mass * c * c)
+    v = c * np.sqrt(1 - 1 / g ** 2)
+    # pitch angles in RADIANS here so that cos(pa) (BounceCenter.py:114) means what it says: 75..88 degrees
+    pa = np.radians(rng.uniform(75, 88, n))
+    f = rb.fields.EarthDipole()
+    ens = rb.BounceCenterEnsemble(pos, v, 0.0, pa, mass, charge, f)
+    st0 = ens.state.copy()
+    par = dict(rb.params); par["BCtimestep"] = 0.25
+    ens.advance(1.0, store_every=0, params=par)
+    ok = ens.status == 1
+    assert ok.mean() > 0.999
+    st = ens.state
+    r0 = np.linalg.norm(st0[:, 1:], axis=1); r1 = np.linalg.norm(st[:, 1:], axis=1)
+    L0 = r0 ** 3 / (st0[:, 1] ** 2 + st0[:, 2] ** 2); L1 = r1 ** 3 / (st[:, 1] ** 2 + st[:, 2] ** 2)
+    assert np.max(np.abs(L1 / L0 - 1)[ok]) < 1e-5
+    dphi = np.unwrap(np.stack([np.arctan2(st0[:, 2], st0[:, 1]), np.arctan2(st[:, 2], st[:, 1])]), axis=0)
+    dphi = dphi[1] - dphi[0]
+    # gradient-curvature drift in a dipole: electrons eastward (dphi > 0), protons westward
+    assert np.all(dphi[ok & ~proton] > 0) and np.all(dphi[ok & proton] < 0)
+    # (i) oracle on three members
+    of = O.make_field("EarthDipole")
+    for i in (0, 1):
+        rows, cnt, dt = O.bounce_center_advance(of, st0[i], ens.mu[i], v[i], mass[i], charge[i], 1.0, bctimestep=0.25)
+        print("member", i, "dt", ens.dt[i] / dt - 1, "pos", np.linalg.norm(st[i, 1:] - rows[-1, 1:]) / np.linalg.norm(rows[-1, 1:]),
+              ens.last_counters[i], cnt)
+        assert ens.dt[i] == pytest.approx(dt, rel=1e-7)
+        assert ens.nrows[i] == len(rows)
+        assert np.linalg.norm(st[i, 1:] - rows[-1, 1:]) / np.linalg.norm(rows[-1, 1:]) < 1e-8
+        assert np.array_equal(ens.last_counters[i], cnt)
+
+
+def test_bounce_period_quadpack_route(eng):
+    """GuidingCenter.bounceperiod with the reference's quadrature route on the device (rapt_b200_bounce_period,
+    RAPT_QUAD_QUADPACK) against the reference's values and against the host scipy leg on the same device traces."""
+    from rapt_b200 import synth
+    d = np.load(os.path.join(H.GOLDEN, "e3_config3_first16.npz"))
+    f = H.gpu_field("DoubleDipole", ())
+    ic = synth.config3_electrons(16)
+    pos = np.column_stack([ic["x"], ic["y"], ic["z"]])
+    ppar, mu = eng.gc_construct(f, ic["t0"], pos, ic["v"], ic["pa"], ic["mass"])
+    st = np.column_stack([ic["t0"], pos, ppar])
+    for arith in ("strict", "fast"):
+        q = eng.bounceperiod_device(f, st, mu, ic["mass"], arith=arith, quadrature="quadpack")
+        host = eng.bounceperiod(f, st, mu, ic["mass"], arith=arith)
+        print(arith, "quadpack vs host scipy", np.max(np.abs(q / host - 1)), "vs golden", np.max(np.abs(q / d["bounceperiod"] - 1)))
+        assert np.max(np.abs(q / host - 1)) < 1e-8
+        assert np.max(np.abs(q / d["bounceperiod"] - 1)) < 1e-5       # the golden's own trace-noise floor (test_gpu_gc)
+        cf = eng.bounceperiod_device(f, st, mu, ic["mass"], arith=arith, quadrature="closed")
+        assert np.max(np.abs(cf / q - 1)) < 1e-4

@@ -116,7 +116,8 @@ def test_constructors_and_params_snapshot():
         rb.BounceCenter(pos=(1, 0, 0), v=1.0, pa=30, mass=1, charge=1, field=rb.fields.UniformCrossedEB())
     b = rb.BounceCenter(pos=(4 * rb.Re, 0, 0), v=1e7, pa=0.5, mass=rb.m_pr, charge=rb.e, field=rb.fields.EarthDipole())
     assert b.trajectory.shape == (1, 4) and b.mu > 0
-    with pytest.raises(NotImplementedError):
+    b.isequatorial = True
+    with pytest.raises(NotImplementedError):                   # the reference's branch cannot run (BounceCenter.py:235)
         b.advance(1.0)
     assert issubclass(rb.Adiabatic, Exception) and issubclass(rb.NonAdiabatic, Exception)
 
@@ -216,3 +217,29 @@ def test_nystrom_tables_are_consistent_with_the_tableau():
     # exact arithmetic agrees with what the generator rounded
     exact = float(sum(Fr(float(B[j])) * Fr(float(A[j, 5])) for j in range(12)))
     assert val["D8N_BA6"] == exact
+
+
+def test_bounce_center_host_side():
+    """BounceCenter (rapt/BounceCenter.py:74-115): constructor behaviour on the host; advance and the flutils
+    integrals are device-only (no CPU fallback)."""
+    import rapt_b200 as rb
+    from rapt_b200 import _lib
+    f = rb.fields.EarthDipole()
+    d = np.load(os.path.join(ROOT, "tests", "golden", "bc_dipole_electron.npz"))
+    b = rb.BounceCenter(pos=tuple(d["pos"]), v=float(d["v"]), t0=0, pa=float(d["pa"]), mass=float(d["mass"]),
+                        charge=float(d["charge"]), field=f)
+    assert b.trajectory.shape == (1, 4) and b.tcur == 0
+    assert b.mu == pytest.approx(float(d["mu"]), rel=1e-14)          # cos() of the pitch angle as given (BounceCenter.py:114)
+    assert b._mirror_field() == pytest.approx(float(d["Bm"]), rel=1e-14)
+    with pytest.raises(RuntimeError, match="nonstatic"):
+        rb.BounceCenter(pos=(1, 1, 1), v=1.0, pa=80, mass=1.0, charge=1.0, field=rb.fields.VarEarthDipole())
+    with pytest.raises(RuntimeError, match="nonstatic"):
+        rb.BounceCenterEnsemble(np.ones((2, 3)), 1.0, 0.0, 1.0, 1.0, 1.0, rb.fields.VarEarthDipole())
+    if _lib.device_count() == 0:
+        with pytest.raises(_lib.RaptB200Error, match="no CUDA device"):
+            b.advance(0.1)
+        with pytest.raises(_lib.RaptB200Error, match="no CUDA device"):
+            rb.eye(d["pts"][0], f, float(d["Bm"]))
+        with pytest.raises(_lib.RaptB200Error, match="no CUDA device"):
+            rb.engine.bounce_center_advance(f, d["traj"][0], float(d["mu"]), float(d["v"]), float(d["mass"]),
+                                            float(d["charge"]), 0.1)

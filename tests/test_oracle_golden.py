@@ -1,6 +1,8 @@
 """CPU: the oracle (oracle/rapt_oracle.c) against the golden vectors generated from the unmodified
 reference (tests/golden/, oracle/gen_golden.py) and against scipy's `_dop` directly.  This is the
 parity PIN of the oracle: trajectories and solver counters must agree bit for bit."""
+import os
+
 import numpy as np
 import pytest
 
@@ -234,3 +236,43 @@ def test_grid_field_bit_exact():
     st0 = np.concatenate(([0.0], d["oob_pos"], gm * d["oob_vel"]))
     o = O.particle_advance(f, O.make_params(cyclotronresolution=10), st0, m_pr, float(d["p_charge"]), 5.0, max_rows=64)
     assert int(o["status"][0]) == -6 and int(o["nstored"][0]) == len(d["oob_traj"])
+
+
+# ---------------------------------------------------------------- BounceCenter
+BC_CASES = ("bc_dipole_electron", "bc_dipole_proton", "bc_doubledipole_electron")
+
+
+@pytest.mark.parametrize("name", BC_CASES)
+def test_bounce_center_pieces_bit_exact(name):
+    """flutils.halfbouncepath / eye / gradI at three rows of the reference's BounceCenter trajectory."""
+    d = np.load(os.path.join(H.GOLDEN, name + ".npz"))
+    f = O.make_field(str(d["field"]))
+    Bm = float(d["Bm"])
+    for r, Sb, I, gI in zip(d["pts"], d["Sb"], d["I"], d["gradI"]):
+        assert O.halfbouncepath(f, r, Bm) == Sb
+        assert O.eye(f, r, Bm) == I
+        assert np.array_equal(O.gradI(f, r, Bm), gI)
+
+
+def test_flutils_special_branches_bit_exact():
+    """gradI's one-sided differences (a displaced line beyond the mirror field) and eye's Simpson branch."""
+    d = np.load(os.path.join(H.GOLDEN, "bc_flutils.npz"))
+    f = O.make_field("EarthDipole")
+    for tp, Bm, Sb, I, gI in zip(d["tpos"], d["Bm"], d["Sb"], d["I"], d["gradI"]):
+        assert O.halfbouncepath(f, tp, Bm) == Sb
+        assert O.eye(f, tp, Bm) == I
+        assert np.array_equal(O.gradI(f, tp, Bm), gI)
+
+
+@pytest.mark.parametrize("name", ["bc_dipole_proton", "bc_doubledipole_electron"])
+def test_bounce_center_advance_bit_exact(name):
+    """BounceCenter.advance: every row and the dopri5 counters of every call (the electron/dipole fixture, 9 s of
+    scipy quadrature, is left to the GPU test, which checks the device against it directly)."""
+    d = np.load(os.path.join(H.GOLDEN, name + ".npz"))
+    f = O.make_field(str(d["field"]))
+    n1 = int(d["nrows_first_call"])
+    rows, cnt, dt = O.bounce_center_advance(f, d["traj"][0], float(d["mu"]), float(d["v"]), float(d["mass"]),
+                                            float(d["charge"]), float(d["delta"]))
+    assert np.array_equal(rows, d["traj"][1:n1])
+    assert np.array_equal(cnt, d["solver_log"][:n1 - 1].sum(0))
+    assert rows[0, 0] == d["traj"][0, 0]            # the first computed row carries the START label (quirk kept)
