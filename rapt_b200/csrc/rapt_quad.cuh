@@ -35,6 +35,15 @@
 
 namespace RAPT_NS {
 
+// The QUADPACK routines are real functions on the device, one copy each, with their own stack frames: inlined into
+// one frame, nvcc 12.9 let qk21's fv1/fv2 share storage with the live extrapolation table rlist2 of qags (measured on
+// sm_100a: rlist2[1..2] came back holding integrand samples; the host build of the same source is ASan/UBSan clean).
+#if defined(__CUDACC__)
+#define RAPT_QUAD_NOINLINE __noinline__
+#else
+#define RAPT_QUAD_NOINLINE
+#endif
+
 #define RAPT_QUAD_PI 3.141592653589793
 #define RAPT_QUAD_LIMIT 50
 
@@ -168,7 +177,7 @@ struct QagsOut { double result, abserr; int neval, ier, last; };
 
 // dqk21: 21-point Gauss-Kronrod rule on [a, b]
 template <class Fn>
-RAPT_HD void qk21(const Fn &f, double a, double b, double &result, double &abserr, double &resabs, double &resasc)
+RAPT_HD RAPT_QUAD_NOINLINE void qk21(const Fn &f, double a, double b, double &result, double &abserr, double &resabs, double &resasc)
 {
     const double wg[5] = {0.066671344308688137593568809893332, 0.149451349150580593145776339657697,
                           0.219086362515982043995534934228163, 0.269266719309996355091226921569469,
@@ -221,7 +230,7 @@ RAPT_HD void qk21(const Fn &f, double a, double b, double &result, double &abser
 }
 
 // dqelg: Wynn's epsilon algorithm on the table epstab[1..n] (room for n + 2)
-RAPT_HD inline void qelg(int &n, double *epstab, double &result, double &abserr, double *res3la, int &nres)
+RAPT_HD RAPT_QUAD_NOINLINE inline void qelg(int &n, double *epstab, double &result, double &abserr, double *res3la, int &nres)
 {
     const int limexp = 50;
     nres++;
@@ -280,7 +289,7 @@ RAPT_HD inline void qelg(int &n, double *epstab, double &result, double &abserr,
 }
 
 // dqpsrt: keep iord[] ordered by decreasing error estimate
-RAPT_HD inline void qpsrt(int limit, int last, int &maxerr, double &ermax, const double *elist, int *iord, int &nrmax)
+RAPT_HD RAPT_QUAD_NOINLINE inline void qpsrt(int limit, int last, int &maxerr, double &ermax, const double *elist, int *iord, int &nrmax)
 {
     if (last <= 2) { iord[1] = 1; iord[2] = 2; }
     else {
@@ -325,7 +334,7 @@ RAPT_HD inline void qpsrt(int limit, int last, int &maxerr, double &ermax, const
 
 // dqagse with limit = 50 (scipy.integrate.quad's default); epsabs / epsrel as given
 template <class Fn>
-RAPT_HD QagsOut qags(const Fn &f, double a, double b, double epsabs, double epsrel)
+RAPT_HD RAPT_QUAD_NOINLINE QagsOut qags(const Fn &f, double a, double b, double epsabs, double epsrel, double *dbg = nullptr)
 {
     const int limit = RAPT_QUAD_LIMIT;
     double alist[RAPT_QUAD_LIMIT + 1], blist[RAPT_QUAD_LIMIT + 1], rlist[RAPT_QUAD_LIMIT + 1], elist[RAPT_QUAD_LIMIT + 1];
@@ -389,6 +398,8 @@ RAPT_HD QagsOut qags(const Fn &f, double a, double b, double epsabs, double epsr
             elist[maxerr] = error1; elist[last] = error2;
         }
         qpsrt(limit, last, maxerr, errmax, elist, iord, nrmax);
+        if (dbg) { double *g = dbg + 12 * (last - 2); g[0] = a1; g[1] = b2; g[2] = area1; g[3] = area2; g[4] = error1; g[5] = error2;
+                   g[6] = errsum; g[7] = errbnd; g[8] = maxerr; g[9] = nrmax; g[10] = extrap; g[11] = ier; }
         if (errsum <= errbnd) { exit_code = 115; break; }
         if (ier != 0) break;
         if (last == 2) {
@@ -424,7 +435,9 @@ RAPT_HD QagsOut qags(const Fn &f, double a, double b, double epsabs, double epsr
         // extrapolate
         numrl2++;
         rlist2[numrl2] = area;
+        if (dbg) { double *g = dbg + 12 * 50 + 12 * (last - 2); g[0] = numrl2; g[1] = rlist2[numrl2]; g[2] = rlist2[numrl2 - 1]; g[3] = rlist2[numrl2 > 2 ? numrl2 - 2 : 1]; g[7] = erlarg; g[8] = ertest; g[9] = small; }
         qelg(numrl2, rlist2, reseps, abseps, res3la, nres);
+        if (dbg) { double *g = dbg + 12 * 50 + 12 * (last - 2); g[4] = reseps; g[5] = abseps; g[6] = nres; g[10] = abserr; g[11] = numrl2; }
         ktmin++;
         if (ktmin > 5 && abserr < 1e-3 * errsum) ier = 5;
         if (abseps < abserr) {
