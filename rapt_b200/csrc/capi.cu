@@ -2,6 +2,7 @@
 // Host-side plumbing only: argument checks, device buffers, H2D/D2H copies, work ordering, launches.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cstdarg>
 #include <string>
@@ -867,7 +868,9 @@ static int bc_run(const rapt_field_t *f, int arith, rapt::BCArgs &a, int64_t n, 
     if (f->kind == RAPT_FIELD_GRID)
         return fail(RAPT_E_UNSUPPORTED, "bounce centre: analytic fields only (built-in or NVRTC user fields)");
     if (!f->is_static) return fail(RAPT_E_ARG, "BounceCenter does not work with nonstatic fields or electric fields.");
-    const long long lanes_max = (long long)g_sms * 4 * 64;
+    // 128 registers per thread: up to 8 blocks of 64 threads (16 warps) are resident per SM
+    static const int blocks_per_sm = getenv("RAPT_B200_BC_BLOCKS") ? std::max(1, atoi(getenv("RAPT_B200_BC_BLOCKS"))) : 8;
+    const long long lanes_max = (long long)g_sms * blocks_per_sm * 64;
     const long long lanes = std::min<long long>(n, lanes_max);
     const int grid = (int)((lanes + 63) / 64);
     (void)status_host; (void)dstatus;

@@ -209,3 +209,35 @@ def test_bounce_period_quadpack_route(eng):
         assert np.max(np.abs(q / d["bounceperiod"] - 1)) < 1e-5       # the golden's own trace-noise floor (test_gpu_gc)
         cf = eng.bounceperiod_device(f, st, mu, ic["mass"], arith=arith, quadrature="closed")
         assert np.max(np.abs(cf / q - 1)) < 1e-4
+
+
+def test_user_field_bounce_centre(eng):
+    """The NVRTC module of a user-defined field carries the bounce-centre kernel too: the notebook's ChargedDipole
+    (examples/Creating new fields.ipynb) with Q = 0 as a static dipole, against the oracle's restatement of it."""
+    import oracle as O
+    from userfield import make_charged_dipole
+    from rapt_b200 import Re, m_el, e, c
+    M = 3.0e-5 * Re ** 3
+    f = make_charged_dipole()(B0=M, Q=0.0)
+    f.static = True
+    f.gradientstepsize = Re / 1000
+    of = O.make_field("ChargedDipole", M, 0.0, gradstep=Re / 1000, static=True)
+    tpos = np.array([[0.0, 5 * Re, 0.5 * Re, 0.1 * Re], [0.0, -3 * Re, 2 * Re, -0.2 * Re]])
+    Bm = np.array([O.field_ops(of, np.array([0.0, tp[1], tp[2], 0.0]))["magB"][0] / np.sin(np.radians(80)) ** 2 for tp in tpos])
+    r = eng.bounce_center_terms(f, tpos, Bm)
+    assert np.all(r["status"] == 1)
+    for i, tp in enumerate(tpos):
+        assert r["Sb"][i] == pytest.approx(O.halfbouncepath(of, tp, Bm[i]), rel=1e-8)
+        assert r["I"][i] == pytest.approx(O.eye(of, tp, Bm[i]), rel=1e-9)
+        g = O.gradI(of, tp, Bm[i])
+        assert np.linalg.norm(r["gradI"][i] - g) / np.linalg.norm(g) < 1e-7
+    # a short advance: 1 MeV electron, local pitch angle such that Bm is the value above
+    ke = 1e6 * e; gam = 1 + ke / (m_el * c * c); v = c * np.sqrt(1 - 1 / gam ** 2)
+    B0 = O.field_ops(of, tpos[0])["magB"][0]
+    mu = gam ** 2 * m_el * v * v * (B0 / Bm[0]) / (2 * B0)          # so that m gamma^2 v^2 / (2 mu) == Bm[0]
+    o = eng.bounce_center_advance(f, tpos[0], mu, v, m_el, -e, 0.15, store_every=1, max_rows=16)
+    rows, cnt, dt = O.bounce_center_advance(of, tpos[0], mu, v, m_el, -e, 0.15)
+    k = int(o["nstored"][0])
+    assert o["status"][0] == 1 and k == len(rows)
+    assert H.vec_relerr(o["rows"][0, :k, 1:], rows[:, 1:]) < 1e-8
+    assert np.array_equal(o["counters"][0], cnt)

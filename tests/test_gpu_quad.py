@@ -70,6 +70,9 @@ def test_device_curve_integrals_match_host_build(dv, pa_eq, n):
         # near-equatorial curves (88 degrees): 1 - B/Bm <= 1e-3 everywhere, so the integrands carry 1e-13 of round-off and
         # the closed form differences two nearly equal primitives; device libm (asin, log) is within 2 ulp of glibc's
         assert dv.dv_curve(_p(s), _p(b), C.c_longlong(n), C.c_double(Bm), what, _p(out)) == 0
+        if np.isnan(ref):            # fewer than two points inside the mirror points: the reference's assert fails on both builds
+            assert np.isnan(out[0]) and (what != 2 or (out[1] == 1 and err.value == 1))
+            continue
         if abs(out[0] / ref - 1) >= tol:
             inside = np.where(b <= Bm)[0] if what < 2 else np.where(b < Bm)[0]
             i1, m = int(inside[0] - 1), int(inside[-1] + 1 - (inside[0] - 1) + 1)
