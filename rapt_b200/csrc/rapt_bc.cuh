@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(64) k_bounce_center(const BCArgs a)
     c.flres = a.flres; c.eyestep = a.eyestep; c.cap = a.max_pts; c.quadrature = a.quadrature;
     c.cv = a.curve + (size_t)lane * a.max_pts * 5;
     c.bw = a.scratch + (size_t)lane * a.max_pts * 4;
-    for (long long i = lane; i < a.n; i += nlanes) {
+    for (long long w = lane; w < a.n; w += nlanes) {
+        const long long i = a.order ? a.order[w] : w;
         const double v = a.v[i], mass = a.mass[i], q = a.charge[i];
         const double vc = v / RAPT_C_LIGHT;
         const double gamma = 1.0 / sqrt(1 - vc * vc);                              // BounceCenter.py:226

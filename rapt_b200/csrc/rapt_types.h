@@ -111,6 +111,7 @@ struct BCArgs {
     int *nrows, *nstored, *counters, *status;
     double *out;              // op 1: [n][8]
     double *curve, *scratch;  // per LANE: [lanes][max_pts][5], [lanes][max_pts][4]
+    const int *order;         // work item -> tracer (sorted by field-line length, so that a warp's lanes trace lines of similar length), or NULL
 };
 
 // Adaptive: per-tracer state of both modes + the epoch bookkeeping (rapt/Adaptive.py:70-104, 187-222)
