@@ -62,9 +62,9 @@ class BounceCenter:
             self.trajectory = np.vstack((self.trajectory, res["rows"][0, :k]))
         st = int(res["status"][0])
         if st != 1:
-            warnings.warn(f"BounceCenter.advance stopped after {k} of {nrows} rows (status {st}: "
-                          f"{ {-2: 'dopri5: larger nsteps is needed', -3: 'dopri5: step size becomes too small', -7: 'field line not traceable between mirror points'}.get(st, 'error')})",
-                          UserWarning)
+            why = {-2: "dopri5: larger nsteps is needed", -3: "dopri5: step size becomes too small",
+                   -7: "a field line could not be traced between its mirror points"}.get(st, "error")
+            warnings.warn(f"BounceCenter.advance stopped after {k} of {nrows} rows (status {st}: {why})", UserWarning)
         self.tcur = self.trajectory[-1, 0]
 
     def _mirror_field(self):

@@ -863,7 +863,7 @@ static int bounce_impl(const rapt_field_t *f, int arith, double fieldlineresolut
 // BounceCenter.advance and the flutils pieces behind it (rapt_bc.cuh).  One lane per tracer up to
 // 148 SMs x 4 blocks x 64 threads; every lane owns a scratch curve of max_pts points, grown on overflow.
 // ------------------------------------------------------------------------------------------------
-static int bc_run(const rapt_field_t *f, int arith, rapt::BCArgs &a, int64_t n, int32_t *status_host, DevBuf &dstatus, cudaStream_t s)
+static int bc_run(const rapt_field_t *f, int arith, rapt::BCArgs &a, int64_t n, cudaStream_t s)
 {
     if (f->kind == RAPT_FIELD_GRID)
         return fail(RAPT_E_UNSUPPORTED, "bounce centre: analytic fields only (built-in or NVRTC user fields)");
@@ -873,7 +873,6 @@ static int bc_run(const rapt_field_t *f, int arith, rapt::BCArgs &a, int64_t n, 
     const long long lanes_max = (long long)g_sms * blocks_per_sm * 64;
     const long long lanes = std::min<long long>(n, lanes_max);
     const int grid = (int)((lanes + 63) / 64);
-    (void)status_host; (void)dstatus;
     DevBuf cv, bw;
     CK(cv.alloc((size_t)grid * 64 * a.max_pts * 5 * sizeof(double)));
     CK(bw.alloc((size_t)grid * 64 * a.max_pts * 4 * sizeof(double)));
@@ -948,7 +947,7 @@ int rapt_b200_bounce_center_advance(const rapt_field_t *f, int arith, int quadra
         a.rows = want_rows ? drows.as<double>() : nullptr;
         a.nrows = dnr.as<int>(); a.nstored = dns.as<int>(); a.counters = dcnt.as<int>(); a.status = dstat.as<int>();
         a.order = order.empty() ? nullptr : dord.as<int>();
-        if (int rc = bc_run(f, arith, a, n, status, dstat, s)) return rc;
+        if (int rc = bc_run(f, arith, a, n, s)) return rc;
         CK(down(status, dstat, ni, s));
         CK(cudaStreamSynchronize(s));
         bool overflow = false;
@@ -992,7 +991,7 @@ int rapt_b200_bounce_center_terms(const rapt_field_t *f, int arith, int quadratu
         a.t = in[0].as<double>(); a.x = in[1].as<double>(); a.y = in[2].as<double>(); a.z = in[3].as<double>();
         a.Bm = in[4].as<double>(); a.v = in[5].as<double>(); a.mass = in[6].as<double>(); a.charge = in[7].as<double>();
         a.out = dout.as<double>(); a.status = dstat.as<int>();
-        if (int rc = bc_run(f, arith, a, n, status, dstat, s)) return rc;
+        if (int rc = bc_run(f, arith, a, n, s)) return rc;
         CK(down(status, dstat, ni, s));
         CK(cudaStreamSynchronize(s));
         bool overflow = false;
