@@ -241,6 +241,13 @@ int rapt_b200_bounce_center_terms(const rapt_field_t *f, int arith, int quadratu
                                   const double *v, const double *mass, const double *charge,
                                   double fieldlineresolution, double eyegradientstep, double *out, int32_t *status);
 
+/* ---- flutils.eye (rapt/flutils.py:65-151) alone, as GuidingCenter.geteye calls it once per trajectory row
+ * (GuidingCenter.py:608-624): I[i] = second invariant of the field line through (t, x, y, z)[i] with mirror field Bm[i].
+ * HOST pointers. */
+int rapt_b200_second_invariant(const rapt_field_t *f, int arith, int64_t n,
+                               const double *t, const double *x, const double *y, const double *z, const double *Bm,
+                               double fieldlineresolution, double *I, int32_t *status);
+
 /* ---- Adaptive.__init__ + Adaptive.advance (Adaptive.py:70-104, 187-222) for an ensemble.
  * In: particle position/velocity (as the Adaptive constructor takes them), t0, mass, charge.
  * gc_dt: guiding-centre output step (params["GCtimestep"], must be != 0 for ensembles).

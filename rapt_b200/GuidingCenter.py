@@ -218,7 +218,7 @@ class GuidingCenter:
 
     def geteye(self, step=1):
         """(time, second invariant I) for every `step`-th row (rapt/GuidingCenter.py:608-624, flutils.py:65-151):
-        all field lines are traced in one device call, the quadrature is the reference's."""
+        every row's field line is traced and integrated on the device in one call."""
         rows = self.trajectory[::step]
         res = engine.eye(self.field, rows[:, :4], self.getBm()[::step])
         return np.column_stack([rows[:, 0], res])

@@ -863,11 +863,13 @@ static int bounce_impl(const rapt_field_t *f, int arith, double fieldlineresolut
 // BounceCenter.advance and the flutils pieces behind it (rapt_bc.cuh).  One lane per tracer up to
 // 148 SMs x 4 blocks x 64 threads; every lane owns a scratch curve of max_pts points, grown on overflow.
 // ------------------------------------------------------------------------------------------------
-static int bc_run(const rapt_field_t *f, int arith, rapt::BCArgs &a, int64_t n, cudaStream_t s)
+static int bc_run(const rapt_field_t *f, int arith, rapt::BCArgs &a, int64_t n, cudaStream_t s, bool any_time_dependence = false)
 {
     if (f->kind == RAPT_FIELD_GRID)
         return fail(RAPT_E_UNSUPPORTED, "bounce centre: analytic fields only (built-in or NVRTC user fields)");
-    if (!f->is_static) return fail(RAPT_E_ARG, "BounceCenter does not work with nonstatic fields or electric fields.");
+    // flutils.eye traces the line at the time of its start point, whatever the field (GuidingCenter.geteye); the
+    // bounce-centre tracer itself is for static fields only (BounceCenter.py:104-105)
+    if (!any_time_dependence && !f->is_static) return fail(RAPT_E_ARG, "BounceCenter does not work with nonstatic fields or electric fields.");
     // 128 registers per thread: up to 8 blocks of 64 threads (16 warps) are resident per SM
     static const int blocks_per_sm = getenv("RAPT_B200_BC_BLOCKS") ? std::max(1, atoi(getenv("RAPT_B200_BC_BLOCKS"))) : 8;
     const long long lanes_max = (long long)g_sms * blocks_per_sm * 64;
@@ -998,6 +1000,45 @@ int rapt_b200_bounce_center_terms(const rapt_field_t *f, int arith, int quadratu
         for (int64_t i = 0; i < n; i++) if (status[i] == RAPT_ST_ROWCAP) { overflow = true; break; }
         if (overflow && max_pts < 16384) continue;
         CK(down(out, dout, 8 * nb, s));
+        CK(cudaStreamSynchronize(s));
+        return RAPT_OK;
+    }
+    return RAPT_OK;
+}
+
+int rapt_b200_second_invariant(const rapt_field_t *f, int arith, int64_t n,
+                               const double *t, const double *x, const double *y, const double *z, const double *Bm,
+                               double fieldlineresolution, double *I, int32_t *status)
+{
+    if (int rc = ensure_init()) return rc;
+    if (int rc = check_field(f)) return rc;
+    if (n < 0 || (n > 0 && (!t || !x || !y || !z || !Bm || !I || !status))) return fail(RAPT_E_ARG, "second_invariant: null argument");
+    if (!(fieldlineresolution > 0)) return fail(RAPT_E_ARG, "second_invariant: bad parameter");
+    if (f->kind == RAPT_FIELD_GRID) return fail(RAPT_E_UNSUPPORTED, "second_invariant: analytic fields only");
+    if (n == 0) return RAPT_OK;
+    cudaStream_t s = 0;
+    const size_t nb = (size_t)n * sizeof(double), ni = (size_t)n * sizeof(int);
+    for (int64_t max_pts = 256; max_pts <= 16384; max_pts *= 4) {
+        DevBuf in[5], dout, dstat;
+        const double *hi[5] = {t, x, y, z, Bm};
+        for (int k = 0; k < 5; k++) CK(up(in[k], hi[k], nb, s));
+        CK(dout.alloc(nb)); CK(dstat.alloc(ni));
+        rapt::BCArgs a;
+        memset(&a, 0, sizeof a);
+        RESOLVE(a.f, f);
+        a.op = 2; a.quadrature = RAPT_QUAD_QUADPACK; a.flres = fieldlineresolution; a.eyestep = 1.0;
+        a.n = n; a.max_pts = max_pts;
+        a.t = in[0].as<double>(); a.x = in[1].as<double>(); a.y = in[2].as<double>(); a.z = in[3].as<double>();
+        a.Bm = in[4].as<double>();
+        a.v = a.Bm; a.mass = a.Bm; a.charge = a.Bm;        // read but unused by op 2
+        a.out = dout.as<double>(); a.status = dstat.as<int>();
+        if (int rc = bc_run(f, arith, a, n, s, /*any_time_dependence=*/true)) return rc;
+        CK(down(status, dstat, ni, s));
+        CK(cudaStreamSynchronize(s));
+        bool overflow = false;
+        for (int64_t i = 0; i < n; i++) if (status[i] == RAPT_ST_ROWCAP) { overflow = true; break; }
+        if (overflow && max_pts < 16384) continue;
+        CK(down(I, dout, nb, s));
         CK(cudaStreamSynchronize(s));
         return RAPT_OK;
     }

@@ -214,7 +214,7 @@ RAPT_DEV int bc_dopri5(const FieldP &f, BcCtx &c, double &x, double (&y)[3], dou
 }
 
 // op 0: BounceCenter.advance.  op 1: the pieces at given points -- out[i] = (S_b, I, gradI[3], deriv[3]) -- so
-// that flutils.halfbouncepath / eye / gradI and the right-hand side are testable on their own.
+// that flutils.halfbouncepath / eye / gradI and the right-hand side are testable on their own.  op 2: out[i] = I only.
 template <class F>
 __global__ void __launch_bounds__(64) k_bounce_center(const BCArgs a)
 {
@@ -233,6 +233,11 @@ __global__ void __launch_bounds__(64) k_bounce_center(const BCArgs a)
         c.coef = gamma * mass * v * v / q;
         c.err = 0;
         double x = a.t[i], Y[3] = {a.x[i], a.y[i], a.z[i]};
+        if (a.op == 2) {                       // flutils.eye only (GuidingCenter.geteye: one value per trajectory row)
+            a.out[i] = bc_eye<F>(a.f, c, x, Y[0], Y[1], Y[2]);
+            a.status[i] = c.err ? c.err : RAPT_ST_OK;
+            continue;
+        }
         if (a.op == 1) {
             double *o = a.out + 8 * i, g[3], dv[3];
             o[0] = bc_halfbounce<F>(a.f, c, x, Y[0], Y[1], Y[2]);

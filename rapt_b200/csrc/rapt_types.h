@@ -98,7 +98,7 @@ struct BounceArgs {
 // BounceCenter.advance (rapt/BounceCenter.py:206-251) and its pieces (flutils.halfbouncepath / eye / gradI)
 struct BCArgs {
     FieldP f;
-    int op;                   // 0: advance; 1: out[i] = (S_b, I, gradI[3], deriv[3]) at the given points
+    int op;                   // 0: advance; 1: out[i] = (S_b, I, gradI[3], deriv[3]) at the given points; 2: out[i] = I
     int quadrature;           // halfbouncepath: 1 brentq + QAGS as the reference, 0 closed form
     double rtol, atol, flres, eyestep, bctimestep, delta;
     long long n, max_pts, store_every, max_rows;
@@ -109,7 +109,7 @@ struct BCArgs {
     double *dt_out, *tsolver; // optional
     double *rows;             // [n][max_rows][4] or NULL
     int *nrows, *nstored, *counters, *status;
-    double *out;              // op 1: [n][8]
+    double *out;              // op 1: [n][8]; op 2: [n]
     double *curve, *scratch;  // per LANE: [lanes][max_pts][5], [lanes][max_pts][4]
     const int *order;         // work item -> tracer (sorted by field-line length, so that a warp's lanes trace lines of similar length), or NULL
 };

@@ -269,8 +269,25 @@ def eye_from_curve(s, b, Bm):
 
 
 def eye(field, tpos, Bm, fieldlineresolution=None, arith="strict"):
-    """flutils.eye for n (t, x, y, z) start points: one device call traces all field lines, the quadrature of
-    each runs on the host as in the reference."""
+    """flutils.eye (rapt/flutils.py:65-151) for n (t, x, y, z) start points, all on the device: field-line trace, then
+    scipy's spline / brentq / QUADPACK route (or the Simpson branch below 70 degrees) per thread."""
+    from . import params as gp
+    f = _field_desc(field)
+    tp = np.asarray(tpos, dtype=np.float64).reshape(-1, 4)
+    n = len(tp)
+    flr = float(gp["fieldlineresolution"] if fieldlineresolution is None else fieldlineresolution)
+    cols = [np.ascontiguousarray(tp[:, i]).copy() for i in range(4)]
+    Bm = _col(Bm, n)
+    out = np.zeros(n); status = np.zeros(n, np.int32)
+    check(_lib.load().rapt_b200_second_invariant(C.byref(f), C.c_int(1 if arith in ("strict", 1) else 0), C.c_int64(n),
+                                                 *[ptr(c_) for c_ in cols], ptr(Bm), C.c_double(flr), ptr(out), ptr(status)))
+    if np.any(status != 1):
+        raise AssertionError("field-line trace does not bracket the mirror points")      # flutils.py:117
+    return out
+
+
+def eye_host(field, tpos, Bm, fieldlineresolution=None, arith="strict"):
+    """Cross-check of `eye`: device traces + scipy's own interp1d / brentq / quad on the host."""
     curves, _ = fieldline_trace_many(field, tpos, Bm, fieldlineresolution, arith)
     Bm = _col(Bm, len(curves))
     return np.array([eye_from_curve(cv[:, 0], cv[:, 4], Bm[i]) for i, cv in enumerate(curves)])
@@ -302,7 +319,7 @@ def halfbouncepath_from_curve(s, b, Bm):
 
 
 def bounceperiod(field, state, mu, mass, fieldlineresolution=None, arith="strict"):
-    """GuidingCenter.bounceperiod for n guiding centres: device field-line trace + host quadrature."""
+    """Cross-check of `bounceperiod_device`: device field-line traces + scipy's own quadrature on the host."""
     bs = bounce_setup(field, state, mu, mass, fieldlineresolution, arith)
     n = len(bs["Bm"])
     out = np.zeros(n)
