@@ -241,3 +241,41 @@ def test_user_field_bounce_centre(eng):
     assert o["status"][0] == 1 and k == len(rows)
     assert H.vec_relerr(o["rows"][0, :k, 1:], rows[:, 1:]) < 1e-8
     assert np.array_equal(o["counters"][0], cnt)
+
+
+def test_advance_options(eng):
+    """C-ABI options of rapt_b200_bounce_center_advance: a given output step, row decimation, a short row buffer,
+    a zero-length call; and the argument checks."""
+    import ctypes as C
+    from rapt_b200 import _lib
+    d = _gold("bc_dipole_proton")
+    f = H.gpu_field("EarthDipole", ())
+    n1 = int(d["nrows_first_call"])
+    args = (f, d["traj"][0], float(d["mu"]), float(d["v"]), float(d["mass"]), float(d["charge"]))
+    full = eng.bounce_center_advance(*args, float(d["delta"]), store_every=1, max_rows=16)
+    k = int(full["nstored"][0])
+    assert k == n1 - 1
+    # the step the device derived, handed back in: identical rows
+    same = eng.bounce_center_advance(*args, float(d["delta"]), dt=full["dt"], store_every=1, max_rows=16)
+    assert np.array_equal(same["rows"][0, :k], full["rows"][0, :k]) and np.array_equal(same["counters"], full["counters"])
+    # every second row
+    dec = eng.bounce_center_advance(*args, float(d["delta"]), store_every=2, max_rows=16)
+    assert dec["nrows"][0] == k and dec["nstored"][0] == k // 2
+    assert np.array_equal(dec["rows"][0, :k // 2], full["rows"][0, 1:k:2])
+    # a row buffer shorter than the run: the first rows are kept, the state still advances to the end
+    short = eng.bounce_center_advance(*args, float(d["delta"]), store_every=1, max_rows=2)
+    assert short["nstored"][0] == 2 and short["nrows"][0] == k and short["status"][0] == 1
+    assert np.array_equal(short["state"], full["state"])
+    # nothing to do
+    zero = eng.bounce_center_advance(*args, 0.0, store_every=1, max_rows=4)
+    assert zero["nrows"][0] == 0 and zero["status"][0] == 1 and np.array_equal(zero["state"][0], d["traj"][0])
+    # argument checks: non-static field, gridded field kind, bad parameters
+    from rapt_b200 import fields
+    with pytest.raises(_lib.RaptB200Error, match="nonstatic"):
+        eng.bounce_center_advance(fields.VarEarthDipole(0.1, 10), *args[1:], 0.1)
+    bad = dict(__import__("rapt_b200").params); bad["BCtimestep"] = 0
+    with pytest.raises(_lib.RaptB200Error, match="BCtimestep"):
+        eng.bounce_center_advance(*args, 0.1, params=bad)
+    bad = dict(__import__("rapt_b200").params); bad["eyegradientstep"] = -1.0
+    with pytest.raises(_lib.RaptB200Error, match="bad parameter"):
+        eng.bounce_center_advance(*args, 0.1, params=bad)
