@@ -273,9 +273,10 @@ def test_advance_options(eng):
     from rapt_b200 import fields
     with pytest.raises(_lib.RaptB200Error, match="nonstatic"):
         eng.bounce_center_advance(fields.VarEarthDipole(0.1, 10), *args[1:], 0.1)
-    bad = dict(__import__("rapt_b200").params); bad["BCtimestep"] = 0
+    import rapt_b200 as rb
+    bad = dict(rb.params); bad["BCtimestep"] = 0
     with pytest.raises(_lib.RaptB200Error, match="BCtimestep"):
         eng.bounce_center_advance(*args, 0.1, params=bad)
-    bad = dict(__import__("rapt_b200").params); bad["eyegradientstep"] = -1.0
+    bad = dict(rb.params); bad["eyegradientstep"] = -1.0
     with pytest.raises(_lib.RaptB200Error, match="bad parameter"):
         eng.bounce_center_advance(*args, 0.1, params=bad)

@@ -235,6 +235,9 @@ def test_bounce_center_host_side():
         rb.BounceCenter(pos=(1, 1, 1), v=1.0, pa=80, mass=1.0, charge=1.0, field=rb.fields.VarEarthDipole())
     with pytest.raises(RuntimeError, match="nonstatic"):
         rb.BounceCenterEnsemble(np.ones((2, 3)), 1.0, 0.0, 1.0, 1.0, 1.0, rb.fields.VarEarthDipole())
+    # setpa: same energy, new pitch angle, data reset (BounceCenter.py:117-132 keeps the constructor's cos() quirk)
+    b.setpa(30.0)
+    assert b.trajectory.shape == (1, 4) and b.pa == 30.0 and b.mu != pytest.approx(float(d["mu"]), rel=1e-3)
     if _lib.device_count() == 0:
         with pytest.raises(_lib.RaptB200Error, match="no CUDA device"):
             b.advance(0.1)
