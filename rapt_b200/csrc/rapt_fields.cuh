@@ -41,10 +41,26 @@ RAPT_DEV double sgn(double z) { return z > 0 ? 1.0 : (z < 0 ? -1.0 : 0.0); }
 // Branch-free reciprocal and reciprocal square root for the fast flavour: MUFU seed (~2^-22) refined
 // to 1-2 ulp with fused Newton steps.  No denormal / special-case slow paths -- every argument on the
 // hot path (r^2, |B|^2, error scales, gamma*m) is a normal, strictly positive number.
+#ifdef RAPT_HOST_BUILD
+// tests/hostcheck/kernel_host.cpp compiles these headers for the CPU (test infrastructure, never loaded by the
+// product): the MUFU seeds become the exact value truncated to 23 mantissa bits, the same accuracy class.
+RAPT_DEV double mufu_seed(double v) { return __longlong_as_double(__double_as_longlong(v) & ~0x1fffffffLL); }
+RAPT_DEV double mufu_rcp(double x) { return mufu_seed(1.0 / x); }
+RAPT_DEV double mufu_rsqrt(double x) { return mufu_seed(1.0 / sqrt(x)); }
+RAPT_DEV unsigned grid_dynamic_smem() { return 0; }
+#else
+RAPT_DEV double mufu_rcp(double x) { double y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); return y; }
+RAPT_DEV double mufu_rsqrt(double x) { double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); return y; }
+RAPT_DEV unsigned grid_dynamic_smem()
+{
+    unsigned n;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(n));
+    return n;
+}
+#endif
 RAPT_DEV double fast_rcp(double x)
 {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double y = mufu_rcp(x);
     double e = fma(-x, y, 1.0);
     y = fma(y, e, y);
     e = fma(-x, y, 1.0);
@@ -79,14 +95,12 @@ RAPT_DEV double fast_exp(double y)
 // one Newton step: ~2^-45; enough for the error-norm scale factors 1/(atol + rtol |y|)
 RAPT_DEV double fast_rcp1(double x)
 {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double y = mufu_rcp(x);
     return fma(y, fma(-x, y, 1.0), y);
 }
 RAPT_DEV double fast_rsqrt(double x)
 {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double y = mufu_rsqrt(x);
     double e = fma(-(x * y), y, 1.0);                 // 1 - x y^2  (~2^-22)
 #ifdef RAPT_RSQRT_POLISH
     y = fma(y * e, fma(0.375, e, 0.5), y);
@@ -171,12 +185,6 @@ RAPT_DEV bool grid_locate(const double *__restrict__ g, int n, double g0, double
 // (conflict-free).  Consecutive evaluations of one tracer -- the RK stages of a step, the 7 stencil points
 // of the guiding-centre right-hand side -- almost always fall in the same cell, so the 16 gathers of 32-byte
 // sectors through L1/L2 happen once per cell instead of once per evaluation (profiles/r1_grid_field.md).
-RAPT_DEV unsigned grid_dynamic_smem()
-{
-    unsigned n;
-    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(n));
-    return n;
-}
 RAPT_DEV void grid_cache_reset()
 {
     extern __shared__ double rapt_grid_cache[];

@@ -1,0 +1,64 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes access to tests/hostcheck/libkernelhost.so, the product's advance kernels
+compiled for the host (tests/hostcheck/kernel_host.cpp).  Same argument conventions as rapt_b200.engine."""
+import ctypes as C
+import os
+import numpy as np
+from rapt_b200 import engine
+from rapt_b200._lib import EOM_KIND, ptr
+
+_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcheck", "libkernelhost.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(_PATH)
+    return _lib
+
+
+def _col(a, n):
+    return np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (n,))).copy()
+
+
+def particle_advance(field, state, mass, charge, delta, store_every=1, max_rows=0, rkn=True, nthreads=4,
+                     check_adiabaticity=False, **over):
+    f = engine._field_desc(field)
+    p = engine.snapshot_params(None, check_adiabaticity, **over)
+    st = np.asarray(state, dtype=np.float64).reshape(-1, 7)
+    n = len(st)
+    cols = [np.ascontiguousarray(st[:, i]).copy() for i in range(7)]
+    mass = _col(mass, n); charge = _col(charge, n)
+    want = store_every > 0 and max_rows > 0
+    rows = np.zeros((n, max_rows, 8)) if want else None
+    nrows = np.zeros(n, np.int32); nstored = np.zeros(n, np.int32); counters = np.zeros((n, 4), np.int32)
+    status = np.zeros(n, np.int32); tcur = np.zeros(n); dt = np.zeros(n)
+    rc = lib().hc_particle_advance(
+        C.byref(f), C.byref(p), C.c_longlong(n), *[ptr(c_) for c_ in cols], ptr(mass), ptr(charge), C.c_double(delta),
+        C.c_longlong(store_every), C.c_longlong(max_rows), ptr(rows), ptr(nrows), ptr(nstored), ptr(counters),
+        ptr(status), ptr(tcur), ptr(dt), C.c_int(1 if rkn else 0), C.c_int(nthreads))
+    assert rc == 0, rc
+    return dict(state=np.column_stack(cols), rows=rows, nrows=nrows, nstored=nstored, counters=counters,
+                status=status, tcur=tcur, dt=dt)
+
+
+def gc_advance(field, state, mu, v, mass, charge, dt, delta, eom="TaoChanBrizardEOM", store_every=1, max_rows=0,
+               nthreads=4, check_adiabaticity=False, **over):
+    f = engine._field_desc(field)
+    p = engine.snapshot_params(None, check_adiabaticity, **over)
+    st = np.asarray(state, dtype=np.float64).reshape(-1, 5)
+    n = len(st)
+    cols = [np.ascontiguousarray(st[:, i]).copy() for i in range(5)]
+    mu, v, mass, charge, dt = _col(mu, n), _col(v, n), _col(mass, n), _col(charge, n), _col(dt, n)
+    want = store_every > 0 and max_rows > 0
+    rows = np.zeros((n, max_rows, 8)) if want else None
+    nrows = np.zeros(n, np.int32); nstored = np.zeros(n, np.int32); counters = np.zeros((n, 4), np.int32)
+    status = np.zeros(n, np.int32); tcur = np.zeros(n)
+    rc = lib().hc_gc_advance(
+        C.byref(f), C.byref(p), C.c_int(EOM_KIND[eom]), C.c_longlong(n), *[ptr(c_) for c_ in cols],
+        ptr(mu), ptr(v), ptr(mass), ptr(charge), ptr(dt), C.c_double(delta),
+        C.c_longlong(store_every), C.c_longlong(max_rows), ptr(rows), ptr(nrows), ptr(nstored), ptr(counters),
+        ptr(status), ptr(tcur), C.c_int(nthreads))
+    assert rc == 0, rc
+    return dict(state=np.column_stack(cols), rows=rows, nrows=nrows, nstored=nstored, counters=counters,
+                status=status, tcur=tcur, dt=dt)
