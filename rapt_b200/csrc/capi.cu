@@ -290,6 +290,7 @@ int build_order(const rapt_field_t *f, rapt::AdvArgs &a, bool strict, cudaStream
     const size_t n = (size_t)a.nwork;
     if (g_sort.n < n) {
         cudaFree(g_sort.key_in); cudaFree(g_sort.key_out); cudaFree(g_sort.idx_in); cudaFree(g_sort.idx_out);
+        g_sort.key_in = g_sort.key_out = nullptr; g_sort.idx_in = g_sort.idx_out = nullptr; g_sort.n = 0;   // a failed cudaMalloc below must not leave freed pointers behind
         CK(cudaMalloc(&g_sort.key_in, n * sizeof(double)));
         CK(cudaMalloc(&g_sort.key_out, n * sizeof(double)));
         CK(cudaMalloc(&g_sort.idx_in, n * sizeof(int)));
@@ -302,6 +303,7 @@ int build_order(const rapt_field_t *f, rapt::AdvArgs &a, bool strict, cudaStream
     cub::DeviceRadixSort::SortPairs(nullptr, need, g_sort.key_in, g_sort.key_out, g_sort.idx_in, g_sort.idx_out, (int)n, 0, 64, s);
     if (need > g_sort.tmp_bytes) {
         cudaFree(g_sort.tmp);
+        g_sort.tmp = nullptr; g_sort.tmp_bytes = 0;
         CK(cudaMalloc(&g_sort.tmp, need));
         g_sort.tmp_bytes = need;
     }

@@ -26,6 +26,9 @@
 #ifndef RAPT_RKN_THREADS
 #define RAPT_RKN_THREADS 128
 #endif
+#ifndef RAPT_RKN_HK
+#define RAPT_RKN_HK 1        /* 1: stage vectors scaled by h (see the step body); 0: the unscaled form measured in round 1 */
+#endif
 namespace RAPT_NS {
 
 // K = dp/dt = q (E + P x B / (gamma m)), Particle.py:295
@@ -81,6 +84,62 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
         nstep_row++; nstep++;
         const double hg = h * igm;
         double K2[3], K3[3], K4[3], K5[3], K6[3], K7[3], K8[3], K9[3], K10[3], K11[3], K12[3];
+#if RAPT_RKN_HK
+        // Stage vectors scaled by the step: K_l holds h K_l.  The field comes back already multiplied by h q/(gamma m)
+        // (one multiply per step instead of one per sum), every stage momentum is an FMA chain onto p and the |h| of
+        // the error norm is absorbed: ~9 % fewer FP64 instructions per step than the unscaled form below.
+        // K1 itself is scaled in place for the duration of the attempt (no second copy in registers): the FSAL
+        // evaluation replaces it when the step is accepted, a rejected step divides the h out again.
+        const double hqg = h * qg, hq = h * q;
+#pragma unroll
+        for (int i = 0; i < 3; i++) K1[i] *= h;
+#define RKN_STAGE(PEXPR, XEXPR, CS, KOUT)                                                          \
+        {                                                                                          \
+            _Pragma("unroll") for (int i = 0; i < 3; i++) { P[i] = (PEXPR); X[i] = fma(hg, (XEXPR), x[i]); } \
+            lorentz_K<F>(a.f, hq, hqg, t + (CS) * h, X, P, KOUT);                                   \
+        }
+        RKN_STAGE(fma(T8(A2_1), K1[i], p[i]),
+                  T8(A2_1) * p[i], T8(C2), K2)
+        RKN_STAGE(fma(T8(A3_2), K2[i], fma(T8(A3_1), K1[i], p[i])),
+                  fma(TN(AA3_1), K1[i], TN(RS3) * p[i]), T8(C3), K3)
+        RKN_STAGE(fma(T8(A4_3), K3[i], fma(T8(A4_1), K1[i], p[i])),
+                  fma(TN(AA4_2), K2[i], fma(TN(AA4_1), K1[i], TN(RS4) * p[i])), T8(C4), K4)
+        RKN_STAGE(fma(T8(A5_4), K4[i], fma(T8(A5_3), K3[i], fma(T8(A5_1), K1[i], p[i]))),
+                  fma(TN(AA5_3), K3[i], fma(TN(AA5_2), K2[i], fma(TN(AA5_1), K1[i], TN(RS5) * p[i]))), T8(C5), K5)
+        RKN_STAGE(fma(T8(A6_5), K5[i], fma(T8(A6_4), K4[i], fma(T8(A6_1), K1[i], p[i]))),
+                  fma(TN(AA6_4), K4[i], fma(TN(AA6_3), K3[i], fma(TN(AA6_1), K1[i], TN(RS6) * p[i]))), T8(C6), K6)
+        RKN_STAGE(fma(T8(A7_6), K6[i], fma(T8(A7_5), K5[i], fma(T8(A7_4), K4[i], fma(T8(A7_1), K1[i], p[i])))),
+                  fma(TN(AA7_5), K5[i], fma(TN(AA7_4), K4[i], fma(TN(AA7_3), K3[i], fma(TN(AA7_1), K1[i], TN(RS7) * p[i])))), T8(C7), K7)
+        RKN_STAGE(fma(T8(A8_7), K7[i], fma(T8(A8_6), K6[i], fma(T8(A8_5), K5[i], fma(T8(A8_4), K4[i], fma(T8(A8_1), K1[i], p[i]))))),
+                  fma(TN(AA8_6), K6[i], fma(TN(AA8_5), K5[i], fma(TN(AA8_4), K4[i], fma(TN(AA8_3), K3[i], fma(TN(AA8_1), K1[i], TN(RS8) * p[i]))))), T8(C8), K8)
+        RKN_STAGE(fma(T8(A9_8), K8[i], fma(T8(A9_7), K7[i], fma(T8(A9_6), K6[i], fma(T8(A9_5), K5[i], fma(T8(A9_4), K4[i], fma(T8(A9_1), K1[i], p[i])))))),
+                  fma(TN(AA9_7), K7[i], fma(TN(AA9_6), K6[i], fma(TN(AA9_5), K5[i], fma(TN(AA9_4), K4[i], fma(TN(AA9_3), K3[i], fma(TN(AA9_1), K1[i], TN(RS9) * p[i])))))), T8(C9), K9)
+        RKN_STAGE(fma(T8(A10_9), K9[i], fma(T8(A10_8), K8[i], fma(T8(A10_7), K7[i], fma(T8(A10_6), K6[i], fma(T8(A10_5), K5[i], fma(T8(A10_4), K4[i], fma(T8(A10_1), K1[i], p[i]))))))),
+                  fma(TN(AA10_8), K8[i], fma(TN(AA10_7), K7[i], fma(TN(AA10_6), K6[i], fma(TN(AA10_5), K5[i], fma(TN(AA10_4), K4[i], fma(TN(AA10_3), K3[i], fma(TN(AA10_1), K1[i], TN(RS10) * p[i]))))))), T8(C10), K10)
+        RKN_STAGE(fma(T8(A11_10), K10[i], fma(T8(A11_9), K9[i], fma(T8(A11_8), K8[i], fma(T8(A11_7), K7[i], fma(T8(A11_6), K6[i], fma(T8(A11_5), K5[i], fma(T8(A11_4), K4[i], fma(T8(A11_1), K1[i], p[i])))))))),
+                  fma(TN(AA11_9), K9[i], fma(TN(AA11_8), K8[i], fma(TN(AA11_7), K7[i], fma(TN(AA11_6), K6[i], fma(TN(AA11_5), K5[i], fma(TN(AA11_4), K4[i], fma(TN(AA11_3), K3[i], fma(TN(AA11_1), K1[i], TN(RS11) * p[i])))))))), T8(C11), K11)
+        RKN_STAGE(fma(T8(A12_11), K11[i], fma(T8(A12_10), K10[i], fma(T8(A12_9), K9[i], fma(T8(A12_8), K8[i], fma(T8(A12_7), K7[i], fma(T8(A12_6), K6[i], fma(T8(A12_5), K5[i], fma(T8(A12_4), K4[i], fma(T8(A12_1), K1[i], p[i]))))))))),
+                  fma(TN(AA12_10), K10[i], fma(TN(AA12_9), K9[i], fma(TN(AA12_8), K8[i], fma(TN(AA12_7), K7[i], fma(TN(AA12_6), K6[i], fma(TN(AA12_5), K5[i], fma(TN(AA12_4), K4[i], fma(TN(AA12_3), K3[i], fma(TN(AA12_1), K1[i], TN(RS12) * p[i]))))))))), 1.0, K12)
+#undef RKN_STAGE
+        // new state (b-weights) in X, P and the two error estimators; everything carries one factor h, which is the |h|
+        // of err = |h| err5 / sqrt(6 (err5 + 0.01 err3))
+        double err = 0, err2 = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const double sb = fma(T8(B12), K12[i], fma(T8(B11), K11[i], fma(T8(B10), K10[i], fma(T8(B9), K9[i], fma(T8(B8), K8[i], fma(T8(B7), K7[i], fma(T8(B6), K6[i], T8(B1) * K1[i])))))));
+            P[i] = p[i] + sb;
+            X[i] = fma(hg, fma(TN(BA11), K11[i], fma(TN(BA10), K10[i], fma(TN(BA9), K9[i], fma(TN(BA8), K8[i], fma(TN(BA7), K7[i], fma(TN(BA6), K6[i], fma(TN(BA1), K1[i], TN(SB) * p[i]))))))), x[i]);
+            const double e5p = fma(T8(ER12), K12[i], fma(T8(ER11), K11[i], fma(T8(ER10), K10[i], fma(T8(ER9), K9[i], fma(T8(ER8), K8[i], fma(T8(ER7), K7[i], fma(T8(ER6), K6[i], T8(ER1) * K1[i])))))));
+            const double e3p = fma(-T8(BHH3), K12[i], fma(-T8(BHH2), K9[i], fma(-T8(BHH1), K1[i], sb)));
+            const double e5x = hg * (fma(TN(ERA11), K11[i], fma(TN(ERA10), K10[i], fma(TN(ERA9), K9[i], fma(TN(ERA8), K8[i], fma(TN(ERA7), K7[i], fma(TN(ERA6), K6[i], fma(TN(ERA5), K5[i], fma(TN(ERA4), K4[i], fma(TN(ERA1), K1[i], TN(SER) * p[i]))))))))));
+            const double e3x = hg * (fma(TN(WA11), K11[i], fma(TN(WA10), K10[i], fma(TN(WA9), K9[i], fma(TN(WA8), K8[i], fma(TN(WA7), K7[i], fma(TN(WA6), K6[i], fma(TN(WA5), K5[i], fma(TN(WA4), K4[i], fma(TN(WA1), K1[i], TN(SW) * p[i]))))))))));
+            const double iskx = fast_rcp1(atol + rtol * fmax(fabs(x[i]), fabs(X[i])));
+            const double iskp = fast_rcp1(atol + rtol * fmax(fabs(p[i]), fabs(P[i])));
+            const double a3 = e3x * iskx, b3 = e3p * iskp, a5 = e5x * iskx, b5 = e5p * iskp;
+            err2 += a3 * a3 + b3 * b3; err += a5 * a5 + b5 * b5;
+        }
+        const double hnorm = 1.0;
+#else
 #define RKN_STAGE(PSUM, XSUM, CS, KOUT)                                                            \
         {                                                                                          \
             _Pragma("unroll") for (int i = 0; i < 3; i++) { P[i] = p[i] + h * (PSUM); X[i] = x[i] + hg * (XSUM); } \
@@ -124,9 +183,11 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
             const double a3 = e3x * iskx, b3 = e3p * iskp, a5 = e5x * iskx, b5 = e5p * iskp;
             err2 += a3 * a3 + b3 * b3; err += a5 * a5 + b5 * b5;
         }
+        const double hnorm = fabs(h);
+#endif
         double deno = err + 0.01 * err2;
         if (deno <= 0.0) deno = 1.0;
-        err = fabs(h) * err * fast_rsqrt(6 * deno);
+        err = hnorm * err * fast_rsqrt(6 * deno);
         if (err <= 1.0) {
             // accepted.  The controller's new step is only consumed when the row continues.
             if (!last) {
@@ -165,6 +226,9 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
                 need_row = true;
             }
         } else {
+#if RAPT_RKN_HK
+            { const double ih = fast_rcp(h); _Pragma("unroll") for (int i = 0; i < 3; i++) K1[i] *= ih; }   // back to f(t, y)
+#endif
             if (a.p.dop853_reject_rule == 1) h = h / fmin(facc1, RAPT_POW(err, expo1) / safe);
             else h = h / facc1;                              // scipy 1.18.1: 0.3 h whatever err is
             reject = true;
