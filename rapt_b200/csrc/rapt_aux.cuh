@@ -366,12 +366,12 @@ __global__ void __launch_bounds__(128) k_bounce_setup(const BounceArgs a)
 // per-warp counts -> block-level scan in shared memory -> one atomicAdd per block and mode.  The next
 // epoch's kernels therefore see tracers regrouped by mode, finished ones dropped.
 // ------------------------------------------------------------------------------------------------
+// the per-tracer part: returns the work list the tracer joins (-1 idle/finished, 0 particle list, 1 GC list)
 template <class F>
-__global__ void __launch_bounds__(256) k_adaptive_switch(const AdaptArgs a)
+RAPT_DEV int adaptive_switch_one(const AdaptArgs &a, const long long i)
 {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    int want = -1;                                       // -1 idle/finished, 0 particle list, 1 GC list
-    if (i < a.n) {
+    int want = -1;
+    {
         const double mass = a.mass[i], q = a.charge[i];
         int mode, st, nseg;
         bool newseg = false;
@@ -452,6 +452,14 @@ __global__ void __launch_bounds__(256) k_adaptive_switch(const AdaptArgs a)
             }
         }
     }
+    return want;
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) k_adaptive_switch(const AdaptArgs a)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int want = (i < a.n) ? adaptive_switch_one<F>(a, i) : -1;
     // ---- regroup by mode: ballot + shared-memory scan + one atomic per block and mode
     __shared__ int wcount[2][8];
     __shared__ int wbase[2][8];

@@ -23,6 +23,15 @@
 
 #define RAPT_DEV __device__ __forceinline__
 
+// Python's scalar `x**2` is glibc pow(x, 2.0), 0.52 ulp and not always x*x ('oracle').  The device has no
+// glibc, so the strict flavour squares by multiplication there; the host build of the same source
+// (tests/hostcheck/kernel_host.cpp, bit-compared with the reference's trajectories) calls pow as the reference does.
+#if defined(RAPT_HOST_BUILD) && RAPT_STRICT
+#define RAPT_SQ(x) pow((x), 2.0)
+#else
+#define RAPT_SQ(x) ((x) * (x))
+#endif
+
 #include "rapt_types.h"
 
 namespace RAPT_NS {

@@ -146,7 +146,7 @@ RAPT_DEV void gc_rhs(const FieldP &f, const GcConst &c, int eom, int equatorial,
     grad_and_curl<F>(f, t, tf, Y[0], Y[1], Y[2], gB, cb);
     if (eom == 0) {
         const double pm = ppar / (m * RAPT_C_LIGHT);
-        const double gamma = sqrt(1 + 2 * mu * Bmag / (m * RAPT_C_LIGHT * RAPT_C_LIGHT) + pm * pm);
+        const double gamma = sqrt(1 + 2 * mu * Bmag / (m * RAPT_C_LIGHT * RAPT_C_LIGHT) + RAPT_SQ(pm));
         const double Bsx = bx + ppar * cb[0] / q, Bsy = by + ppar * cb[1] / q, Bsz = bz + ppar * cb[2] / q;
         const double Bsp = dot3(Bsx, Bsy, Bsz, ux, uy, uz);
         double ex = 0, ey = 0, ez = 0, dbx = 0, dby = 0, dbz = 0;
@@ -163,7 +163,7 @@ RAPT_DEV void gc_rhs(const FieldP &f, const GcConst &c, int eom, int equatorial,
         out[3] = q * dot3(Esx, Esy, Esz, Bsx, Bsy, Bsz) / Bsp;
     } else if (eom == 1) {
         const double vc = c.v / RAPT_C_LIGHT;
-        const double gamma = 1.0 / sqrt(1 - vc * vc);
+        const double gamma = 1.0 / sqrt(1 - RAPT_SQ(vc));
         const double Bsx = bx + ppar * cb[0] / q, Bsy = by + ppar * cb[1] / q, Bsz = bz + ppar * cb[2] / q;
         const double Bsp = dot3(Bsx, Bsy, Bsz, ux, uy, uz);
         const double cx = uy * gB[2] - uz * gB[1], cy = uz * gB[0] - ux * gB[2], cz = ux * gB[1] - uy * gB[0];
@@ -174,10 +174,10 @@ RAPT_DEV void gc_rhs(const FieldP &f, const GcConst &c, int eom, int equatorial,
         out[3] = -mu * dot3(Bsx, Bsy, Bsz, gB[0], gB[1], gB[2]) / (gamma * Bsp);
     } else {
         const double vc = c.v / RAPT_C_LIGHT;
-        const double gamma = 1.0 / sqrt(1 - vc * vc);
+        const double gamma = 1.0 / sqrt(1 - RAPT_SQ(vc));
         const double gm = gamma * m;
         const double cx = uy * gB[2] - uz * gB[1], cy = uz * gB[0] - ux * gB[2], cz = ux * gB[1] - uy * gB[0];
-        const double s = (gm * (c.v * c.v) + ppar * ppar / gm) / (2 * q * (Bmag * Bmag));
+        const double s = (gm * RAPT_SQ(c.v) + RAPT_SQ(ppar) / gm) / (2 * q * RAPT_SQ(Bmag));
         out[0] = s * cx + ppar * ux / gm;
         out[1] = s * cy + ppar * uy / gm;
         out[2] = s * cz + ppar * uz / gm;

@@ -33,6 +33,9 @@ static inline double __hiloint2double(int hi, int lo)
     return __longlong_as_double(((long long)hi << 32) | (long long)(unsigned)lo);
 }
 template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned __ballot_sync(unsigned, int pred) { return pred ? 1u : 0u; }   // a "warp" of one lane
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline void __syncthreads() {}
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }   // work queue
 using std::min; using std::max;
 using std::fabs; using std::fmax; using std::fmin; using std::sqrt; using std::fma; using std::rint;

@@ -6,16 +6,28 @@
 // bookkeeping and Nystrom-form arithmetic are checked in the CPU-only test run as well.  Differences from the device
 // build: MUFU seeds are 23-bit truncations of the exact value, FMA contraction is g++'s (-ffp-contract=fast -mfma).
 // Nothing in rapt_b200/ loads this library and it is not part of librapt_b200.so; the product has no CPU path.
+// Built twice (Makefile): libkernelhost.so = fast flavour (-ffp-contract=fast, as nvcc contracts that flavour);
+// libkernelhost_strict.so = -DHC_STRICT, the strict flavour (-ffp-contract=off, as nvcc -fmad=false), whose operation
+// order is the reference's: its trajectories are compared BIT FOR BIT with the goldens.
 #include "cuda_shim.h"
+#ifdef HC_STRICT
+#define RAPT_STRICT 1
+#else
 #define RAPT_STRICT 0
-#define RAPT_NS rapt_hostfast
+#endif
+#define RAPT_NS rapt_hostkernels
 #include "../../include/rapt_b200.h"
+#include "../../rapt_b200/csrc/rapt_particle.cuh"
+#if !RAPT_STRICT
 #include "../../rapt_b200/csrc/rapt_particle_rkn.cuh"
+#endif
 #include "../../rapt_b200/csrc/rapt_gc.cuh"
+#include "../../rapt_b200/csrc/rapt_aux.cuh"
 #include <omp.h>
+#include <vector>
 
-namespace rapt_hostfast { double rapt_grid_cache[1]; }
-using namespace rapt_hostfast;
+namespace rapt_hostkernels { double rapt_grid_cache[1]; }
+using namespace rapt_hostkernels;
 
 template <class Fn> static void run_lanes(int nthreads, Fn body)
 {
@@ -25,8 +37,10 @@ template <class Fn> static void run_lanes(int nthreads, Fn body)
 
 template <int KIND> static void go_particle(const rapt::AdvArgs &a, int rkn, int nthreads)
 {
-    if (rkn) run_lanes(nthreads, [&] { k_particle_rkn<Field<KIND>>(a); });
-    else run_lanes(nthreads, [&] { k_particle_dop853<Field<KIND>>(a); });
+#if !RAPT_STRICT
+    if (rkn) { run_lanes(nthreads, [&] { k_particle_rkn<Field<KIND>>(a); }); return; }
+#endif
+    run_lanes(nthreads, [&] { k_particle_dop853<Field<KIND>>(a); });
 }
 template <int KIND> static void go_gc(const rapt::AdvArgs &a, int nthreads)
 {
@@ -54,7 +68,7 @@ int hc_particle_advance(const rapt_field_t *f, const rapt_params_t *p, long long
                         int rkn, int nthreads)
 {
     if (f->kind < 0 || f->kind > 5) return -1;
-    if (rkn && (!f->is_static || p->enforce_equatorial)) return -2;
+    if (rkn && (!f->is_static || p->enforce_equatorial || RAPT_STRICT)) return -2;
     rapt::AdvArgs a;
     fill_common(a, f, p);
     int queue = 0;
@@ -98,6 +112,117 @@ int hc_gc_advance(const rapt_field_t *f, const rapt_params_t *p, int eom, long l
     case 5: go_gc<5>(a, nthreads); break;
     }
     return 0;
+}
+
+}  // extern "C"
+
+// AdaptiveEnsemble: the epoch loop of rapt_b200_adaptive_advance (capi.cu) over the host builds of the same three
+// kernels: [particle kernel over the particle-mode list, guiding-centre kernel over the GC-mode list] -> per-tracer
+// switch (adaptive_switch_one, the body of k_adaptive_switch) -> regroup by mode.  One slice (the library's default).
+template <int KIND> static int go_adaptive(const rapt_field_t *f, const rapt_params_t *p, long long n,
+                                           const double *x, const double *y, const double *z,
+                                           const double *vx, const double *vy, const double *vz,
+                                           const double *t0, const double *mass, const double *charge,
+                                           double gc_dt, double delta, long long store_every, long long max_rows, double *rows,
+                                           int *nstored, int *nseg, int *mode_out, double *fin, int *counters, int *status,
+                                           int *epochs_out, int nthreads)
+{
+    const bool want_rows = rows && max_rows > 0;
+    std::vector<double> ps[7], gs[7], tvar(n), rem(n), tcur(n), dtg(n, gc_dt), dtp(n), sts(n), sx(n), sdt(n);
+    for (int k = 0; k < 7; k++) { ps[k].assign(n, 0.0); gs[k].assign(n, 0.0); }
+    std::vector<int> mode(n), segtag(n), srow(n), listP(n), listG(n);
+    int counts[2] = {0, 0};
+    for (long long i = 0; i < 4 * n; i++) counters[i] = 0;
+    rapt::AdaptArgs sw;
+    memset(&sw, 0, sizeof sw);
+    memcpy(&sw.f, f, sizeof sw.f); memcpy(&sw.p, p, sizeof sw.p);
+    sw.n = n; sw.delta = delta;
+    sw.x0 = x; sw.y0 = y; sw.z0 = z; sw.vx0 = vx; sw.vy0 = vy; sw.vz0 = vz; sw.t0 = t0; sw.mass = mass; sw.charge = charge;
+    sw.pt = ps[0].data(); sw.px = ps[1].data(); sw.py = ps[2].data(); sw.pz = ps[3].data();
+    sw.ppx = ps[4].data(); sw.ppy = ps[5].data(); sw.ppz = ps[6].data();
+    sw.gt = gs[0].data(); sw.gx = gs[1].data(); sw.gy = gs[2].data(); sw.gz = gs[3].data();
+    sw.gpp = gs[4].data(); sw.mu = gs[5].data(); sw.v = gs[6].data();
+    sw.mode = mode.data(); sw.status = status; sw.nseg = nseg; sw.segtag = segtag.data(); sw.nstored = nstored;
+    sw.tvar = tvar.data(); sw.rem = rem.data(); sw.tcur = tcur.data();
+    sw.max_rows = want_rows ? max_rows : 0; sw.rows = want_rows ? rows : nullptr;
+    sw.listP = listP.data(); sw.listG = listG.data(); sw.counts = counts;
+    sw.seg_tstop = sts.data(); sw.seg_x = sx.data(); sw.seg_dt = sdt.data(); sw.seg_row = srow.data();
+    auto do_switch = [&](int first) {
+        sw.first = first;
+        counts[0] = counts[1] = 0;
+        for (long long i = 0; i < n; i++) {
+            const int want = adaptive_switch_one<Field<KIND>>(sw, i);
+            if (want == 0) listP[counts[0]++] = (int)i;
+            if (want == 1) listG[counts[1]++] = (int)i;
+        }
+    };
+    do_switch(1);
+    rapt_params_t pc = *p;
+    pc.check_adiabaticity = 1;
+    double tmin = t0[0];
+    for (long long i = 1; i < n; i++) tmin = std::min(tmin, t0[i]);
+    const double slice_end = tmin + (delta > 0 ? delta : 1.0);
+    int epochs = 0;
+    for (;; epochs++) {
+        if (counts[0] == 0 && counts[1] == 0) break;
+        if (epochs > 100000) return -3;
+        const int cnt[2] = {counts[0], counts[1]};
+        const bool rkn = !RAPT_STRICT && f->is_static && !p->enforce_equatorial;
+        if (cnt[0] > 0) {
+            rapt::AdvArgs a;
+            fill_common(a, f, &pc);
+            int queue = 0;
+            a.nwork = cnt[0]; a.order = sw.listP; a.queue = &queue;
+            a.t = sw.pt; a.s1 = sw.px; a.s2 = sw.py; a.s3 = sw.pz; a.s4 = sw.ppx; a.s5 = sw.ppy; a.s6 = sw.ppz;
+            a.mass = sw.mass; a.charge = sw.charge; a.delta = 0; a.delta_arr = sw.rem;
+            a.store_every = want_rows ? std::max<long long>(store_every, 1) : 0; a.max_rows = sw.max_rows; a.rows = sw.rows;
+            a.nstored = sw.nstored; a.nrows = nullptr; a.counters = counters; a.status = sw.status;
+            a.tcur = sw.tcur; a.dt_out = dtp.data(); a.segtag = sw.segtag; a.append = 1;
+            a.seg_tstop = sw.seg_tstop; a.seg_x = sw.seg_x; a.seg_dt = sw.seg_dt; a.seg_row = sw.seg_row; a.slice_end = slice_end;
+            go_particle<KIND>(a, rkn, nthreads);
+        }
+        if (cnt[1] > 0) {
+            rapt::AdvArgs a;
+            fill_common(a, f, &pc);
+            int queue = 0;
+            a.nwork = cnt[1]; a.order = sw.listG; a.queue = &queue;
+            a.t = sw.gt; a.s1 = sw.gx; a.s2 = sw.gy; a.s3 = sw.gz; a.s4 = sw.gpp;
+            a.mass = sw.mass; a.charge = sw.charge; a.mu = sw.mu; a.v = sw.v; a.dtin = dtg.data();
+            a.delta = 0; a.delta_arr = sw.rem; a.eom = RAPT_EOM_TAOCHANBRIZARD;
+            a.store_every = want_rows ? std::max<long long>(store_every, 1) : 0; a.max_rows = sw.max_rows; a.rows = sw.rows;
+            a.nstored = sw.nstored; a.nrows = nullptr; a.counters = counters; a.status = sw.status;
+            a.tcur = sw.tcur; a.segtag = sw.segtag; a.append = 1;
+            a.seg_tstop = sw.seg_tstop; a.seg_x = sw.seg_x; a.seg_dt = sw.seg_dt; a.seg_row = sw.seg_row; a.slice_end = slice_end;
+            go_gc<KIND>(a, nthreads);
+        }
+        do_switch(0);
+    }
+    if (epochs_out) *epochs_out = epochs;
+    for (long long i = 0; i < n; i++) {
+        if (mode_out) mode_out[i] = mode[i];
+        if (fin) {
+            double *o = fin + 8 * i;
+            if (mode[i] == 0) { for (int k = 0; k < 7; k++) o[k] = ps[k][i]; o[7] = 0; }
+            else { for (int k = 0; k < 5; k++) o[k] = gs[k][i]; o[5] = gs[5][i]; o[6] = gs[6][i]; o[7] = 1; }
+        }
+    }
+    return 0;
+}
+
+extern "C" {
+
+int hc_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, long long n,
+                        const double *x, const double *y, const double *z, const double *vx, const double *vy, const double *vz,
+                        const double *t0, const double *mass, const double *charge,
+                        double gc_dt, double delta, long long store_every, long long max_rows, double *rows,
+                        int *nstored, int *nseg, int *mode_out, double *fin, int *counters, int *status, int *epochs_out,
+                        int nthreads)
+{
+#define HC_ADAPT(K) case K: return go_adaptive<K>(f, p, n, x, y, z, vx, vy, vz, t0, mass, charge, gc_dt, delta, store_every, \
+                                                  max_rows, rows, nstored, nseg, mode_out, fin, counters, status, epochs_out, nthreads);
+    switch (f->kind) { HC_ADAPT(0) HC_ADAPT(1) HC_ADAPT(2) HC_ADAPT(3) HC_ADAPT(4) HC_ADAPT(5) }
+#undef HC_ADAPT
+    return -1;
 }
 
 }  // extern "C"

@@ -6,15 +6,15 @@ import numpy as np
 from rapt_b200 import engine
 from rapt_b200._lib import EOM_KIND, ptr
 
-_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcheck", "libkernelhost.so")
-_lib = None
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcheck")
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(_PATH)
-    return _lib
+def lib(arith="fast"):
+    """fast: libkernelhost.so (FMA contraction on); strict: libkernelhost_strict.so (the reference's operation order)."""
+    if arith not in _libs:
+        _libs[arith] = C.CDLL(os.path.join(_DIR, "libkernelhost_strict.so" if arith == "strict" else "libkernelhost.so"))
+    return _libs[arith]
 
 
 def _col(a, n):
@@ -22,9 +22,9 @@ def _col(a, n):
 
 
 def particle_advance(field, state, mass, charge, delta, store_every=1, max_rows=0, rkn=True, nthreads=4,
-                     check_adiabaticity=False, **over):
+                     check_adiabaticity=False, arith="fast", **over):
     f = engine._field_desc(field)
-    p = engine.snapshot_params(None, check_adiabaticity, **over)
+    p = engine.snapshot_params(None, check_adiabaticity, arith=arith, **over)
     st = np.asarray(state, dtype=np.float64).reshape(-1, 7)
     n = len(st)
     cols = [np.ascontiguousarray(st[:, i]).copy() for i in range(7)]
@@ -33,7 +33,7 @@ def particle_advance(field, state, mass, charge, delta, store_every=1, max_rows=
     rows = np.zeros((n, max_rows, 8)) if want else None
     nrows = np.zeros(n, np.int32); nstored = np.zeros(n, np.int32); counters = np.zeros((n, 4), np.int32)
     status = np.zeros(n, np.int32); tcur = np.zeros(n); dt = np.zeros(n)
-    rc = lib().hc_particle_advance(
+    rc = lib(arith).hc_particle_advance(
         C.byref(f), C.byref(p), C.c_longlong(n), *[ptr(c_) for c_ in cols], ptr(mass), ptr(charge), C.c_double(delta),
         C.c_longlong(store_every), C.c_longlong(max_rows), ptr(rows), ptr(nrows), ptr(nstored), ptr(counters),
         ptr(status), ptr(tcur), ptr(dt), C.c_int(1 if rkn else 0), C.c_int(nthreads))
@@ -43,9 +43,9 @@ def particle_advance(field, state, mass, charge, delta, store_every=1, max_rows=
 
 
 def gc_advance(field, state, mu, v, mass, charge, dt, delta, eom="TaoChanBrizardEOM", store_every=1, max_rows=0,
-               nthreads=4, check_adiabaticity=False, **over):
+               nthreads=4, check_adiabaticity=False, arith="fast", **over):
     f = engine._field_desc(field)
-    p = engine.snapshot_params(None, check_adiabaticity, **over)
+    p = engine.snapshot_params(None, check_adiabaticity, arith=arith, **over)
     st = np.asarray(state, dtype=np.float64).reshape(-1, 5)
     n = len(st)
     cols = [np.ascontiguousarray(st[:, i]).copy() for i in range(5)]
@@ -54,7 +54,7 @@ def gc_advance(field, state, mu, v, mass, charge, dt, delta, eom="TaoChanBrizard
     rows = np.zeros((n, max_rows, 8)) if want else None
     nrows = np.zeros(n, np.int32); nstored = np.zeros(n, np.int32); counters = np.zeros((n, 4), np.int32)
     status = np.zeros(n, np.int32); tcur = np.zeros(n)
-    rc = lib().hc_gc_advance(
+    rc = lib(arith).hc_gc_advance(
         C.byref(f), C.byref(p), C.c_int(EOM_KIND[eom]), C.c_longlong(n), *[ptr(c_) for c_ in cols],
         ptr(mu), ptr(v), ptr(mass), ptr(charge), ptr(dt), C.c_double(delta),
         C.c_longlong(store_every), C.c_longlong(max_rows), ptr(rows), ptr(nrows), ptr(nstored), ptr(counters),
@@ -62,3 +62,25 @@ def gc_advance(field, state, mu, v, mass, charge, dt, delta, eom="TaoChanBrizard
     assert rc == 0, rc
     return dict(state=np.column_stack(cols), rows=rows, nrows=nrows, nstored=nstored, counters=counters,
                 status=status, tcur=tcur, dt=dt)
+
+
+def adaptive_advance(field, pos, vel, t0, mass, charge, delta, gc_dt, store_every=1, max_rows=0, nthreads=4,
+                     arith="fast", **over):
+    """Same arguments and result dict as rapt_b200.engine.adaptive_advance."""
+    f = engine._field_desc(field)
+    p = engine.snapshot_params(None, True, arith=arith, **over)
+    pos = np.asarray(pos, dtype=np.float64).reshape(-1, 3); vel = np.asarray(vel, dtype=np.float64).reshape(-1, 3)
+    n = len(pos)
+    cols = [np.ascontiguousarray(pos[:, i]).copy() for i in range(3)] + [np.ascontiguousarray(vel[:, i]).copy() for i in range(3)]
+    t0, mass, charge = _col(t0, n), _col(mass, n), _col(charge, n)
+    rows = np.zeros((n, max_rows, 8)) if max_rows > 0 else None
+    nstored = np.zeros(n, np.int32); nseg = np.zeros(n, np.int32); mode = np.zeros(n, np.int32)
+    fin = np.zeros((n, 8)); counters = np.zeros((n, 4), np.int32); status = np.zeros(n, np.int32)
+    epochs = C.c_int32(0)
+    rc = lib(arith).hc_adaptive_advance(
+        C.byref(f), C.byref(p), C.c_longlong(n), *[ptr(c_) for c_ in cols], ptr(t0), ptr(mass), ptr(charge),
+        C.c_double(gc_dt), C.c_double(delta), C.c_longlong(store_every), C.c_longlong(max_rows), ptr(rows),
+        ptr(nstored), ptr(nseg), ptr(mode), ptr(fin), ptr(counters), ptr(status), C.byref(epochs), C.c_int(nthreads))
+    assert rc == 0, rc
+    return dict(rows=rows, nstored=nstored, nseg=nseg, mode=mode, final=fin, counters=counters, status=status,
+                epochs=epochs.value)

@@ -132,3 +132,167 @@ def test_gc_kernel_source_config3_vs_oracle():
     assert np.max(np.abs(g["state"][:, 4] - r["state"][:, 4])) < 1e-8 * np.max(np.abs(r["state"][:, 4]))
     same = np.all(g["counters"] == r["counters"], axis=1)
     assert same.mean() > 0.98, f"only {same.mean():.4f} of guiding centres match counts"
+
+
+# ---- strict flavour: the kernel source executes the reference's operation order; compiled for the host (g++
+# -ffp-contract=off, glibc pow/sin as the reference's numpy uses) it reproduces the reference's trajectories BIT FOR BIT.
+# (On the B200 the same source differs in the last bits through CUDA's libm: tests/test_gpu_particle.py.)
+
+@pytest.mark.parametrize("name", list(H.PARTICLE_CASES))
+def test_strict_particle_kernel_source_is_bit_identical_to_the_reference(name):
+    d, par = H.load(name)
+    fname, fargs = H.PARTICLE_CASES[name]
+    traj = d["traj"]
+    o = K.particle_advance(H.gpu_field(fname, fargs), traj[0], float(d["mass"]), float(d["charge"]), float(d["delta"]),
+                           store_every=1, max_rows=len(traj) + 8, rkn=False, nthreads=1, arith="strict", **par)
+    n = int(o["nstored"][0])
+    assert n == len(traj) == o["nrows"][0] and o["status"][0] == 1
+    assert np.array_equal(o["rows"][0, :n, :7], traj), "every row of the trajectory, all 7 columns, same bits"
+    assert tuple(o["counters"][0]) == tuple(d["counters"].sum(0))
+    assert np.array_equal(o["rows"][0, 1:n, 7].astype(np.int64), np.cumsum(d["counters"][:, 1]))
+    assert o["tcur"][0] == float(d["tcur"])
+
+
+@pytest.mark.parametrize("name", list(H.GC_CASES))
+def test_strict_gc_kernel_source_is_bit_identical_to_the_reference(name):
+    d, par = H.load(name)
+    fname, fargs = H.GC_CASES[name]
+    traj = d["traj"]
+    dt = float(d["bs_period"]) / par.get("bounceresolution", 10) if "bs_period" in d.files else par["GCtimestep"]
+    eom = str(d["eom"]) if "eom" in d.files else "TaoChanBrizardEOM"
+    gpar = {k: v_ for k, v_ in par.items() if k in ("solvertolerances", "enforce equatorial")}
+    o = K.gc_advance(H.gpu_field(fname, fargs), traj[0, :5], float(d["mu"]), float(d["v"]), float(d["mass"]),
+                     float(d["charge"]), dt, float(d["delta"]), eom=eom, store_every=1, max_rows=len(traj) + 8,
+                     nthreads=1, arith="strict", **gpar)
+    n = int(o["nstored"][0])
+    assert n == len(traj) == o["nrows"][0] and o["status"][0] == 1
+    assert np.array_equal(o["rows"][0, :n, :5], traj[:, :5]), "every row (t, X, Y, Z, p_par), same bits"
+    assert tuple(o["counters"][0]) == tuple(d["counters"].sum(0))
+
+
+def test_strict_kernel_source_equals_oracle_on_an_ensemble():
+    """256 protons of config 2 and 64 electrons of config 3: strict kernel source on the host == oracle, bit for bit."""
+    import oracle as O
+    from rapt_b200 import engine, synth
+    ic = synth.config2_protons(256)
+    vel = np.column_stack([ic["vx"], ic["vy"], ic["vz"]])
+    st = np.column_stack([ic["t0"], ic["x"], ic["y"], ic["z"], engine.particle_momentum(vel, ic["mass"])])
+    par = dict(cyclotronresolution=20)
+    ref = O.particle_advance(O.make_field("EarthDipole"), O.make_params(**par), st, ic["mass"], ic["charge"], 0.25,
+                             store_every=5, max_rows=64, nthreads=8)
+    o = K.particle_advance(H.gpu_field("EarthDipole", ()), st, ic["mass"], ic["charge"], 0.25, store_every=5, max_rows=64,
+                           rkn=False, nthreads=8, arith="strict", **par)
+    for k in ("state", "nrows", "nstored", "counters", "status"):
+        assert np.array_equal(o[k], ref[k]), k
+    for i in range(256):
+        assert np.array_equal(o["rows"][i, :o["nstored"][i], :7], ref["rows"][i, :ref["nstored"][i], :7])
+    ic3 = synth.config3_electrons(64)
+    pos = np.column_stack([ic3["x"], ic3["y"], ic3["z"]])
+    of = O.make_field("DoubleDipole")
+    ppar, mu3 = O.gc_construct(of, ic3["t0"], pos, ic3["v"], ic3["pa"], ic3["mass"])
+    st3 = np.column_stack([ic3["t0"], pos, ppar])
+    r = O.gc_advance(of, O.make_params(), st3, mu3, ic3["v"], ic3["mass"], ic3["charge"], 0.1, 1.0, store_every=0, nthreads=8)
+    g = K.gc_advance(H.gpu_field("DoubleDipole", ()), st3, mu3, ic3["v"], ic3["mass"], ic3["charge"], 0.1, 1.0,
+                     store_every=0, nthreads=8, arith="strict")
+    for k in ("state", "nrows", "counters", "status"):
+        assert np.array_equal(g[k], r[k]), k
+    # time-dependent field, adiabaticity predicate evaluated after every row, the other two equations of motion
+    ic5 = synth.config5_belt(64)
+    pos = np.column_stack([ic5["x"], ic5["y"], ic5["z"]])
+    of = O.make_field("VarEarthDipole", 0.1, 10)
+    ppar, mu = O.gc_construct(of, ic5["t0"], pos, ic5["v"], ic5["pa"], ic5["mass"])
+    st5 = np.column_stack([ic5["t0"], pos, ppar])
+    r = O.gc_advance(of, O.make_params(), st5, mu, ic5["v"], ic5["mass"], ic5["charge"], 0.05, 0.5, check_adiab=True,
+                     store_every=0, nthreads=8)
+    g = K.gc_advance(H.gpu_field("VarEarthDipole", (0.1, 10)), st5, mu, ic5["v"], ic5["mass"], ic5["charge"], 0.05, 0.5,
+                     store_every=0, nthreads=8, arith="strict", check_adiabaticity=True)
+    for k in ("state", "nrows", "counters", "status"):
+        assert np.array_equal(g[k], r[k]), k
+    of = O.make_field("DoubleDipole")
+    for eom in ("BrizardChanEOM", "NorthropTellerEOM"):
+        r = O.gc_advance(of, O.make_params(), st3, mu3, ic3["v"], ic3["mass"], ic3["charge"], 0.1, 0.5, eom=eom, store_every=0, nthreads=8)
+        g = K.gc_advance(H.gpu_field("DoubleDipole", ()), st3, mu3, ic3["v"], ic3["mass"], ic3["charge"], 0.1, 0.5, eom=eom,
+                         store_every=0, nthreads=8, arith="strict")
+        for k in ("state", "nrows", "counters", "status"):
+            assert np.array_equal(g[k], r[k]), (eom, k)
+
+
+# ---- Adaptive: the epoch loop of rapt_b200_adaptive_advance over the host builds of the three kernels
+# (particle / guiding-centre advance with the adiabaticity predicate, per-tracer switch = the body of k_adaptive_switch)
+
+SPEISER = ["g3_speiser", "e4_speiser_1", "e4_speiser_2", "e4_speiser_3", "e4_speiser_4", "e4_speiser_5"]
+
+
+def _segments(rows):
+    tags = rows[:, 7].astype(int)
+    return [(int(t & 1), rows[tags == t]) for t in sorted(set(tags))]
+
+
+def _ref_segments(d):
+    rows, out, k = d["rows"], [], 0
+    for m, n in zip(d["seg_mode"], d["seg_nrows"]):
+        out.append((int(m), rows[k:k + n])); k += n
+    return out
+
+
+@pytest.mark.parametrize("name", SPEISER)
+def test_strict_adaptive_kernel_source_is_bit_identical_to_the_reference(name):
+    """Every row of every segment of the reference's Adaptive trajectory (the chaotic Speiser orbit of the notebook
+    included: 1990 rows, switches at t = 168.0 and 271.5378...), same bits."""
+    d, par = H.load(name)
+    ref = _ref_segments(d)
+    o = K.adaptive_advance(H.gpu_field(*H.ADAPTIVE_CASES[name]), d["pos"], d["vel"], 0.0, float(d["mass"]), float(d["charge"]),
+                           float(d["delta"]), par["GCtimestep"], store_every=1, max_rows=len(d["rows"]) + 64, arith="strict",
+                           nthreads=1, solvertolerances=par["solvertolerances"], epss=par["epss"])
+    assert o["status"][0] == 1 and o["nseg"][0] == len(ref) and o["nstored"][0] == len(d["rows"])
+    segs = _segments(o["rows"][0, :o["nstored"][0]])
+    assert [m for m, _ in segs] == [m for m, _ in ref]
+    for (m, r), (_, g) in zip(segs, ref):
+        ncol = 7 if m == 0 else 5
+        assert np.array_equal(r[:, :ncol], g[:, :ncol])
+
+
+@pytest.mark.parametrize("name", SPEISER)
+def test_fast_adaptive_kernel_source_vs_reference(name):
+    """The fast flavour (the Nystrom-form particle kernel inside the epochs), bars of tests/test_gpu_adaptive.py."""
+    d, par = H.load(name)
+    ref = _ref_segments(d)
+    o = K.adaptive_advance(H.gpu_field(*H.ADAPTIVE_CASES[name]), d["pos"], d["vel"], 0.0, float(d["mass"]), float(d["charge"]),
+                           float(d["delta"]), par["GCtimestep"], store_every=1, max_rows=len(d["rows"]) + 64, arith="fast",
+                           nthreads=1, solvertolerances=par["solvertolerances"], epss=par["epss"])
+    assert o["status"][0] == 1 and o["nseg"][0] == len(ref)
+    segs = _segments(o["rows"][0, :o["nstored"][0]])
+    assert [m for m, _ in segs] == [m for m, _ in ref]
+    m0, r0 = segs[0]; _, g0 = ref[0]
+    assert len(r0) == len(g0)
+    ncol = 7 if m0 == 0 else 5
+    assert np.max(np.abs(r0[:, :ncol] - g0[:, :ncol]) / (np.abs(g0[:, :ncol]) + 1e-3)) < 1e-8
+    t_sw = np.array([s[1][0, 0] for s in segs]); t_ref = np.array([s[1][0, 0] for s in ref])
+    assert np.max(np.abs(t_sw - t_ref)) < 1e-7 * max(1.0, np.max(np.abs(t_ref)))
+    for (m, r), (mr, g) in zip(segs, ref):
+        assert abs(len(r) - len(g)) <= 2
+    fin = o["final"][0]; gl = ref[-1][1][-1]
+    assert abs(fin[0] - gl[0]) < 1e-6
+    assert np.linalg.norm(fin[1:4] - gl[1:4]) / np.linalg.norm(gl[1:4]) < 1e-5
+    if name == "g3_speiser":
+        assert t_sw[1] == 168.0 and abs(t_sw[2] - 271.537802289) < 1e-7      # the notebook-stored answers
+
+
+def test_adaptive_kernel_source_ensemble_vs_oracle():
+    """64 Speiser tracers of config 4 in one epoch loop (mixed modes per epoch) vs the oracle, strict: same bits."""
+    import oracle as O
+    from rapt_b200 import synth
+    n = 64
+    ic = synth.config4_speiser(n)
+    pos = np.column_stack([ic["x"], ic["y"], ic["z"]]); vel = np.column_stack([ic["vx"], ic["vy"], ic["vz"]])
+    par = dict(solvertolerances=(1e-12, 1e-12), epss=0.02)
+    o = K.adaptive_advance(H.gpu_field("Parabolic", ()), pos, vel, 0.0, 1.0, 1.0, 200.0, 1.0, store_every=1,
+                           max_rows=2048, arith="strict", nthreads=8, **par)
+    assert np.all(o["status"] == 1) and o["epochs"] >= 2
+    of = O.make_field("Parabolic"); op = O.make_params(GCtimestep=1, **par)
+    for i in range(n):
+        nseg, rows, seglog, cnt = O.adaptive_c(of, op, pos[i], vel[i], 0.0, 1.0, 1.0, 200.0)
+        mine = o["rows"][i, :o["nstored"][i]]
+        assert o["nseg"][i] == nseg and len(mine) == len(rows), i
+        assert np.array_equal(mine[:, 0], rows[:, 0]), i                     # every row label
+        assert np.array_equal(mine[:, 1:4], rows[:, 1:4]), i                 # every position
