@@ -22,13 +22,13 @@ namespace RAPT_NS {
 using rapt::ParamsP;
 using rapt::AdvArgs;
 
-// |B| and b at one point.  tf: time factor of a separable field (already evaluated by the caller).
+// |B| and b at one point.  tf: time factor (times the field's constant) of a separable field, evaluated once by the caller.
 template <class F>
 RAPT_DEV void mag_and_unit(const FieldP &f, double t, double tf, double x, double y, double z,
                            double &m, double &ux, double &uy, double &uz)
 {
     double bx, by, bz;
-    if (F::SEPARABLE) { F::Bspace(f, x, y, z, bx, by, bz); bx *= tf; by *= tf; bz *= tf; }
+    if (F::SEPARABLE) F::Bspace(f, tf, x, y, z, bx, by, bz);
     else F::B(f, t, x, y, z, bx, by, bz);
 #if RAPT_STRICT
     m = sqrt(dot3(bx, by, bz, bx, by, bz));
@@ -85,7 +85,7 @@ RAPT_DEV void gc_rhs(const FieldP &f, const GcConst &c, int eom, int equatorial,
     const double m = c.mass, q = c.q, mu = c.mu, ppar = Y[3];
     double bx, by, bz, gB[3], cb[3];
     double tf = 1.0;
-    if (F::SEPARABLE) { tf = F::tfactor(f, t); F::Bspace(f, Y[0], Y[1], Y[2], bx, by, bz); bx *= tf; by *= tf; bz *= tf; }
+    if (F::SEPARABLE) { tf = F::tfactor(f, t); F::Bspace(f, tf, Y[0], Y[1], Y[2], bx, by, bz); }
     else F::B(f, t, Y[0], Y[1], Y[2], bx, by, bz);
 #if !RAPT_STRICT
     // fast flavour: one rsqrt for |B| and b, reciprocals instead of divisions

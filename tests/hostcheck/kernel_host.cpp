@@ -209,7 +209,45 @@ template <int KIND> static int go_adaptive(const rapt_field_t *f, const rapt_par
     return 0;
 }
 
+// k_field_ops (the _Field operator layer, fields.py:76-280), one "thread" per point
+template <int KIND> static void go_field_ops(rapt::OpsArgs a)
+{
+    // the kernel reads blockIdx.x * blockDim.x + threadIdx.x: present one point per call through a one-element view
+    const long long n = a.n;
+    double *outs[12] = {a.B, a.E, a.unitb, a.magB, a.gradB, a.jac, a.curlb, a.curv, a.dBdt, a.dbdt, a.lscale, a.tscale};
+    const int width[12] = {3, 3, 3, 1, 3, 9, 3, 1, 1, 3, 1, 1};
+    for (long long i = 0; i < n; i++) {
+        rapt::OpsArgs b = a;
+        b.n = 1; b.tpos = a.tpos + 4 * i;
+        double **dst[12] = {&b.B, &b.E, &b.unitb, &b.magB, &b.gradB, &b.jac, &b.curlb, &b.curv, &b.dBdt, &b.dbdt, &b.lscale, &b.tscale};
+        for (int k = 0; k < 12; k++) *dst[k] = outs[k] ? outs[k] + (long long)width[k] * i : nullptr;
+        k_field_ops<Field<KIND>>(b);
+    }
+}
+
 extern "C" {
+
+int hc_field_ops(const rapt_field_t *f, long long npt, const double *tpos,
+                 double *B, double *E, double *unitb, double *magB, double *gradB, double *jacobianB,
+                 double *curlb, double *curvature, double *dBdt, double *dbdt, double *lengthscale, double *timescale)
+{
+    rapt::OpsArgs a;
+    memset(&a, 0, sizeof a);
+    memcpy(&a.f, f, sizeof a.f);
+    a.n = npt; a.tpos = tpos;
+    a.B = B; a.E = E; a.unitb = unitb; a.magB = magB; a.gradB = gradB; a.jac = jacobianB; a.curlb = curlb; a.curv = curvature;
+    a.dBdt = dBdt; a.dbdt = dbdt; a.lscale = lengthscale; a.tscale = timescale;
+    switch (f->kind) {
+    case 0: go_field_ops<0>(a); break;
+    case 1: go_field_ops<1>(a); break;
+    case 2: go_field_ops<2>(a); break;
+    case 3: go_field_ops<3>(a); break;
+    case 4: go_field_ops<4>(a); break;
+    case 5: go_field_ops<5>(a); break;
+    default: return -1;
+    }
+    return 0;
+}
 
 int hc_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, long long n,
                         const double *x, const double *y, const double *z, const double *vx, const double *vy, const double *vz,

@@ -84,3 +84,18 @@ def adaptive_advance(field, pos, vel, t0, mass, charge, delta, gc_dt, store_ever
     assert rc == 0, rc
     return dict(rows=rows, nstored=nstored, nseg=nseg, mode=mode, final=fin, counters=counters, status=status,
                 epochs=epochs.value)
+
+
+def field_ops(field, tpos, arith="strict", which=None):
+    """Same arguments and result dict as rapt_b200.engine.field_ops (k_field_ops on the host)."""
+    f = engine._field_desc(field)
+    tpos = np.ascontiguousarray(np.asarray(tpos, dtype=np.float64).reshape(-1, 4))
+    n = len(tpos)
+    shapes = dict(B=(n, 3), E=(n, 3), unitb=(n, 3), magB=(n,), gradB=(n, 3), jacobianB=(n, 3, 3), curlb=(n, 3),
+                  curvature=(n,), dBdt=(n,), dbdt=(n, 3), lengthscale=(n,), timescale=(n,))
+    names = list(shapes)
+    which = names if which is None else list(which)
+    out = {k: (np.zeros(shapes[k]) if k in which else None) for k in names}
+    rc = lib(arith).hc_field_ops(C.byref(f), C.c_longlong(n), ptr(tpos), *[ptr(out[k]) for k in names])
+    assert rc == 0, rc
+    return {k: v for k, v in out.items() if v is not None}

@@ -296,3 +296,36 @@ def test_adaptive_kernel_source_ensemble_vs_oracle():
         assert o["nseg"][i] == nseg and len(mine) == len(rows), i
         assert np.array_equal(mine[:, 0], rows[:, 0]), i                     # every row label
         assert np.array_equal(mine[:, 1:4], rows[:, 1:4]), i                 # every position
+
+
+# ---- the _Field operator layer (k_field_ops): golden values from the reference at seeded points
+
+FIELD_OPS = {"earthdipole": ("EarthDipole", ()), "doubledipole": ("DoubleDipole", ()), "uniformbz": ("UniformBz", (2e-4,)),
+             "crossedeb": ("UniformCrossedEB", (2.0, 1e-4)), "vardipole": ("VarEarthDipole", (0.1, 10)),
+             "parabolic": ("Parabolic", ())}
+
+
+@pytest.mark.parametrize("name", list(FIELD_OPS))
+def test_strict_field_operators_source_is_bit_identical_to_the_reference(name):
+    u = np.load(H.GOLDEN + "/units.npz")
+    o = K.field_ops(H.gpu_field(*FIELD_OPS[name]), u[name + "_pts"], arith="strict")
+    for k in ("B", "E", "unitb", "magB", "gradB", "curlb", "jacobianB", "dBdt", "dbdt", "lengthscale", "curvature"):
+        g = u[f"{name}_{k}"]
+        assert np.array_equal(o[k], g, equal_nan=True), k
+
+
+@pytest.mark.parametrize("name", list(FIELD_OPS))
+def test_fast_field_operators_source_vs_reference(name):
+    """Bars of tests/test_gpu_gc.py::test_field_ops_vs_reference for the fast flavour."""
+    u = np.load(H.GOLDEN + "/units.npz")
+    o = K.field_ops(H.gpu_field(*FIELD_OPS[name]), u[name + "_pts"], arith="fast")
+    for k in ("B", "E", "unitb", "magB"):
+        assert H.relerr(o[k], u[f"{name}_{k}"], floor=1e-300) < 1e-13, k
+    d = H.gpu_field(*FIELD_OPS[name]).gradientstepsize
+    for k in ("gradB", "curlb", "jacobianB"):
+        g = u[f"{name}_{k}"]; m = o[k]
+        scale = np.max(np.abs(g)) + 1e-300
+        noise = 1e-15 * (np.max(np.abs(u[name + "_pts"][:, 1:])) / d + 1) * 50
+        if k == "curlb" and name == "parabolic":
+            noise = 1e-9
+        assert np.max(np.abs(m - g)) / scale < max(noise, 1e-13), (k, np.max(np.abs(m - g)) / scale)
