@@ -246,3 +246,15 @@ def test_bounce_center_host_side():
         with pytest.raises(_lib.RaptB200Error, match="no CUDA device"):
             rb.engine.bounce_center_advance(f, d["traj"][0], float(d["mu"]), float(d["v"]), float(d["mass"]),
                                             float(d["charge"]), 0.1)
+
+
+def test_user_field_module_compiles_with_nvrtc_without_a_device():
+    """rapt_b200_field_nvrtc compiles the embedded kernel headers around a user snippet at registration time; NVRTC
+    needs no device, so a header that nvcc accepts but NVRTC rejects shows up here and not first on the GPU box."""
+    import userfield
+    from rapt_b200 import engine
+    CD = userfield.make_charged_dipole()
+    uid = engine.compile_user_field(CD.cuda_source, True)
+    assert uid >= 0
+    with pytest.raises(Exception, match="NVRTC"):
+        engine.compile_user_field("__device__ void rapt_user_B(double t) { this is not CUDA }", False)
