@@ -258,3 +258,12 @@ def test_user_field_module_compiles_with_nvrtc_without_a_device():
     assert uid >= 0
     with pytest.raises(Exception, match="NVRTC"):
         engine.compile_user_field("__device__ void rapt_user_B(double t) { this is not CUDA }", False)
+
+
+def test_integration_doc_covers_every_entry_point():
+    """INTEGRATION.md shows (or tabulates) the reference-side binding of every symbol the header declares."""
+    hdr = open(os.path.join(ROOT, "include", "rapt_b200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    declared = set(re.findall(r"\b(rapt_b200_[a-z0-9_]+)\s*\(", hdr))
+    missing = sorted(s for s in declared if s not in doc)
+    assert not missing, missing
