@@ -225,7 +225,49 @@ template <int KIND> static void go_field_ops(rapt::OpsArgs a)
     }
 }
 
+// k_bounce_setup (GuidingCenter.bounceperiod: field-line RKF45 trace + half-bounce path), one "thread" per guiding centre
+template <int KIND> static void go_bounce(const rapt::BounceArgs &a)
+{
+    for (long long i = 0; i < a.n; i++) {
+        rapt::BounceArgs b = a;
+        b.n = 1;
+        b.t = a.t + i; b.x = a.x + i; b.y = a.y + i; b.z = a.z + i;
+        if (a.ppar) b.ppar = a.ppar + i;
+        if (a.mu) b.mu = a.mu + i;
+        if (a.mass) b.mass = a.mass + i;
+        b.Bm = a.Bm + i; b.v = a.v + i; b.ds = a.ds + i; b.npts = a.npts + i;
+        b.curve = a.curve + i * a.max_pts * 5; b.scratch = a.scratch + i * a.max_pts * 4;
+        if (a.period) b.period = a.period + i;
+        k_bounce_setup<Field<KIND>>(b);
+    }
+}
+
 extern "C" {
+
+// rapt_b200_bounce_setup / rapt_b200_bounce_period in one: curve and/or period may be NULL
+int hc_bounce(const rapt_field_t *f, int quadrature, double fieldlineresolution, long long n,
+              const double *t, const double *x, const double *y, const double *z, const double *ppar,
+              const double *mu, const double *mass, double *Bm, double *v, double *ds, int *npts, long long max_pts,
+              double *curve, double *period)
+{
+    std::vector<double> cv, scr((size_t)n * max_pts * 4);
+    if (!curve) { cv.resize((size_t)n * max_pts * 5); curve = cv.data(); }
+    rapt::BounceArgs a;
+    memset(&a, 0, sizeof a);
+    memcpy(&a.f, f, sizeof a.f);
+    a.flres = fieldlineresolution; a.n = n; a.max_pts = max_pts;
+    a.t = t; a.x = x; a.y = y; a.z = z; a.ppar = ppar; a.mu = mu; a.mass = mass;
+    a.Bm = Bm; a.v = v; a.ds = ds; a.npts = npts; a.curve = curve; a.scratch = scr.data();
+    a.period = period; a.quadrature = quadrature;
+    switch (f->kind) {
+    case 0: go_bounce<0>(a); break;
+    case 1: go_bounce<1>(a); break;
+    case 4: go_bounce<4>(a); break;
+    case 5: go_bounce<5>(a); break;
+    default: return -1;
+    }
+    return 0;
+}
 
 int hc_field_ops(const rapt_field_t *f, long long npt, const double *tpos,
                  double *B, double *E, double *unitb, double *magB, double *gradB, double *jacobianB,

@@ -99,3 +99,20 @@ def field_ops(field, tpos, arith="strict", which=None):
     rc = lib(arith).hc_field_ops(C.byref(f), C.c_longlong(n), ptr(tpos), *[ptr(out[k]) for k in names])
     assert rc == 0, rc
     return {k: v for k, v in out.items() if v is not None}
+
+
+def bounce(field, state, mu, mass, fieldlineresolution=50.0, arith="strict", max_pts=512, quadrature=1):
+    """k_bounce_setup on the host: mirror field, speed, ds, the traced field line and the bounce period
+    (quadrature 1: brentq + QAGS as the reference, 0: closed form) of every guiding centre."""
+    f = engine._field_desc(field)
+    st = np.asarray(state, dtype=np.float64).reshape(-1, 5)
+    n = len(st)
+    cols = [np.ascontiguousarray(st[:, i]).copy() for i in range(5)]
+    mu, mass = _col(mu, n), _col(mass, n)
+    Bm = np.zeros(n); v = np.zeros(n); ds = np.zeros(n); npts = np.zeros(n, np.int32); period = np.zeros(n)
+    curve = np.zeros((n, max_pts, 5))
+    rc = lib(arith).hc_bounce(C.byref(f), C.c_int(quadrature), C.c_double(fieldlineresolution), C.c_longlong(n),
+                              *[ptr(c_) for c_ in cols], ptr(mu), ptr(mass), ptr(Bm), ptr(v), ptr(ds), ptr(npts),
+                              C.c_longlong(max_pts), ptr(curve), ptr(period))
+    assert rc == 0, rc
+    return dict(Bm=Bm, v=v, ds=ds, npts=npts, curve=curve, period=period)

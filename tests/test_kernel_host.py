@@ -329,3 +329,35 @@ def test_fast_field_operators_source_vs_reference(name):
         if k == "curlb" and name == "parabolic":
             noise = 1e-9
         assert np.max(np.abs(m - g)) / scale < max(noise, 1e-13), (k, np.max(np.abs(m - g)) / scale)
+
+
+# ---- GuidingCenter.bounceperiod set-up (k_bounce_setup: mirror field, ds from the curvature, RKF45 field-line trace,
+# half-bounce path through the spline / brentq / QAGS restatement of rapt_quad.cuh)
+
+@pytest.mark.parametrize("name", ["g2_gc_doubledipole", "gc_earthdipole"])
+def test_strict_bounce_setup_source_traces_the_reference_field_line_bit_for_bit(name):
+    d, par = H.load(name)
+    o = K.bounce(H.gpu_field(*H.GC_CASES[name]), d["traj"][0, :5], float(d["mu"]), float(d["mass"]),
+                 fieldlineresolution=par.get("fieldlineresolution", 50), arith="strict")
+    k = int(o["npts"][0])
+    assert k == len(d["bs_curve"])
+    assert o["Bm"][0] == float(d["bs_Bm"]) and o["ds"][0] == float(d["bs_ds"]) and o["v"][0] == float(d["bs_v"])
+    assert np.array_equal(o["curve"][0, :k, :4], d["bs_curve"]), "every point (s, x, y, z) of the trace, same bits"
+    assert np.array_equal(o["curve"][0, :k, 4], d["bs_B"])
+    # the period goes through this repo's restatement of scipy's interp1d / brentq / quad: not bit-equal, 1e-11
+    assert abs(o["period"][0] / float(d["bs_period"]) - 1) < 1e-11
+    # closed form on the same spline: differs by QUADPACK's own error
+    c = K.bounce(H.gpu_field(*H.GC_CASES[name]), d["traj"][0, :5], float(d["mu"]), float(d["mass"]),
+                 fieldlineresolution=par.get("fieldlineresolution", 50), arith="strict", quadrature=0)
+    assert abs(c["period"][0] / float(d["bs_period"]) - 1) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["g2_gc_doubledipole", "gc_earthdipole"])
+def test_fast_bounce_setup_source_vs_reference(name):
+    d, par = H.load(name)
+    o = K.bounce(H.gpu_field(*H.GC_CASES[name]), d["traj"][0, :5], float(d["mu"]), float(d["mass"]),
+                 fieldlineresolution=par.get("fieldlineresolution", 50), arith="fast")
+    k = int(o["npts"][0])
+    assert k == len(d["bs_curve"])
+    assert np.max(np.abs(o["curve"][0, :k, :4] - d["bs_curve"])) < 1e-6 * np.max(np.abs(d["bs_curve"]))
+    assert abs(o["period"][0] / float(d["bs_period"]) - 1) < 1e-6
