@@ -99,7 +99,7 @@ RAPT_DEV double fast_exp(double y)
     p = fma(p, f, 1.0 / 3628800.0); p = fma(p, f, 1.0 / 362880.0); p = fma(p, f, 1.0 / 40320.0); p = fma(p, f, 1.0 / 5040.0);
     p = fma(p, f, 1.0 / 720.0); p = fma(p, f, 1.0 / 120.0); p = fma(p, f, 1.0 / 24.0); p = fma(p, f, 1.0 / 6.0);
     p = fma(p, f, 0.5); p = fma(p, f, 1.0); p = fma(p, f, 1.0);
-    return __hiloint2double(__double2hiint(p) + ((int)n << 20), __double2loint(p));
+    return __hiloint2double(__double2hiint(p) + (int)n * (1 << 20), __double2loint(p));
 }
 // one Newton step: ~2^-45; enough for the error-norm scale factors 1/(atol + rtol |y|)
 RAPT_DEV double fast_rcp1(double x)
