@@ -361,3 +361,40 @@ def test_fast_bounce_setup_source_vs_reference(name):
     assert k == len(d["bs_curve"])
     assert np.max(np.abs(o["curve"][0, :k, :4] - d["bs_curve"])) < 1e-6 * np.max(np.abs(d["bs_curve"]))
     assert abs(o["period"][0] / float(d["bs_period"]) - 1) < 1e-6
+
+
+# ---- edge cases of the row bookkeeping (same list as the oracle's own edge-case test)
+
+@pytest.mark.parametrize("kernel", ["rkn-fast", "generic-fast", "generic-strict"])
+def test_kernel_source_edge_cases(kernel):
+    import oracle as O
+    rkn, arith = kernel.startswith("rkn"), kernel.split("-")[1]
+    f = H.gpu_field("EarthDipole", ())
+    d, _ = H.load("g1b_generic")
+    m, q, r0 = float(d["mass"]), float(d["charge"]), d["traj"][0]
+    run = lambda delta, **kw: K.particle_advance(f, r0, m, q, delta, rkn=rkn, arith=arith, nthreads=1, cyclotronresolution=20, **kw)
+    # empty ensemble, zero duration
+    o = K.particle_advance(f, np.zeros((0, 7)), np.zeros(0), np.zeros(0), 1.0, rkn=rkn, arith=arith)
+    assert o["state"].shape == (0, 7)
+    o = run(0.0, max_rows=4)
+    assert o["nrows"][0] == 1 and o["nstored"][0] == 1 and np.array_equal(o["state"][0], r0)
+    # decimation: stored rows are every k-th row of the full trajectory; the final state does not depend on storage
+    full = run(1.0, max_rows=400)
+    dec = run(1.0, store_every=5, max_rows=400)
+    nf, nd = int(full["nstored"][0]), int(dec["nstored"][0])
+    assert np.array_equal(dec["rows"][0, :nd, :7], full["rows"][0, :nf:5, :7])
+    assert np.array_equal(dec["state"], full["state"])
+    # row buffer too small: integration continues, only storage stops (and nothing is written past the buffer:
+    # tools/hostcheck_asan.sh runs this under AddressSanitizer)
+    small = run(1.0, max_rows=10)
+    assert small["nstored"][0] == 10 and small["nrows"][0] == full["nrows"][0]
+    assert np.array_equal(small["state"], full["state"])
+    none = run(1.0, store_every=0, max_rows=0)
+    assert np.array_equal(none["state"], full["state"]) and none["nstored"][0] == 0
+    # nsteps = 500 per row: an absurd output step makes the solver fail like scipy (-2) and ends the loop
+    o = K.particle_advance(f, r0, m, q, 1e6, rkn=rkn, arith=arith, nthreads=1, cyclotronresolution=1e-4, max_rows=4)
+    ref = O.particle_advance(O.make_field("EarthDipole"), O.make_params(cyclotronresolution=1e-4), r0, m, q, 1e6, max_rows=4)
+    assert o["status"][0] == -2 == ref["status"][0] and o["nrows"][0] == 2 == ref["nrows"][0]
+    # a neutral tracer has no cyclotron period: the reference would never return; the kernels stop it
+    o = K.particle_advance(f, r0, m, 0.0, 1.0, rkn=rkn, arith=arith, nthreads=1, cyclotronresolution=20, max_rows=4)
+    assert o["status"][0] == -3 and o["nrows"][0] == 1
