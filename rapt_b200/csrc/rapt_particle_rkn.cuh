@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
             const double iskx = fast_rcp1(atol + rtol * fmax(fabs(x[i]), fabs(X[i])));
             const double iskp = fast_rcp1(atol + rtol * fmax(fabs(p[i]), fabs(P[i])));
             const double a3 = e3x * iskx, b3 = e3p * iskp, a5 = e5x * iskx, b5 = e5p * iskp;
-            err2 += a3 * a3 + b3 * b3; err += a5 * a5 + b5 * b5;
+            err2 = fma(b3, b3, fma(a3, a3, err2)); err = fma(b5, b5, fma(a5, a5, err));
         }
         const double hnorm = 1.0;
 #else
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
                 dnf += a_ * a_ + c_ * c_; dny += b_ * b_ + d_ * d_; s1 = fma(e_, e_, s1);
             }
             double h0 = 1e-6;
-            if (!(dnf <= 1e-10 || dny <= 1e-10)) { const double qq = dny * fast_rcp(dnf); h0 = (qq * fast_rsqrt(qq)) * 0.01; }
+            if (!(dnf <= 1e-10 || dny <= 1e-10)) h0 = (dny * fast_rsqrt(dny * dnf)) * 0.01;      // 0.01 sqrt(dny / dnf)
             h0 = fmin(h0, hmax);
             // Euler probe f1 = f(t + h0, y + h0 f0); f1 - f0 = (h0 K1 / gm, K' - K1)
 #pragma unroll
