@@ -23,6 +23,7 @@
 #endif
 #include "../../rapt_b200/csrc/rapt_gc.cuh"
 #include "../../rapt_b200/csrc/rapt_aux.cuh"
+#include "../../rapt_b200/csrc/rapt_bc.cuh"
 #include <omp.h>
 #include <vector>
 
@@ -243,6 +244,34 @@ template <int KIND> static void go_bounce(const rapt::BounceArgs &a)
 }
 
 extern "C" {
+
+// k_bounce_center: op 0 = BounceCenter.advance, op 1 = (S_b, I, gradI, deriv) at given points.  One lane walks the
+// tracers (the shim's grid is one block of one thread), scratch curves of max_pts points.
+int hc_bounce_center(const rapt_field_t *f, int op, int quadrature, long long n,
+                     double *t, double *x, double *y, double *z, const double *mu, const double *Bm,
+                     const double *v, const double *mass, const double *charge, const double *dt_in,
+                     double bctimestep, double delta, double rtol, double atol, double fieldlineresolution, double eyegradientstep,
+                     long long store_every, long long max_rows, double *rows, int *nrows, int *nstored, int *counters,
+                     int *status, double *dt_out, double *out, long long max_pts)
+{
+    std::vector<double> cv((size_t)max_pts * 5), bw((size_t)max_pts * 4);
+    rapt::BCArgs a;
+    memset(&a, 0, sizeof a);
+    memcpy(&a.f, f, sizeof a.f);
+    a.op = op; a.quadrature = quadrature; a.rtol = rtol; a.atol = atol; a.flres = fieldlineresolution;
+    a.eyestep = eyegradientstep; a.bctimestep = bctimestep; a.delta = delta;
+    a.n = n; a.max_pts = max_pts; a.store_every = rows ? store_every : 0; a.max_rows = rows ? max_rows : 0;
+    a.t = t; a.x = x; a.y = y; a.z = z; a.mu = mu; a.Bm = Bm; a.v = v; a.mass = mass; a.charge = charge;
+    a.dtin = dt_in; a.dt_out = dt_out; a.rows = rows;
+    a.nrows = nrows; a.nstored = nstored; a.counters = counters; a.status = status; a.out = out;
+    a.curve = cv.data(); a.scratch = bw.data();
+    switch (f->kind) {
+    case 0: k_bounce_center<Field<0>>(a); break;
+    case 1: k_bounce_center<Field<1>>(a); break;
+    default: return -1;
+    }
+    return 0;
+}
 
 // rapt_b200_bounce_setup / rapt_b200_bounce_period in one: curve and/or period may be NULL
 int hc_bounce(const rapt_field_t *f, int quadrature, double fieldlineresolution, long long n,

@@ -116,3 +116,46 @@ def bounce(field, state, mu, mass, fieldlineresolution=50.0, arith="strict", max
                               C.c_longlong(max_pts), ptr(curve), ptr(period))
     assert rc == 0, rc
     return dict(Bm=Bm, v=v, ds=ds, npts=npts, curve=curve, period=period)
+
+
+def _bc_call(arith, f, op, n, cols, mu, Bm, v, mass, charge, dtin, src, delta, store_every, max_rows, rows, nrows, nstored,
+             counters, status, dt_out, out, max_pts=1024):
+    rtol, atol = src["solvertolerances"]
+    rc = lib(arith).hc_bounce_center(
+        C.byref(f), C.c_int(op), C.c_int(1), C.c_longlong(n), *[ptr(c_) for c_ in cols], ptr(mu), ptr(Bm), ptr(v), ptr(mass),
+        ptr(charge), ptr(dtin), C.c_double(float(src["BCtimestep"])), C.c_double(float(delta)), C.c_double(float(rtol)),
+        C.c_double(float(atol)), C.c_double(float(src["fieldlineresolution"])), C.c_double(float(src["eyegradientstep"])),
+        C.c_longlong(store_every), C.c_longlong(max_rows), ptr(rows), ptr(nrows), ptr(nstored), ptr(counters), ptr(status),
+        ptr(dt_out), ptr(out), C.c_longlong(max_pts))
+    assert rc == 0, rc
+
+
+def bounce_center_advance(field, state, mu, v, mass, charge, delta, store_every=1, max_rows=0, arith="strict"):
+    """k_bounce_center op 0 on the host; arguments and result as rapt_b200.engine.bounce_center_advance."""
+    from rapt_b200 import params as gp
+    f = engine._field_desc(field)
+    st = np.asarray(state, dtype=np.float64).reshape(-1, 4)
+    n = len(st)
+    cols = [np.ascontiguousarray(st[:, i]).copy() for i in range(4)]
+    mu, v, mass, charge = _col(mu, n), _col(v, n), _col(mass, n), _col(charge, n)
+    rows = np.zeros((n, max_rows, 4)) if max_rows > 0 else None
+    nrows = np.zeros(n, np.int32); nstored = np.zeros(n, np.int32); counters = np.zeros((n, 4), np.int32)
+    status = np.zeros(n, np.int32); dt_out = np.zeros(n)
+    _bc_call(arith, f, 0, n, cols, mu, None, v, mass, charge, None, dict(gp), delta, store_every, max_rows, rows, nrows,
+             nstored, counters, status, dt_out, None)
+    return dict(state=np.column_stack(cols), rows=rows, nrows=nrows, nstored=nstored, counters=counters, status=status, dt=dt_out)
+
+
+def bounce_center_terms(field, tpos, Bm, v, mass, charge, arith="strict"):
+    """k_bounce_center op 1 on the host: S_b, I, gradI and the right-hand side at the given points."""
+    from rapt_b200 import params as gp
+    f = engine._field_desc(field)
+    tp = np.asarray(tpos, dtype=np.float64).reshape(-1, 4)
+    n = len(tp)
+    cols = [np.ascontiguousarray(tp[:, i]).copy() for i in range(4)]
+    Bm, v, mass, charge = _col(Bm, n), _col(v, n), _col(mass, n), _col(charge, n)
+    out = np.zeros((n, 8)); status = np.zeros(n, np.int32)
+    nrows = np.zeros(n, np.int32); nstored = np.zeros(n, np.int32); counters = np.zeros((n, 4), np.int32)
+    _bc_call(arith, f, 1, n, cols, None, Bm, v, mass, charge, None, dict(gp), 0.0, 0, 0, None, nrows, nstored, counters,
+             status, None, out)
+    return dict(Sb=out[:, 0], I=out[:, 1], gradI=out[:, 2:5], deriv=out[:, 5:8], status=status)
