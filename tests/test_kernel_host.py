@@ -432,3 +432,49 @@ def test_bounce_center_kernel_source_vs_reference(name, arith):
         assert abs(int(o["counters"][0, 1]) - int(ref_cnt[1])) <= 4 and o["counters"][0, 3] == 0
     else:
         assert np.array_equal(o["counters"][0], ref_cnt)
+
+
+# ---- the reference's own ensemble fixtures (first members of configs 2, 3, 5 advanced by the unmodified reference)
+
+@pytest.mark.parametrize("kernel", ["rkn-fast", "generic-fast", "generic-strict"])
+def test_kernel_source_config2_first32_vs_reference(kernel):
+    from rapt_b200 import engine, synth
+    rkn, arith = kernel.startswith("rkn"), kernel.split("-")[1]
+    d, par = H.load("e2_config2_first32")
+    n = int(d["n"])
+    ic = synth.config2_protons(n)
+    vel = np.column_stack([ic["vx"], ic["vy"], ic["vz"]])
+    st = np.column_stack([ic["t0"], ic["x"], ic["y"], ic["z"], engine.particle_momentum(vel, ic["mass"])])
+    o = K.particle_advance(H.gpu_field("EarthDipole", ()), st, ic["mass"], ic["charge"], float(d["delta"]), store_every=0,
+                           rkn=rkn, arith=arith, **par)
+    fin = d["final"]
+    assert np.array_equal(o["nrows"], d["nrows"])
+    assert np.array_equal(o["counters"], d["totals"]), "per-particle (nfcn,nstep,naccpt,nrejct) equal scipy's"
+    if arith == "strict":
+        assert np.array_equal(o["state"], fin)
+    else:
+        assert H.vec_relerr(o["state"][:, 1:4], fin[:, 1:4]) < 1e-8 and H.vec_relerr(o["state"][:, 4:7], fin[:, 4:7]) < 1e-8
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+@pytest.mark.parametrize("case", ["e3_config3_first16", "e5_config5_first16"])
+def test_gc_kernel_source_ensembles_vs_reference(case, arith):
+    import oracle as O
+    from rapt_b200 import synth
+    d, par = H.load(case)
+    n = int(d["n"])
+    fa = ("DoubleDipole", ()) if case.startswith("e3") else ("VarEarthDipole", (0.1, 10))
+    ic = synth.config3_electrons(n) if case.startswith("e3") else synth.config5_belt(n)
+    pos = np.column_stack([ic["x"], ic["y"], ic["z"]])
+    ppar, mu = O.gc_construct(O.make_field(fa[0], *fa[1]), ic["t0"], pos, ic["v"], ic["pa"], ic["mass"])
+    st0 = np.column_stack([ic["t0"], pos, ppar])
+    o = K.gc_advance(H.gpu_field(*fa), st0, mu, ic["v"], ic["mass"], ic["charge"], par["GCtimestep"], float(d["delta"]),
+                     store_every=0, arith=arith)
+    fin = d["final"]
+    assert np.array_equal(o["nrows"], d["nrows"])
+    if arith == "strict":
+        assert np.array_equal(o["state"][:, :5], fin[:, :5]) and np.array_equal(o["counters"], d["totals"])
+    else:
+        assert H.vec_relerr(o["state"][:, 1:4], fin[:, 1:4]) < 1e-8
+        dn = np.abs(o["counters"][:, 1].astype(int) - d["totals"][:, 1].astype(int))
+        assert dn.max() <= max(2, 0.005 * d["totals"][:, 1].max()), dn
