@@ -418,7 +418,11 @@ def main():
             cores = os.cpu_count() or 1
             v, steps, el = (cpu_sample_gc(args.workload, min(args.cpu_sample, 2048), args.delta, cores) if is_gc
                             else cpu_sample(args.cpu_sample, args.delta, cores))
-            res["cpu_baseline"] = {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+            # the unmodified Python reference cannot travel to the GPU box (/root/reference is absent there); its rate was
+            # measured in the build container (README Particle case 1.4-1.6e3, GuidingCenter 0.46e3
+            # particle-steps/s on one core) and is quoted here for scale only -- the C port above is ~10^3 x faster per core
+            py_ref = {"value": 0.46e3 if is_gc else 1.4e3, "unit": "particle-steps/s per core", "measured": "build container, SURVEY.md section 6; not re-timed in this run"}
+            res["cpu_baseline"] = {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": "port", "python_reference": py_ref,
                                    "sample": f"first {min(args.cpu_sample, 2048) if is_gc else args.cpu_sample} tracers of the same ensemble, advance({args.delta} s), "
                                              f"{steps} steps in {el:.1f} s, C oracle port with OpenMP"}
         sys.stdout.flush()
