@@ -75,7 +75,7 @@ RAPT_DEV void grad_and_curl(const FieldP &f, double t, double tf, double x, doub
 #undef RAPT_FD
 }
 
-struct GcConst { double mass, q, mu, v, iq, im; };
+struct GcConst { double mass, q, mu, v; };
 
 // GuidingCenter._TaoChanBrizardEOM :329-355, _BrizardChanEOM :357-379, _NorthropTellerEOM :381-395
 template <class F>
@@ -94,7 +94,7 @@ RAPT_DEV void gc_rhs(const FieldP &f, const GcConst &c, int eom, int equatorial,
     const double ux = bx * ib, uy = by * ib, uz = bz * ib;
     // divisions by the tracer's constants (m, q, c) as multiplications by branch-free reciprocals: a true fp64
     // division is ~12 FP64-pipe instructions plus a slow-path call site, three of them per right-hand side
-    const double iq = c.iq, im = c.im;
+    const double iq = fast_rcp(q), im = fast_rcp(m);
     const double ic = 1.0 / RAPT_C_LIGHT;                          // folded at compile time
     grad_and_curl<F>(f, t, tf, Y[0], Y[1], Y[2], gB, cb);
     if (eom == 0) {
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
 
     double y[4], k1[4], k2[4], k3[4], k4[4], k5[4], k6[4], y1[4], yin[4], kout[4];
     double x = 0, h = 0, xend = 0, tstop = 0, tlim = 0, dt = 0, facold = 1e-4, hmax = 0, tin = 0, dnf = 0;
-    GcConst gc = {0, 0, 0, 0, 0, 0};
+    GcConst gc = {0, 0, 0, 0};
     int pid = -1;
     int nstep = 0, naccpt = 0, nrejct = 0, ncalls = 0, nstep_row = 0, naccpt_row = 0;
     int rowidx = 0, nst = 0, st = RAPT_ST_OK;
@@ -275,9 +275,6 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
             x = a.t[pid];
             y[0] = a.s1[pid]; y[1] = a.s2[pid]; y[2] = a.s3[pid]; y[3] = a.s4[pid];
             gc.mass = a.mass[pid]; gc.q = a.charge[pid]; gc.mu = a.mu[pid]; gc.v = a.v[pid];
-#if !RAPT_STRICT
-            gc.iq = fast_rcp(gc.q); gc.im = fast_rcp(gc.mass);
-#endif
             dt = a.dtin[pid];
             double delta = a.delta_arr ? a.delta_arr[pid] : a.delta;
             tstop = x + delta;                                   // GuidingCenter.py:452
