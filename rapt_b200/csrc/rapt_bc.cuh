@@ -18,7 +18,9 @@
 namespace RAPT_NS {
 using rapt::BCArgs;
 
+#ifndef RAPT_ST_TRACE           /* same value as include/rapt_b200.h (not visible to NVRTC) */
 #define RAPT_ST_TRACE (-7)      /* a field line could not be traced / mirror points not bracketed (the reference raises) */
+#endif
 
 struct BcCtx {
     double Bm, coef;            // mirror field; gamma m v^2 / q
