@@ -415,6 +415,20 @@ def case_grid():
     # GuidingCenter: 1 MeV electron, pa 60
     ve = ru.speedfromKE(1e6, m_el)
     g, Lg = run_gc(pos, ve, 60, m_el, -e, SynthGrid(files), 2.6, GCtimestep=0.05)
+    # Sensitivity band of that guiding-centre run, measured with the reference itself: on a multilinear interpolant
+    # grad|B| and curl b are piecewise constant, so the ODE is discontinuous at every cell face and the result depends on
+    # the step sequence.  Eight reruns with the start position moved by a few ulp (relative 1e-15): the spread of the
+    # reference's own trajectories / step counts is the resolution at which this case can be compared at all.
+    prng = np.random.default_rng(12)
+    band_pos, band_pp, band_ns = [], [], []
+    for k in range(8):
+        pk = tuple(np.array(pos) * (1 + 1e-15 * prng.choice([-3, -2, -1, 1, 2, 3], 3)) + np.array([0, 1e-9, 1e-9]) * prng.uniform(-1, 1, 3))
+        gk, Lk = run_gc(pk, ve, 60, m_el, -e, SynthGrid(files), 2.6, GCtimestep=0.05)
+        assert gk.trajectory.shape == g.trajectory.shape
+        band_pos.append(np.max(np.linalg.norm(gk.trajectory[:, 1:4] - g.trajectory[:, 1:4], axis=1) / np.linalg.norm(g.trajectory[:, 1:4], axis=1)))
+        band_pp.append(np.max(np.abs(gk.trajectory[:, 4] - g.trajectory[:, 4])) / np.max(np.abs(g.trajectory[:, 4])))
+        band_ns.append(int(Lk[:, 1].sum()))
+    print("  grid GC sensitivity band:", band_pos, band_pp, band_ns, int(Lg[:, 1].sum()))
     # leaving the grid: ValueError, rows before it are kept (Particle.py:304-307)
     refshim.reset_params(rapt, cyclotronresolution=10)
     pe = rapt.Particle(pos=(7.9 * Re, 0, 0), vel=(v * 0.6, 0, v * 0.8), t0=0, mass=m_pr, charge=e, field=SynthGrid(files))
@@ -430,6 +444,7 @@ def case_grid():
          p_params=parjson(cyclotronresolution=10), p_traj=p.trajectory, p_counters=L, p_tcur=p.tcur,
          g_pos=np.array(pos, float), g_v=ve, g_pa=60.0, g_mass=m_el, g_charge=-e, g_delta=2.6,
          g_params=parjson(GCtimestep=0.05), g_traj=g.trajectory, g_counters=Lg, g_tcur=g.tcur, g_mu=g.mu,
+         g_band_pos=np.array(band_pos), g_band_ppar=np.array(band_pp), g_band_nstep=np.array(band_ns),
          oob_pos=np.array((7.9 * Re, 0, 0)), oob_vel=np.array((v * 0.6, 0, v * 0.8)), oob_raised=raised,
          oob_traj=pe.trajectory, **{"ops_" + k: v_ for k, v_ in out.items()})
 
@@ -554,7 +569,27 @@ def case_bc():
          simps_name_bound=np.array([r[5] for r in rows]))
 
 
+def case_fail():
+    """Solver failure inside advance(): scipy's nsteps=500 limit ends the `while r.successful()` loop AFTER the row of the
+    failed call has been appended (Particle.py:304-307 -- label = the row's end time, values = the state reached,
+    tcur = time reached + dt; GuidingCenter.py:452-456 -- label = tcur = the time reached)."""
+    v = ru.speedfromKE(1e6, m_pr); pa = 30 * np.pi / 180
+    pos = (6 * Re, 0, 0); vel = (0, -v * np.sin(pa), v * np.cos(pa))
+    par = dict(cyclotronresolution=20, solvertolerances=(1e-15, 1e-30))
+    p, L = run_particle(pos, vel, m_pr, e, rf.EarthDipole(), 10, **par)
+    assert p.trajectory.shape[0] == 2
+    save("p_fail_nmax", pos=np.array(pos), vel=np.array(vel), mass=m_pr, charge=e, delta=10.0, params=parjson(**par),
+         traj=p.trajectory, counters=L, tcur=p.tcur)
+    ve = ru.speedfromKE(1e6, m_el)
+    par = dict(GCtimestep=50.0)
+    g, Lg = run_gc(pos, ve, 30, m_el, -e, rf.EarthDipole(), 100, **par)
+    assert g.trajectory.shape[0] == 2
+    save("gc_fail_nmax", pos=np.array(pos), v=ve, pa=30.0, mass=m_el, charge=-e, delta=100.0, params=parjson(**par),
+         traj=g.trajectory, counters=Lg, tcur=g.tcur, mu=g.mu)
+
+
 CASES = {
+    "fail": case_fail,
     "g1": case_g1, "g1b": case_g1b, "pfields": case_pfields, "g2": case_g2, "gcfields": case_gcfields,
     "g3": case_g3, "e4": case_e4, "adip": case_adaptive_dipole, "e2": case_e2, "e3": case_e3,
     "e5": case_e5, "units": case_units, "eye": case_eye, "grid": case_grid, "bc": case_bc,

@@ -126,13 +126,15 @@ class GuidingCenter:
             dt = self.bounceperiod() / params["bounceresolution"]
         last = self.trajectory[-1]
         max_rows = max(int(np.ceil(delta / dt)) + 8, 8) if delta > 0 and np.isfinite(dt) and dt > 0 else 8
+        asked = -1
         while True:
             o = engine.gc_advance(self.field, last, self.mu, self.v, self.mass, self.charge, dt, float(delta), eom=eom,
                                   store_every=1, max_rows=max_rows, check_adiabaticity=self.check_adiabaticity)
             n = int(o["nstored"][0])
-            if o["nrows"][0] <= n:
+            if o["nrows"][0] <= n or o["nrows"][0] == asked:
                 break
-            max_rows = int(o["nrows"][0]) + 8
+            asked = int(o["nrows"][0])
+            max_rows = asked + 8
         self.trajectory = np.vstack((self.trajectory, o["rows"][0, 1:n, :5]))
         self.solver_counters = o["counters"][0].astype(np.int64)
         if n > 1:

@@ -99,13 +99,15 @@ class Particle:
         last = self.trajectory[-1]
         dt = float(engine.particle_dt(self.field, last, self.mass, self.charge)[0])
         max_rows = max(int(np.ceil(delta / dt)) + 8, 8) if delta > 0 and np.isfinite(dt) and dt > 0 else 8
+        asked = -1
         while True:
             o = engine.particle_advance(self.field, last, self.mass, self.charge, float(delta), store_every=1,
                                         max_rows=max_rows, check_adiabaticity=self.check_adiabaticity)
             n = int(o["nstored"][0])
-            if o["nrows"][0] <= n:
-                break
-            max_rows = int(o["nrows"][0]) + 8      # buffer was too small (dt estimate off): rerun, deterministic
+            if o["nrows"][0] <= n or o["nrows"][0] == asked:
+                break                              # all rows stored (or a rerun that asks for the same size again)
+            asked = int(o["nrows"][0])
+            max_rows = asked + 8                   # buffer was too small (dt estimate off): rerun, deterministic
         self.trajectory = np.vstack((self.trajectory, o["rows"][0, 1:n, :7]))
         self.solver_counters = o["counters"][0].astype(np.int64)
         if n > 1:

@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
             gc_rhs<F>(a.f, gc, eom, eqf, x, y, k1);              // k1 = f(x, y)
         }
         // ---- (B) one step attempt; stage 1 = HINIT's Euler probe for lanes that start an output row
-        bool skip = false, hin = false;
+        bool skip = false, hin = false, rowdone = false;
 #pragma unroll 1
         for (int s = 1; s <= 7; s++) {
             bool active = !skip;
@@ -379,7 +379,9 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
                 if (nstep_row > 500) st = RAPT_ST_NMAX;
                 else if (0.1 * fabs(h) <= fabs(x) * uround) st = RAPT_ST_HSMALL;
                 if (st != RAPT_ST_OK) {
-                    rowidx++; need_row = true; skip = true; active = false;   // the failed row is still appended
+                    // solver failure: the state reached is still appended as a row, labelled with the time reached, before
+                    // `while r.successful()` ends the loop (GuidingCenter.py:452-456)
+                    rowdone = true; skip = true; active = false;
                 } else {
                     if ((x + 1.01 * h - xend) > 0.0) { h = xend - x; last = true; }
                     nstep_row++; nstep++;
@@ -475,21 +477,8 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
 #pragma unroll
                 for (int i = 0; i < 4; i++) { k1[i] = kout[i]; y[i] = y1[i]; }
                 x = x + h;
-                if (last) {
-                    // ---- output row complete (GuidingCenter.py:453-458)
-                    rowidx++;
-                    if (myrows && a.store_every > 0 && (rowidx % a.store_every) == 0 && nst < a.max_rows) {
-                        double2 *r = reinterpret_cast<double2 *>(myrows + (size_t)nst * 8);
-                        double tag = a.segtag ? (double)a.segtag[pid] : (double)nstep;
-                        r[0] = make_double2(x, y[0]); r[1] = make_double2(y[1], y[2]);
-                        r[2] = make_double2(y[3], gc.mu); r[3] = make_double2(0.0, tag);
-                        nst++;
-                    }
-                    if (a.p.check_adiabaticity) {
-                        if (!gc_isadiabatic<F>(a.f, a.p, x, y, gc.mu, gc.mass, gc.q)) st = RAPT_ST_NONADIABATIC;
-                    }
-                    need_row = true;
-                } else {
+                if (last) rowdone = true;
+                else {
                     h = hnew;
                     reject = false;
                 }
@@ -505,6 +494,21 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
                 last = false;
                 if (F::CAN_FAIL && !(err == err)) { st = RAPT_ST_FIELD; need_row = true; }   // left the grid: keep the last row
             }
+        }
+        if (rowdone) {
+            // ---- output row complete (GuidingCenter.py:453-458)
+            rowidx++;
+            if (myrows && a.store_every > 0 && (rowidx % a.store_every) == 0 && nst < a.max_rows) {
+                double2 *r = reinterpret_cast<double2 *>(myrows + (size_t)nst * 8);
+                double tag = a.segtag ? (double)a.segtag[pid] : (double)nstep;
+                r[0] = make_double2(x, y[0]); r[1] = make_double2(y[1], y[2]);
+                r[2] = make_double2(y[3], gc.mu); r[3] = make_double2(0.0, tag);
+                nst++;
+            }
+            if (a.p.check_adiabaticity) {
+                if (!gc_isadiabatic<F>(a.f, a.p, x, y, gc.mu, gc.mass, gc.q)) st = RAPT_ST_NONADIABATIC;
+            }
+            need_row = true;
         }
     }
 }

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(128, 2) k_particle_dop853(const AdvArgs a)
             particle_rhs<F>(a.f, q, mass, gm, igm, eqf, x, y, k1);           // k1 = f(x, y)
         }
         // ---- (B) one step attempt; stage 1 = HINIT for lanes that start an output row
-        bool accepted = false, skip = false;
+        bool accepted = false, skip = false, rowdone = false;
 #pragma unroll 1
         for (int s = 1; s <= 13; s++) {
             bool active = !skip;
@@ -235,8 +235,9 @@ __global__ void __launch_bounds__(128, 2) k_particle_dop853(const AdvArgs a)
                 if (nstep_row > 500) st = ST_NMAX;
                 else if (0.1 * fabs(h) <= fabs(x) * uround) st = ST_HSMALL;
                 if (st != ST_OK) {
-                    // the reference's loop ends silently on solver failure (Particle.py:304); the row is still appended
-                    rowidx++; need_row = true; skip = true; active = false;
+                    // solver failure: r.integrate() hands back the state it reached and the reference appends it as a row
+                    // labelled with the row's end time before `while r.successful()` ends the loop (Particle.py:304-307)
+                    rowdone = true; skip = true; active = false;
                 } else {
                     if ((x + 1.01 * h - xend) > 0.0) { h = xend - x; last = true; }
                     nstep_row++; nstep++;
@@ -368,27 +369,29 @@ __global__ void __launch_bounds__(128, 2) k_particle_dop853(const AdvArgs a)
 #pragma unroll
                     for (int i = 0; i < 6; i++) y[i] = k5[i];
                     x = x + h;
-                    if (last) {
-                        // ---- output row complete (Particle.py:305-309)
-                        rowidx++;
-                        if (myrows && a.store_every > 0 && (rowidx % a.store_every) == 0 && nst < a.max_rows) {
-                            double2 *r = reinterpret_cast<double2 *>(myrows + (size_t)nst * 8);
-                            double tag = a.segtag ? (double)a.segtag[pid] : (double)nstep;
-                            r[0] = make_double2(label, y[0]); r[1] = make_double2(y[1], y[2]);
-                            r[2] = make_double2(y[3], y[4]); r[3] = make_double2(y[5], tag);
-                            nst++;
-                        }
-                        if (a.p.check_adiabaticity) {
-                            if (particle_isadiabatic<F>(a.f, a.p, label, y, mass, q)) st = ST_ADIABATIC;
-                        }
-                        need_row = true;
-                    } else {
+                    if (last) rowdone = true;
+                    else {
                         h = hnew;
                         reject = false;
                     }
                 }
                 break;
             }
+        }
+        if (rowdone) {
+            // ---- output row complete (Particle.py:305-309)
+            rowidx++;
+            if (myrows && a.store_every > 0 && (rowidx % a.store_every) == 0 && nst < a.max_rows) {
+                double2 *r = reinterpret_cast<double2 *>(myrows + (size_t)nst * 8);
+                double tag = a.segtag ? (double)a.segtag[pid] : (double)nstep;
+                r[0] = make_double2(label, y[0]); r[1] = make_double2(y[1], y[2]);
+                r[2] = make_double2(y[3], y[4]); r[3] = make_double2(y[5], tag);
+                nst++;
+            }
+            if (a.p.check_adiabaticity) {
+                if (particle_isadiabatic<F>(a.f, a.p, label, y, mass, q)) st = ST_ADIABATIC;
+            }
+            need_row = true;
         }
     }
 }

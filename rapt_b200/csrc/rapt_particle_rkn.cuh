@@ -76,9 +76,12 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
         // iteration: the warp reconverges at the loop's back edge and runs the step with all lanes.
         // (With HINIT in front of the step the lanes that skipped it ran ahead: 19 of 32 lanes per issue.)
         if (have && !need_row) {
+        bool rowdone = false;
         if (nstep_row > 500) st = ST_NMAX;
         else if (0.1 * fabs(h) <= fabs(t) * uround) st = ST_HSMALL;
-        if (st != ST_OK) { rowidx++; need_row = true; }   // failed row is still appended (Particle.py:304-307)
+        // solver failure: r.integrate() hands back the state it reached and the reference appends it as a row labelled
+        // with the row's end time before `while r.successful()` ends the loop (Particle.py:304-307)
+        if (st != ST_OK) rowdone = true;
         else {
         if ((t + 1.01 * h - xend) > 0.0) { h = xend - t; last = true; }
         nstep_row++; nstep++;
@@ -209,22 +212,7 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
             lorentz_K<F>(a.f, q, qg, t, X, P, K1);           // FSAL: k1 = f(t+h, ynew); the step becomes the state
 #pragma unroll
             for (int i = 0; i < 3; i++) { x[i] = X[i]; p[i] = P[i]; }
-            if (last) {
-                // ---- output row complete (Particle.py:305-309)
-                rowidx++;
-                if (myrows && a.store_every > 0 && (rowidx % a.store_every) == 0 && nst < a.max_rows) {
-                    double2 *r = reinterpret_cast<double2 *>(myrows + (size_t)nst * 8);
-                    double tag = a.segtag ? (double)a.segtag[pid] : (double)nstep;
-                    r[0] = make_double2(xend, x[0]); r[1] = make_double2(x[1], x[2]);
-                    r[2] = make_double2(p[0], p[1]); r[3] = make_double2(p[2], tag);
-                    nst++;
-                }
-                if (a.p.check_adiabaticity) {
-                    const double yy[6] = {x[0], x[1], x[2], p[0], p[1], p[2]};
-                    if (particle_isadiabatic<F>(a.f, a.p, xend, yy, a.mass[pid], a.charge[pid])) st = ST_ADIABATIC;
-                }
-                need_row = true;
-            }
+            rowdone = last;
         } else {
 #if RAPT_RKN_HK
             { const double ih = fast_rcp(h); _Pragma("unroll") for (int i = 0; i < 3; i++) K1[i] *= ih; }   // back to f(t, y)
@@ -237,6 +225,22 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
             if (F::CAN_FAIL && !(err == err)) { st = RAPT_ST_FIELD; need_row = true; }   // left the grid: keep the last row
         }
         }   // st == ST_OK
+        if (rowdone) {
+            // ---- output row complete (Particle.py:305-309)
+            rowidx++;
+            if (myrows && a.store_every > 0 && (rowidx % a.store_every) == 0 && nst < a.max_rows) {
+                double2 *r = reinterpret_cast<double2 *>(myrows + (size_t)nst * 8);
+                double tag = a.segtag ? (double)a.segtag[pid] : (double)nstep;
+                r[0] = make_double2(xend, x[0]); r[1] = make_double2(x[1], x[2]);
+                r[2] = make_double2(p[0], p[1]); r[3] = make_double2(p[2], tag);
+                nst++;
+            }
+            if (a.p.check_adiabaticity) {
+                const double yy[6] = {x[0], x[1], x[2], p[0], p[1], p[2]};
+                if (particle_isadiabatic<F>(a.f, a.p, xend, yy, a.mass[pid], a.charge[pid])) st = ST_ADIABATIC;
+            }
+            need_row = true;
+        }
         }   // have && !need_row
         // ---- (B) particle finished?  write it back and fetch the next one
         if (have && need_row && !(st == ST_OK && t < tlim)) {

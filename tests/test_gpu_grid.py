@@ -90,15 +90,20 @@ def test_grid_particle_and_guiding_centre_trajectories(eng, gold, arith):
         assert np.allclose(g.trajectory[:, 0], traj[:, 0], rtol=0, atol=1e-12)
         # The guiding-centre right-hand side differentiates the field: on a multilinear interpolant grad|B|
         # and curl b are piecewise constant, i.e. the ODE is DISCONTINUOUS at every cell face.  The reference
-        # itself rejects 965 of 2385 step attempts here and its result depends on the step sequence at the
-        # 1e-5 level, so a last-bit difference (CUDA pow vs glibc pow in the controller) moves the trajectory
-        # by that much.  Gate: rows and times equal, trajectory to 1e-4, step counts to 3 %; the right-hand
-        # side itself is compared bit for bit in test_grid_gc_rhs_probe below.
-        assert H.vec_relerr(g.trajectory[:, 1:4], traj[:, 1:4]) < 1e-4
-        pscale = np.max(np.abs(traj[:, 4]))
-        assert np.max(np.abs(g.trajectory[:, 4] - traj[:, 4])) < 1e-3 * pscale
+        # itself rejects 965 of 2385 step attempts here and its result depends on the step sequence.  The
+        # resolution of the comparison is therefore MEASURED, not chosen: the fixture holds the spread of the
+        # reference's own result over eight reruns whose start position is moved by a few ulp
+        # (oracle/gen_golden.py:case_grid -- positions 4.9e-5 ... 1.1e-4, p_par 2.3e-4 ... 5.2e-4 of its scale,
+        # step counts +0.3 ... +3.3 %).  Gate: rows and times equal, and the CUDA result inside twice that band;
+        # the right-hand side itself is compared bit for bit in test_grid_gc_rhs_probe below.
+        band_pos, band_pp = float(np.max(d["g_band_pos"])), float(np.max(d["g_band_ppar"]))
         ref = d["g_counters"].sum(0)
-        assert abs(int(g.solver_counters[1]) - int(ref[1])) <= 0.03 * ref[1]
+        band_ns = float(np.max(np.abs(d["g_band_nstep"] - ref[1]))) / ref[1]
+        assert 4e-5 < band_pos < 2e-4 and 2e-4 < band_pp < 1e-3 and 0.02 < band_ns < 0.05      # what was measured
+        assert H.vec_relerr(g.trajectory[:, 1:4], traj[:, 1:4]) < 2 * band_pos
+        pscale = np.max(np.abs(traj[:, 4]))
+        assert np.max(np.abs(g.trajectory[:, 4] - traj[:, 4])) < 2 * band_pp * pscale
+        assert abs(int(g.solver_counters[1]) - int(ref[1])) <= 2 * band_ns * ref[1]
     finally:
         R.params.clear(); R.params.update(old)
 

@@ -276,3 +276,24 @@ def test_bounce_center_advance_bit_exact(name):
     assert np.array_equal(rows, d["traj"][1:n1])
     assert np.array_equal(cnt, d["solver_log"][:n1 - 1].sum(0))
     assert rows[0, 0] == d["traj"][0, 0]            # the first computed row carries the START label (quirk kept)
+
+
+def test_solver_failure_row_bit_exact():
+    """scipy's nsteps = 500 limit inside advance(): the failed call's row is appended (Particle.py:304-307 label = row end
+    time, GuidingCenter.py:452-456 label = time reached) and the loop ends -- fixtures p_fail_nmax / gc_fail_nmax."""
+    d, par = H.load("p_fail_nmax")
+    traj = d["traj"]
+    o = O.particle_advance(O.make_field("EarthDipole"), O.make_params(**par), traj[0], float(d["mass"]), float(d["charge"]),
+                           float(d["delta"]), max_rows=8, want_percall=True)
+    assert o["status"][0] == -2 and o["nrows"][0] == o["nstored"][0] == 2
+    assert np.array_equal(o["rows"][0, :2, :7], traj) and np.array_equal(o["percall"], d["counters"])
+    assert o["tcur"][0] == float(d["tcur"])
+    d, par = H.load("gc_fail_nmax")
+    traj = d["traj"]
+    f = O.make_field("EarthDipole")
+    ppar, mu = O.gc_construct(f, 0.0, d["pos"], float(d["v"]), float(d["pa"]), float(d["mass"]))
+    o = O.gc_advance(f, O.make_params(), np.concatenate(([0.0], d["pos"], ppar)), mu, float(d["v"]), float(d["mass"]),
+                     float(d["charge"]), par["GCtimestep"], float(d["delta"]), max_rows=8, want_percall=True)
+    assert o["status"][0] == -2 and o["nrows"][0] == o["nstored"][0] == 2
+    assert np.array_equal(o["rows"][0, :2, :5], traj) and np.array_equal(o["percall"], d["counters"])
+    assert o["tcur"][0] == float(d["tcur"])
