@@ -1,21 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the particle-advance hot path (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload particle|gc]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload particle|gc|belt|adaptive] [--n-per-gpu M] [--scaling weak|strong]
 
-Metric: particle-steps/s (fp64) = attempted Runge-Kutta steps of all particles per second of device
-time, whole job.  Workload at N = 1: BASELINE.json configs[1] -- 1 M protons in EarthDipole, full orbit,
-random energies 0.1-10 MeV and pitch angles (rapt_b200/synth.py, seed 20260201), Particle.advance(10 s),
-cyclotronresolution 20.  One bench "step" = one such advance of the whole ensemble from the same initial
-state.  N > 1: weak scaling, 1 M protons per GPU (rank r takes members r, r+N, ... of the N-million
-ensemble), no data-path collective; the final states are all-gathered and an energy histogram
-all-reduced over NCCL inside the timed region.
+Metric: particle-steps/s (fp64) = attempted Runge-Kutta steps of all particles per second of device time, whole job.
+Workload at N = 1: BASELINE.json configs[1] -- 1 M protons in EarthDipole, full orbit, random energies 0.1-10 MeV and
+pitch angles (rapt_b200/synth.py, seed 20260201), Particle.advance(10 s), cyclotronresolution 20.  One bench "step" =
+one such advance of the whole ensemble from the same initial state.
 
-`value` is device-resident (inputs already in HBM, CUDA events on the launching stream, max over
-ranks); `e2e` is the same metric through the host-buffer C ABI (pinned host inputs, H2D + D2H inside
-the timed region).  `roofline` is against the FP64 DFMA peak measured in this run (MEASURED_PEAKS.json
-has no FP64 figure), with the algorithmic flop count of DESIGN.md.  `cpu_baseline` / `--impl reference`
-time the CPU oracle port (oracle/, OpenMP over all host cores) on a bounded sample of the same ensemble.
+N > 1 goes through the product's own multi-GPU path (rapt_b200/ensemble.py): every rank builds the ensemble,
+`.shard()` keeps members r, r+N, ... on its GPU, `.advance()` runs the kernels with no data-path collective,
+`.gather()` packs + bins the final states in one kernel and all-gathers / all-reduces them over NCCL -- all inside the
+timed region.  `--scaling weak` (default): M tracers per GPU (N x M in total); `--scaling strong`: M tracers in total.
+
+`value` is device-resident (inputs already in HBM, CUDA events on the launching stream, max over ranks); `e2e` is the
+same metric through the host-buffer C ABI (pinned host inputs, H2D + D2H inside the timed region).  `roofline` is
+against the FP64 DFMA peak measured in this run (MEASURED_PEAKS.json has no FP64 figure), with the algorithmic flop
+count of DESIGN.md.  `per_rank` splits every rank's step into kernel time and collection time (pack + collectives +
+waiting for the slowest rank).  `cpu_baseline` / `--impl reference` time the REFERENCE's own CPU path -- a Python
+loop over rapt.Particle objects and a multiprocessing.Pool over all host cores (oracle/refbench.py, the unmodified
+reference installed into oracle/_ref by build()) -- on a bounded sample of the same workload; the C/OpenMP oracle
+port is reported beside it.  `extra.workloads` carries the guiding-centre (configs 3, 5) and adaptive (config 4)
+lines measured in the same run at N = 1.
 """
 import argparse
 import json
@@ -35,21 +42,33 @@ DELTA = 10.0
 PARAMS = dict(cyclotronresolution=20)
 F_RHS = 38            # Lorentz 18 + EarthDipole 20 flop (E == 0 compiled out)
 F_STAGE = 6 * 158 + 20
-
-
-def algorithmic_flops(nstep, naccpt, ncalls):
-    """DESIGN.md 'flop accounting': 11 RHS per attempted step + 1 per accepted step, stage sums + error
-    norm + controller per attempted step, HINIT (1 extra RHS + norms) per solver call (= output row)."""
-    return nstep * (11 * F_RHS + F_STAGE) + naccpt * F_RHS + ncalls * (F_RHS + 60)
-
+GC_DT = {"gc": 0.1, "belt": 0.05}          # params["GCtimestep"] of configs 3 and 5 (SURVEY.md §8d)
+ADAPTIVE = dict(delta=300.0, gc_dt=1.0, params={"solvertolerances": (1e-12, 1e-12), "epss": 0.02})   # config 4
 
 WORKLOAD_NAME = {
-    "particle": "config2: 1M protons per GPU / EarthDipole / Particle.advance(10 s) / cyclotronresolution 20 / "
-                "KE 0.1-10 MeV / seed 20260201",
+    "particle": "config2: protons / EarthDipole / Particle.advance(10 s) / cyclotronresolution 20 / KE 0.1-10 MeV / seed 20260201",
     "gc": "config3: electrons / DoubleDipole / GuidingCenter.advance (TaoChanBrizard) / GCtimestep 0.1 / KE 50 keV-1 MeV / "
           "seed 20260301",
     "belt": "config5: electrons / VarEarthDipole(0.1, 10 s) / GuidingCenter.advance / GCtimestep 0.05 / seed 20260501",
+    "adaptive": "config4: Adaptive Speiser orbits / Parabolic current sheet / advance(300) / tol 1e-12 / epss 0.02 / "
+                "GCtimestep 1 / seed 20260401",
 }
+
+
+def algorithmic_flops(nstep, naccpt, ncalls, f_rhs=F_RHS):
+    """DESIGN.md 'flop accounting': 11 RHS per attempted step + 1 per accepted step, stage sums + error
+    norm + controller per attempted step, HINIT (1 extra RHS + norms) per solver call (= output row)."""
+    return nstep * (11 * f_rhs + F_STAGE) + naccpt * f_rhs + ncalls * (f_rhs + 60)
+
+
+def gc_flops(workload, nstep, ncalls):
+    """DESIGN.md §5.2: 6 RHS + stage sums per attempted step, HINIT per row; RHS = n_B field evaluations + 176.
+    Belt (VarEarthDipole) counts what the fast kernel executes, not the reference's 9 evaluations with a sine
+    each: 7 dipole evaluations scaled by one time factor (~25 flop) per RHS; db/dt is identically zero.
+    Adaptive (Parabolic, F_B = 3): 7 evaluations."""
+    f_b, n_b, f_t = {"gc": (48, 7, 0), "belt": (23, 7, 25), "adaptive": (3, 7, 0)}[workload]
+    f_rhs = n_b * f_b + f_t + 176
+    return nstep * (6 * f_rhs + 4 * 64 + 20) + ncalls * (f_rhs + 40)
 
 
 class ClockSampler:
@@ -83,130 +102,341 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for ln in self.lines:
             p = [s.strip() for s in ln.split(",")]
             if len(p) < 9:
                 continue
             try:
-                sm.append(float(p[1])); mx.append(float(p[2]))
+                sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    power_w=float(np.median(pw)) if pw else None, reasons=sorted(reasons), samples=len(sm))
 
 
-def make_ensemble(world, rank, n_per_gpu, workload):
-    from rapt_b200 import synth, engine
-    n_total = n_per_gpu * world
-    if workload == "particle":
-        ic = synth.config2_protons(n_total)
-        sl = slice(rank, n_total, world)
-        vel = np.column_stack([ic["vx"][sl], ic["vy"][sl], ic["vz"][sl]])
-        mom = engine.particle_momentum(vel, ic["mass"][sl])
-        cols = [ic["t0"][sl], ic["x"][sl], ic["y"][sl], ic["z"][sl], mom[:, 0], mom[:, 1], mom[:, 2]]
-        return dict(cols=[np.ascontiguousarray(c) for c in cols], mass=np.ascontiguousarray(ic["mass"][sl]),
-                    charge=np.ascontiguousarray(ic["charge"][sl]))
-    if workload in ("gc", "belt"):
-        gen = synth.config3_electrons if workload == "gc" else synth.config5_belt
-        if n_total > 20_000_000:
-            # 100 M-tracer ensembles: every rank draws its own shard (seed + rank) instead of slicing one
-            # global draw, so that no process has to hold the whole ensemble in host memory
-            ic = gen(n_per_gpu, seed=(20260301 if workload == "gc" else 20260501) + 1000 * rank)
-            sl = slice(0, n_per_gpu)
-        else:
-            ic = gen(n_total)
-            sl = slice(rank, n_total, world)
-        field = gc_field(workload)
-        pos = np.column_stack([ic["x"][sl], ic["y"][sl], ic["z"][sl]])
-        ppar, mu = engine.gc_construct(field, ic["t0"][sl], pos, ic["v"][sl], ic["pa"][sl], ic["mass"][sl], arith="fast")
-        cols = [ic["t0"][sl], pos[:, 0], pos[:, 1], pos[:, 2], ppar]
-        return dict(cols=[np.ascontiguousarray(c) for c in cols], mass=np.ascontiguousarray(ic["mass"][sl]),
-                    charge=np.ascontiguousarray(ic["charge"][sl]), mu=mu, v=np.ascontiguousarray(ic["v"][sl]),
-                    dt=np.full(len(mu), GC_DT[workload]))
-    raise ValueError(workload)
-
-
-GC_DT = {"gc": 0.1, "belt": 0.05}          # params["GCtimestep"] of configs 3 and 5 (SURVEY.md §8d)
-
-
+# ----------------------------------------------------------------------------------------------------------------
+# ensembles (product API)
+# ----------------------------------------------------------------------------------------------------------------
 def gc_field(workload):
     from rapt_b200 import fields
     return fields.DoubleDipole() if workload == "gc" else fields.VarEarthDipole(0.1, 10)
 
 
-def gc_flops(workload, nstep, ncalls):
-    """DESIGN.md §5.2: 6 RHS + stage sums per attempted step, HINIT per row; RHS = n_B field evaluations + 176.
-    Belt (VarEarthDipole) counts what the fast kernel executes, not the reference's 9 evaluations with a sine
-    each: 7 dipole evaluations scaled by one time factor (~25 flop) per RHS; db/dt is identically zero."""
-    f_b, n_b, f_t = (48, 7, 0) if workload == "gc" else (23, 7, 25)
-    f_rhs = n_b * f_b + f_t + 176
-    return nstep * (6 * f_rhs + 4 * 64 + 20) + ncalls * (f_rhs + 40)
+def build_ensemble(workload, n_total, world, rank):
+    """The seeded ensemble of `workload` as the product's ensemble object, sharded onto this rank's GPU."""
+    import rapt_b200 as R
+    from rapt_b200 import synth
+    big = n_total > 20_000_000      # 100 M-tracer ensembles: every rank draws its own shard (seed + rank) instead of
+    n_make = n_total // world if big else n_total                 # holding the whole ensemble in host memory
+    if workload == "particle":
+        ic = synth.config2_protons(n_make, **({"seed": 20260201 + 1000 * rank} if big else {}))
+        ens = R.ParticleEnsemble(np.column_stack([ic["x"], ic["y"], ic["z"]]), np.column_stack([ic["vx"], ic["vy"], ic["vz"]]),
+                                 0.0, ic["mass"], ic["charge"], R.fields.EarthDipole())
+    else:
+        gen = synth.config3_electrons if workload == "gc" else synth.config5_belt
+        seed = (20260301 if workload == "gc" else 20260501) + (1000 * rank if big else 0)
+        ic = gen(n_make, seed=seed)
+        ens = R.GuidingCenterEnsemble(np.column_stack([ic["x"], ic["y"], ic["z"]]), ic["v"], pa=ic["pa"], mass=ic["mass"],
+                                      charge=ic["charge"], field=gc_field(workload))
+    if big:
+        ens.world, ens.rank, ens.n_total, ens._group = world, rank, ens.n * world, None
+        from rapt_b200 import dist as rd
+        return ens.cuda(rd.local_device())
+    return ens.shard()
 
 
-def cpu_sample_gc(workload, n_sample, delta, nthreads):
+def run_advance(ens, workload, delta, arith):
+    if workload == "particle":
+        ens.advance(delta, arith=arith, **PARAMS)
+    else:
+        ens.advance(delta, dt=GC_DT[workload], arith=arith)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU baselines
+# ----------------------------------------------------------------------------------------------------------------
+def port_sample(workload, n_sample, delta, nthreads):
+    """The C/OpenMP oracle port on n_sample tracers drawn by the same generator (same seed and distributions)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     from rapt_b200 import synth
-    ic = synth.config3_electrons(n_sample) if workload == "gc" else synth.config5_belt(n_sample)
-    f = O.make_field("DoubleDipole") if workload == "gc" else O.make_field("VarEarthDipole", 0.1, 10)
-    pos = np.column_stack([ic["x"], ic["y"], ic["z"]])
-    ppar, mu = O.gc_construct(f, ic["t0"], pos, ic["v"], ic["pa"], ic["mass"])
-    st = np.column_stack([ic["t0"], pos, ppar])
     t = time.perf_counter()
-    o = O.gc_advance(f, O.make_params(), st, mu, ic["v"], ic["mass"], ic["charge"], GC_DT[workload], delta, store_every=0,
-                     nthreads=nthreads)
+    if workload == "particle":
+        ic = synth.config2_protons(n_sample)
+        vel = np.column_stack([ic["vx"], ic["vy"], ic["vz"]])
+        st = np.column_stack([ic["t0"], ic["x"], ic["y"], ic["z"], O.particle_momentum(vel, ic["mass"])])
+        t = time.perf_counter()
+        o = O.particle_advance(O.make_field("EarthDipole"), O.make_params(**PARAMS), st, ic["mass"], ic["charge"], delta,
+                               store_every=0, nthreads=nthreads)
+    else:
+        ic = synth.config3_electrons(n_sample) if workload == "gc" else synth.config5_belt(n_sample)
+        f = O.make_field("DoubleDipole") if workload == "gc" else O.make_field("VarEarthDipole", 0.1, 10)
+        pos = np.column_stack([ic["x"], ic["y"], ic["z"]])
+        ppar, mu = O.gc_construct(f, ic["t0"], pos, ic["v"], ic["pa"], ic["mass"])
+        st = np.column_stack([ic["t0"], pos, ppar])
+        t = time.perf_counter()
+        o = O.gc_advance(f, O.make_params(), st, mu, ic["v"], ic["mass"], ic["charge"], GC_DT[workload], delta, store_every=0,
+                         nthreads=nthreads)
     el = time.perf_counter() - t
     steps = int(o["counters"][:, 1].sum())
     return steps / el, steps, el
 
 
-def cpu_sample(n_sample, delta, nthreads):
-    """The CPU oracle port on the first n_sample members of the same ensemble."""
+def reference_pool_sample(workload, n_sample, delta, cores):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as O
-    from rapt_b200 import synth
-    ic = synth.config2_protons(n_sample)
-    vel = np.column_stack([ic["vx"], ic["vy"], ic["vz"]])
-    st = np.column_stack([ic["t0"], ic["x"], ic["y"], ic["z"], O.particle_momentum(vel, ic["mass"])])
-    f, p = O.make_field("EarthDipole"), O.make_params(**PARAMS)
-    t = time.perf_counter()
-    o = O.particle_advance(f, p, st, ic["mass"], ic["charge"], delta, store_every=0, nthreads=nthreads)
-    el = time.perf_counter() - t
-    steps = int(o["counters"][:, 1].sum())
-    return steps / el, steps, el
+    import refbench
+    return refbench.time_pool(workload, n_sample, delta, cores, n_sample)
+
+
+def cpu_baseline_record(workload, delta, port_n):
+    """`cpu_baseline` of our arm: the unmodified reference (Python loop on 1 core + multiprocessing.Pool over all cores)
+    on a bounded sample; the C/OpenMP port of it as a second figure.  Falls back to the port alone when the reference
+    copy is absent (oracle/_ref is made by __graft_entry__.build())."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    cores = os.cpu_count() or 1
+    pv, psteps, pel = port_sample(workload, port_n, delta, cores)
+    port = {"value": pv, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{port_n} tracers of the same generator and seed, advance({delta} s): {psteps} steps in {pel:.1f} s, C oracle port with OpenMP"}
+    try:
+        import refbench
+        if not refbench.available():
+            raise RuntimeError("oracle/_ref missing")
+        n_pool = max(cores, 64)
+        rv, rsteps, rel, procs = refbench.time_pool(workload, n_pool, delta, cores, n_pool)
+        lv, lsteps, lel = refbench.time_loop(workload, 4, delta, n_pool)
+        refbench.close()
+        return {"value": rv, "unit": "particle-steps/s", "cores": procs, "kind": "reference",
+                "sample": f"unmodified rapt classes, {n_pool} tracers of the same generator and seed, advance({delta} s) each: "
+                          f"multiprocessing.Pool({procs}) {rsteps} steps in {rel:.1f} s; plain Python loop on one core over the "
+                          f"first 4: {lsteps} steps in {lel:.1f} s",
+                "python_loop_1core": {"value": lv, "unit": "particle-steps/s", "cores": 1},
+                "port": port}
+    except Exception as ex:          # no reference copy on this box
+        port["reference_unavailable"] = str(ex)[:200]
+        return port
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python
-    and cannot travel to the GPU box, so this is the C oracle port (bit-exact against the reference's
-    own trajectories, tests/test_oracle_golden.py), all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores -- the unmodified rapt
+    classes under multiprocessing.Pool(os.cpu_count()), each bench step a bounded sample of the
+    workload sized so that warmup + steps end within a few minutes.  Falls back to the C oracle port when the copy of
+    the reference (oracle/_ref, made by build()) is not there."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     cores = os.cpu_count() or 1
-    n_sample = args.cpu_sample
+    workload = args.workload if args.workload != "adaptive" else "particle"
+    delta = args.delta
+    import refbench
+    use_ref = refbench.available()
+    total = args.warmup + args.steps
+    if use_ref:
+        # ~1.3e3 (Particle) / ~0.5e3 (GuidingCenter) steps/s per core; ~2.9e3 / ~1e3 steps per tracer: ~2 core-seconds per
+        # tracer either way.  Budget ~150 s of wall time for the whole run.
+        n_sample = args.ref_sample or int(min(256, max(cores, (150.0 / total) * cores / 2.2)))
+    else:
+        n_sample = args.cpu_sample
     vals = []
-    for i in range(args.warmup + args.steps):
-        v, steps, el = (cpu_sample(n_sample, DELTA, cores) if args.workload == "particle"
-                        else cpu_sample_gc(args.workload, n_sample, DELTA, cores))
+    for i in range(total):
+        if use_ref:
+            v, steps, el, _ = refbench.time_pool(workload, n_sample, delta, cores, n_sample)
+        else:
+            v, steps, el = port_sample(workload, n_sample, delta, cores)
         if i >= args.warmup:
             vals.append((v, steps, el))
+    if use_ref:
+        refbench.close()
     steps = sum(s for _, s, _ in vals); el = sum(e for _, _, e in vals)
     value = steps / el
-    sample = f"first {n_sample} tracers of the {WORKLOAD_NAME[args.workload].split(':')[0]} ensemble, advance({DELTA} s) each, OpenMP x{cores}"
+    kind = "reference" if use_ref else "port"
+    how = (f"unmodified rapt classes, multiprocessing.Pool({cores})" if use_ref else f"C oracle port, OpenMP x{cores}")
+    sample = (f"{n_sample} tracers of the {WORKLOAD_NAME[workload].split(':')[0]} generator (same seed and distributions), "
+              f"advance({delta} s) each, per bench step; {how}")
     print(json.dumps({
         "impl": "reference", "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / max(len(vals), 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME[args.workload], "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME[workload], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def measured_traffic(workload, n, delta):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch, from the committed `ncu --set full`
+    capture of this configuration (profiles/ncu_traffic.json, written from the .ncu-rep by tools/ncu_summary.py)."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        for e in tab["captures"]:
+            if e["workload"] == workload and e["n"] == n and e["delta"] == delta:
+                return e["dram_bytes"], e["source"]
+    except Exception:
+        pass
+    return None, None
+
+
+def time_workload(args, workload, n_per_gpu, world, rank, dev, steps, warmup, want_e2e=True):
+    """Device-resident timing of one workload through the ensemble API.  Returns the record pieces (rank 0) or None."""
+    import torch
+    import torch.distributed as dist
+    from rapt_b200 import engine, _lib
+    n_total = n_per_gpu * world if args.scaling == "weak" else n_per_gpu
+    ens = build_ensemble(workload, n_total, world, rank)
+    n = ens.n
+    d = ens._dev
+    pristine = [c.clone() for c in d.cols]
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def one_step(ev=None):
+        ens.load_state(pristine)
+        flush.fill_(1)                                                   # L2 flush between steps
+        if ev is not None:
+            ev[0].record()
+        run_advance(ens, workload, args.delta, args.arith)
+        if ev is not None:
+            ev[1].record()
+        if world > 1:
+            ens.gather(nbins=64)                                         # pack + histogram kernel, all-gather, all-reduce
+        if ev is not None:
+            ev[2].record()
+
+    for _ in range(warmup):
+        one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    t_wall = time.perf_counter()
+    for k in range(steps):
+        one_step(evs[k])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - launches0
+    ms_kernel = sum(e[0].elapsed_time(e[1]) for e in evs)
+    ms_collect = sum(e[1].elapsed_time(e[2]) for e in evs)
+    ms = ms_kernel + ms_collect
+    out = d.out
+    cnt = out["counters"].to(torch.int64).sum(0)
+    nrows = out["nrows"].to(torch.int64).sum()
+    failed = torch.nonzero(out["status"] != 1).flatten()[:8].cpu().tolist()
+    stats = torch.tensor([float(cnt[1]), float(cnt[2]), float(nrows) - n, float((out["status"] == 1).sum()), float(n)],
+                         dtype=torch.float64, device=dev)
+    times = torch.tensor([ms, ms_kernel, ms_collect, float(clocks.get("sm_mhz") or 0), float(clocks.get("power_w") or 0)],
+                         dtype=torch.float64, device=dev)
+    per_rank = None
+    if world > 1:
+        allt = torch.empty((world, 5), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allt.view(-1), times)
+        dist.all_reduce(stats)
+        ms = float(allt[:, 0].max())
+        per_rank = {"kernel_ms_per_step": [round(float(v) / steps, 3) for v in allt[:, 1]],
+                    "collect_ms_per_step": [round(float(v) / steps, 3) for v in allt[:, 2]],
+                    "sm_mhz": [float(v) for v in allt[:, 3]], "power_w": [float(v) for v in allt[:, 4]],
+                    "note": "collect = pack/histogram kernel + NCCL all-gather + all-reduce, including the wait for the slowest rank"}
+    nstep, naccpt, ncalls, nok, nall = (float(stats[i]) for i in range(5))
+    ms_per_step = ms / steps
+    rec = dict(value=nstep / (ms_per_step * 1e-3), ms_per_step=ms_per_step, nstep=nstep, naccpt=naccpt, ncalls=ncalls,
+               failures=int(nall - nok), failed_members_rank0=[int(i) * world + rank for i in failed], clocks=clocks,
+               launches=int(launches), wall=wall, per_rank=per_rank, n=n, n_total=n_total,
+               kernel_ms_rank0=ms_kernel / steps)
+
+    # ---- end to end through the host-buffer C ABI (pinned inputs, H2D + D2H inside the timed region)
+    if want_e2e:
+        import ctypes as C
+        from rapt_b200._lib import ptr, check
+        lib = _lib.load()
+        ncol = len(pristine)
+        pin = [c.cpu().pin_memory() for c in pristine]
+        hwork = [torch.empty_like(c).pin_memory() for c in pin]
+        ex = {k: v.cpu().pin_memory() for k, v in d.extras.items()}
+        hout = dict(nrows=np.zeros(n, np.int32), nstored=np.zeros(n, np.int32), counters=np.zeros((n, 4), np.int32),
+                    status=np.zeros(n, np.int32), tcur=np.zeros(n), dt=np.zeros(n))
+        f_desc = ens.field.device_descriptor()
+        p_desc = engine.snapshot_params(None, False, arith=args.arith, **(PARAMS if workload == "particle" else {}))
+        if workload != "particle":
+            ex["dt"] = torch.full((n,), GC_DT[workload], dtype=torch.float64).pin_memory()
+
+        def host_step():
+            for w, p0 in zip(hwork, pin):
+                w.copy_(p0)
+            if workload == "particle":
+                check(lib.rapt_b200_particle_advance(
+                    C.byref(f_desc), C.byref(p_desc), C.c_int64(n), *[ptr(w.numpy()) for w in hwork], ptr(ex["mass"].numpy()),
+                    ptr(ex["charge"].numpy()), C.c_double(args.delta), C.c_int64(0), C.c_int64(0), None, ptr(hout["nrows"]),
+                    ptr(hout["nstored"]), ptr(hout["counters"]), ptr(hout["status"]), ptr(hout["tcur"]), ptr(hout["dt"])))
+            else:
+                check(lib.rapt_b200_gc_advance(
+                    C.byref(f_desc), C.byref(p_desc), C.c_int(0), C.c_int64(n), *[ptr(w.numpy()) for w in hwork],
+                    ptr(ex["mu"].numpy()), ptr(ex["v"].numpy()), ptr(ex["mass"].numpy()), ptr(ex["charge"].numpy()),
+                    ptr(ex["dt"].numpy()), C.c_double(args.delta), C.c_int64(0), C.c_int64(0), None, ptr(hout["nrows"]),
+                    ptr(hout["nstored"]), ptr(hout["counters"]), ptr(hout["status"]), ptr(hout["tcur"])))
+        host_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ts = time.perf_counter()
+            host_step()
+            print(f"[e2e {workload}] host-buffer step {1e3 * (time.perf_counter() - ts):.1f} ms", file=sys.stderr)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        tt = torch.tensor([el], dtype=torch.float64, device=dev)
+        st2 = torch.tensor([float(hout["counters"][:, 1].astype(np.int64).sum())], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(st2)
+        n_in = ncol + len(ex)
+        rec["e2e"] = {"value": float(st2[0]) * steps / float(tt[0]), "unit": "particle-steps/s",
+                      "h2d_bytes_per_step": n * n_in * 8,
+                      "d2h_bytes_per_step": n * (ncol * 8 + (2 if workload == "particle" else 1) * 8 + 4 * 4 + 3 * 4)}
+    del ens, pristine, flush
+    torch.cuda.empty_cache()
+    return rec
+
+
+def time_adaptive(args, n, dev, steps, warmup):
+    """Config 4 through rapt_b200_adaptive_advance (host-pointer ABI: constructor arguments in, final states out; the
+    epoch loop runs on the device).  Steps/s over the device time of the epoch loop, roofline from the executed mix."""
+    import torch
+    from rapt_b200 import engine, fields, synth, _lib
+    ic = synth.config4_speiser(n)
+    pos = np.column_stack([ic["x"], ic["y"], ic["z"]]); vel = np.column_stack([ic["vx"], ic["vy"], ic["vz"]])
+    f = fields.Parabolic()
+    recs = []
+    l0 = 0
+    for k in range(warmup + steps):
+        if k == warmup:
+            l0 = _lib.launch_count()
+        t = time.perf_counter()
+        r = engine.adaptive_advance(f, pos, vel, ic["t0"], ic["mass"], ic["charge"], ADAPTIVE["delta"], ADAPTIVE["gc_dt"],
+                                    store_every=0, max_rows=0, arith=args.arith, **ADAPTIVE["params"])
+        wall = time.perf_counter() - t
+        if k >= warmup:
+            recs.append((r["stats"], wall, r))
+    launches = _lib.launch_count() - l0
+    st = {k: float(np.mean([a[0][k] for a in recs])) for k in recs[0][0]}
+    wall = float(np.mean([a[1] for a in recs]))
+    r = recs[-1][2]
+    nstep = st["steps_particle"] + st["steps_gc"]
+    flops = (algorithmic_flops(st["steps_particle"], st["accepted_particle"], st["calls_particle"], f_rhs=18 + 3)
+             + gc_flops("adaptive", st["steps_gc"], st["calls_gc"]))
+    nseg = r["nseg"]
+    return dict(st=st, wall=wall, nstep=nstep, flops=flops, launches=int(launches), ok=int((r["status"] == 1).sum()),
+                nseg_max=int(nseg.max()), nseg_mean=float(nseg.mean()), n=n,
+                nseg_hist={str(int(k)): int(v) for k, v in zip(*np.unique(np.minimum(nseg, 12), return_counts=True))})
 
 
 def main():
@@ -215,13 +445,17 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="particle", choices=["particle", "gc", "belt"])
-    ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--workload", default="particle", choices=["particle", "gc", "belt", "adaptive"])
+    ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU,
+                    help="tracers per GPU (--scaling weak) or in total (--scaling strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--delta", type=float, default=DELTA)
-    ap.add_argument("--cpu-sample", type=int, default=8192)
+    ap.add_argument("--cpu-sample", type=int, default=8192, help="tracers of the C oracle-port sample")
+    ap.add_argument("--ref-sample", type=int, default=0, help="tracers per step of the Python-reference sample (0: sized for ~150 s)")
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the gc / belt / adaptive sub-records (extra.workloads)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -233,7 +467,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from rapt_b200 import engine, fields, _lib
+    from rapt_b200 import engine, _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -245,186 +479,100 @@ def main():
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     _lib.init(local)
-    is_gc = args.workload != "particle"
-    field = gc_field(args.workload) if is_gc else fields.EarthDipole()
-    n = args.n_per_gpu
-    ens = make_ensemble(world, rank, n, args.workload)
-    ncol = len(ens["cols"])
-    pristine = [torch.tensor(c, device=dev) for c in ens["cols"]]
-    mass = torch.tensor(ens["mass"], device=dev); charge = torch.tensor(ens["charge"], device=dev)
-    if is_gc:
-        gmu = torch.tensor(ens["mu"], device=dev); gv = torch.tensor(ens["v"], device=dev); gdt = torch.tensor(ens["dt"], device=dev)
-    out = engine.alloc_outputs(n, dev)
-    work = [torch.empty_like(c) for c in pristine]
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    gathered = torch.empty((world, n, ncol), dtype=torch.float64, device=dev) if world > 1 else None
-    nbins = 64
-    hist_edges = torch.logspace(4.5, 7.5, nbins + 1, dtype=torch.float64, device=dev)
-
-    def one_step(timed_events=None):
-        for w, p0 in zip(work, pristine):
-            w.copy_(p0)
-        flush.fill_(1)                                                   # L2 flush between steps
-        if timed_events is not None:
-            timed_events[0].record()
-        if is_gc:
-            engine.gc_advance_dev(field, work, gmu, gv, mass, charge, gdt, args.delta, out, arith=args.arith)
-        else:
-            engine.particle_advance_dev(field, work, mass, charge, args.delta, out, arith=args.arith, **PARAMS)
-        if world > 1:
-            fin = torch.stack(work, dim=1)
-            dist.all_gather_into_tensor(gathered.view(-1), fin.view(-1))
-            if is_gc:      # diagnostic: histogram of the radial distance (drift-shell occupation)
-                h = torch.histc(torch.sqrt((fin[:, 1:4] ** 2).sum(1)) / 6378137.0, bins=nbins, min=0.0, max=16.0)
-            else:          # diagnostic: kinetic-energy histogram
-                p2 = (fin[:, 4:7] ** 2).sum(1)
-                ke_ev = (torch.sqrt(1 + p2 / (mass * 299792458.0) ** 2) - 1) * mass * 299792458.0 ** 2 / 1.602176565e-19
-                h = torch.histc(torch.log10(ke_ev), bins=nbins, min=4.5, max=7.5)
-            dist.all_reduce(h)
-        if timed_events is not None:
-            timed_events[1].record()
-
     fp64_peak, _ = engine.fp64_peak(1 << 15)
-    for _ in range(args.warmup):
-        one_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    launches0 = _lib.launch_count()
-    sampler = ClockSampler(local)
-    sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_wall = time.perf_counter()
-    for k in range(args.steps):
-        one_step(evs[k])
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    wall = time.perf_counter() - t_wall
-    clocks = sampler.stop()
-    launches = _lib.launch_count() - launches0
-    ms = sum(a.elapsed_time(b) for a, b in evs)
-    cnt = out["counters"].to(torch.int64).sum(0)
-    nrows = out["nrows"].to(torch.int64).sum()
-    stats = torch.tensor([float(cnt[1]), float(cnt[2]), float(nrows) - n, float((out["status"] == 1).sum()), ms],
-                         dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        dist.all_reduce(stats)
-        ms = float(mx[4])
-    nstep, naccpt, ncalls, nok = (float(stats[i]) for i in range(4))
-    ms_per_step = ms / args.steps
-    value = nstep / (ms_per_step * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
 
-    # ---- end to end through the host-buffer C ABI (pinned inputs, H2D + D2H inside the timed region)
-    e2e = None
-    if not args.no_e2e and not is_gc:
-        pin = [torch.tensor(c).pin_memory() for c in ens["cols"]]
-        pm = torch.tensor(ens["mass"]).pin_memory(); pq = torch.tensor(ens["charge"]).pin_memory()
-        hwork = [torch.empty_like(c).pin_memory() for c in pin]
-        hout = dict(nrows=np.zeros(n, np.int32), nstored=np.zeros(n, np.int32), counters=np.zeros((n, 4), np.int32),
-                    status=np.zeros(n, np.int32), tcur=np.zeros(n), dt=np.zeros(n))
-        import ctypes as C
-        from rapt_b200._lib import ptr, check
-        f_desc = field.device_descriptor(); p_desc = engine.snapshot_params(None, False, arith=args.arith, **PARAMS)
-        lib = _lib.load()
+    def roofline(flops_per_gpu_step, ms_per_step, nstep_per_gpu, traffic=(None, None), io_bytes=None):
+        achieved = flops_per_gpu_step / (ms_per_step * 1e-3) / 1e12
+        r = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+             "traffic": traffic[0], "traffic_source": traffic[1],
+             "peak_source": "FP64 DFMA microbenchmark measured in this run (rapt_b200_fp64_peak); MEASURED_PEAKS.json has HBM and bf16 only",
+             "algorithmic_flop_per_step": flops_per_gpu_step / max(nstep_per_gpu, 1)}
+        if io_bytes:
+            r["hbm"] = {"algorithmic_bytes": io_bytes, "achieved_GBps": io_bytes / (ms_per_step * 1e-3) / 1e9,
+                        "peak_GBps": peaks.get("hbm_gbs"), "note": "state in/out only: compute-bound kernel"}
+        return r
 
-        def host_step():
-            for w, p0 in zip(hwork, pin):
-                w.copy_(p0)
-            check(lib.rapt_b200_particle_advance(
-                C.byref(f_desc), C.byref(p_desc), C.c_int64(n), *[ptr(w.numpy()) for w in hwork], ptr(pm.numpy()), ptr(pq.numpy()),
-                C.c_double(args.delta), C.c_int64(0), C.c_int64(0), None, ptr(hout["nrows"]), ptr(hout["nstored"]),
-                ptr(hout["counters"]), ptr(hout["status"]), ptr(hout["tcur"]), ptr(hout["dt"])))
-        host_step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            ts = time.perf_counter()
-            host_step()
-            print(f"[e2e] host-buffer step {1e3 * (time.perf_counter() - ts):.1f} ms", file=sys.stderr)
-        torch.cuda.synchronize()
-        el = time.perf_counter() - t0
-        tt = torch.tensor([el], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_steps = float(hout["counters"][:, 1].astype(np.int64).sum())
-        st2 = torch.tensor([e2e_steps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(st2)
-        e2e = {"value": float(st2[0]) * args.steps / float(tt[0]), "unit": "particle-steps/s",
-               "h2d_bytes_per_step": n * 9 * 8, "d2h_bytes_per_step": n * (7 * 8 + 2 * 8 + 4 * 4 + 3 * 4)}
+    res = None
+    if args.workload == "adaptive":
+        a = time_adaptive(args, args.n_per_gpu, dev, args.steps, args.warmup)
+        ms = a["st"]["ms_epochs"]
+        res = {"metric": "particle-steps/s", "value": a["nstep"] / (ms * 1e-3), "unit": "particle-steps/s", "n_gpus": 1,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": WORKLOAD_NAME["adaptive"], "particles_per_gpu": a["n"], "arith": args.arith,
+                          "l2": "state (9 columns x n) is re-uploaded every step; epochs stream > L2 of state",
+                          "epochs": a["st"]["epochs"], "tracers_ok": a["ok"], "segments_max": a["nseg_max"],
+                          "segments_mean": a["nseg_mean"], "segments_hist": a["nseg_hist"],
+                          "steps_particle_mode": a["st"]["steps_particle"], "steps_gc_mode": a["st"]["steps_gc"],
+                          "kernel_ms": {k: a["st"][k] for k in ("ms_particle", "ms_gc", "ms_switch", "ms_epochs")},
+                          "tracer_launches": [a["st"]["tracer_launches_particle"], a["st"]["tracer_launches_gc"]]},
+               "gpu_launches": a["launches"], "wall_s_per_step_host_abi": a["wall"],
+               "roofline": roofline(a["flops"], ms, a["nstep"]),
+               "e2e": {"value": a["nstep"] / a["wall"], "unit": "particle-steps/s", "h2d_bytes_per_step": a["n"] * 9 * 8,
+                       "d2h_bytes_per_step": a["n"] * (8 * 8 + 4 * 4 + 4 * 4)}}
+    else:
+        is_gc = args.workload != "particle"
+        r = time_workload(args, args.workload, args.n_per_gpu, world, rank, dev, args.steps, args.warmup,
+                          want_e2e=not args.no_e2e)
+        if rank == 0:
+            flops = (gc_flops(args.workload, r["nstep"], r["ncalls"]) if is_gc
+                     else algorithmic_flops(r["nstep"], r["naccpt"], r["ncalls"])) / world
+            n = r["n"]
+            io_bytes = n * ((10 * 8 + 5 * 8 + 8 + 7 * 4) if is_gc else (9 * 8 + 7 * 8 + 2 * 8 + 7 * 4))
+            # the roofline is the KERNEL's: rank 0's kernel time per step, its share of the flops
+            res = {
+                "metric": "particle-steps/s", "value": r["value"], "unit": "particle-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD_NAME[args.workload], "particles_per_gpu": n, "particles_total": r["n_total"],
+                           "delta_s": args.delta, "arith": args.arith,
+                           "l2": "512 MiB flush write between steps (inputs < L2)",
+                           "particle_steps_per_bench_step": r["nstep"], "accepted": r["naccpt"], "output_rows": r["ncalls"],
+                           # members whose row loop ended on scipy's nsteps = 500 limit, as the reference's does for the
+                           # same member (tests/test_gpu_particle.py::test_config2_solver_failure_member)
+                           "solver_failures": r["failures"], "failed_members_rank0": r["failed_members_rank0"],
+                           "collective": ("ensemble.gather(): pack+histogram kernel, NCCL all_gather(final states, in place) + "
+                                          "all_reduce(histogram, invariant sums)") if world > 1 else "none"},
+                "clocks": r["clocks"],
+                "gpu_launches": r["launches"],
+                "wall_s_timed_region": r["wall"],
+                "roofline": roofline(flops, r["kernel_ms_rank0"], r["nstep"] / world,
+                                     measured_traffic(args.workload, n, args.delta), io_bytes),
+            }
+            if r["per_rank"]:
+                res["per_rank"] = r["per_rank"]
+            if "e2e" in r:
+                res["e2e"] = r["e2e"]
+        # ---- the other named configurations, measured in the same run (N = 1 only): sub-records for the driver's file
+        if world == 1 and not args.no_extra and args.workload == "particle" and args.n_per_gpu == N_PER_GPU:
+            extra = {}
+            for w in ("gc", "belt"):
+                x = time_workload(args, w, N_PER_GPU, 1, 0, dev, 2, 3, want_e2e=False)
+                fl = gc_flops(w, x["nstep"], x["ncalls"])
+                extra[w] = {"workload": WORKLOAD_NAME[w], "particles": x["n"], "delta_s": args.delta, "value": x["value"],
+                            "unit": "particle-steps/s", "ms_per_step": x["ms_per_step"], "steps": 2, "warmup": 3,
+                            "gpu_launches": x["launches"], "solver_failures": x["failures"],
+                            "roofline": roofline(fl, x["kernel_ms_rank0"], x["nstep"],
+                                                 measured_traffic(w, x["n"], args.delta))}
+            a = time_adaptive(args, N_PER_GPU, dev, 1, 1)
+            ms = a["st"]["ms_epochs"]
+            extra["adaptive"] = {"workload": WORKLOAD_NAME["adaptive"], "particles": a["n"], "value": a["nstep"] / (ms * 1e-3),
+                                 "unit": "particle-steps/s", "ms_per_step": ms, "steps": 1, "warmup": 1,
+                                 "epochs": a["st"]["epochs"], "tracers_ok": a["ok"], "segments_max": a["nseg_max"],
+                                 "kernel_ms": {k: a["st"][k] for k in ("ms_particle", "ms_gc", "ms_switch", "ms_epochs")},
+                                 "e2e_value": a["nstep"] / a["wall"], "gpu_launches": a["launches"],
+                                 "roofline": roofline(a["flops"], ms, a["nstep"])}
+            res["extra"] = {"workloads": extra}
 
-    if not args.no_e2e and is_gc:
-        # guiding-centre workloads: host-buffer C ABI (numpy in, numpy out; H2D + D2H inside the call)
-        st_host = np.column_stack(ens["cols"])
-        engine.gc_advance(field, st_host, ens["mu"], ens["v"], ens["mass"], ens["charge"], ens["dt"], args.delta,
-                          store_every=0, arith=args.arith)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            oh = engine.gc_advance(field, st_host, ens["mu"], ens["v"], ens["mass"], ens["charge"], ens["dt"], args.delta,
-                                   store_every=0, arith=args.arith)
-        el = time.perf_counter() - t0
-        tt = torch.tensor([el], dtype=torch.float64, device=dev)
-        st2 = torch.tensor([float(oh["counters"][:, 1].astype(np.int64).sum())], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(st2)
-        e2e = {"value": float(st2[0]) * args.steps / float(tt[0]), "unit": "particle-steps/s",
-               "h2d_bytes_per_step": n * 10 * 8, "d2h_bytes_per_step": n * (5 * 8 + 8 + 4 * 4 + 3 * 4)}
-
-    if rank == 0:
-        flops = gc_flops(args.workload, nstep, ncalls) if is_gc else algorithmic_flops(nstep, naccpt, ncalls)
-        achieved = flops / world / (ms_per_step * 1e-3) / 1e12     # per GPU: the kernel's own rate
-        io_bytes = n * ((10 * 8 + 5 * 8 + 8 + 7 * 4) if is_gc else (9 * 8 + 7 * 8 + 2 * 8 + 7 * 4))
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        res = {
-            "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME[args.workload], "particles_per_gpu": n, "delta_s": args.delta, "arith": args.arith,
-                       "l2": "512 MiB flush write between steps (inputs < L2)",
-                       "particle_steps_per_bench_step": nstep, "accepted": naccpt, "output_rows": ncalls,
-                       "solver_failures": int(n * world - nok),     # members whose row loop ended on scipy's nsteps=500
-                                                                   # limit, exactly as the reference's does (checked vs the oracle)
-                       "collective": "all_gather(final state) + all_reduce(KE histogram) over NCCL" if world > 1 else "none"},
-            "clocks": clocks,
-            "gpu_launches": int(launches),
-            "wall_s_timed_region": wall,
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this configuration, one
-                         # launch, from `ncu --set full` (profiles/r1_particle_v8_bench_kernel_ncu_summary.txt):
-                         # 452 MB + 289 MB.  4x the algorithmic state I/O because tracers are fetched in
-                         # longest-first order, i.e. as scattered 8-byte accesses (32-byte sectors); at 0.27 s
-                         # per launch that is 3 GB/s and irrelevant to this compute-bound kernel.
-                         "traffic": 740606720 if (n == N_PER_GPU and args.delta == DELTA and not is_gc) else None,
-                         "peak_source": "FP64 DFMA microbenchmark measured in this run (rapt_b200_fp64_peak); "
-                                        "MEASURED_PEAKS.json has HBM and bf16 only",
-                         "algorithmic_flop_per_step": flops / nstep,
-                         "hbm": {"algorithmic_bytes": io_bytes, "achieved_GBps": io_bytes / (ms_per_step * 1e-3) / 1e9,
-                                 "peak_GBps": peaks.get("hbm_gbs"), "note": "state in/out only: compute-bound kernel"}},
-        }
-        if e2e is not None:
-            res["e2e"] = e2e
-        if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            v, steps, el = (cpu_sample_gc(args.workload, min(args.cpu_sample, 2048), args.delta, cores) if is_gc
-                            else cpu_sample(args.cpu_sample, args.delta, cores))
-            # the unmodified Python reference cannot travel to the GPU box (/root/reference is absent there); its rate was
-            # measured in the build container (README Particle case 1.4-1.6e3, GuidingCenter 0.46e3
-            # particle-steps/s on one core) and is quoted here for scale only -- the C port above is ~10^3 x faster per core
-            py_ref = {"value": 0.46e3 if is_gc else 1.4e3, "unit": "particle-steps/s per core", "measured": "build container, SURVEY.md section 6; not re-timed in this run"}
-            res["cpu_baseline"] = {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": "port", "python_reference": py_ref,
-                                   "sample": f"first {min(args.cpu_sample, 2048) if is_gc else args.cpu_sample} tracers of the same ensemble, advance({args.delta} s), "
-                                             f"{steps} steps in {el:.1f} s, C oracle port with OpenMP"}
+    if rank == 0 and res is not None:
+        if not args.no_cpu_baseline and world == 1:
+            w = args.workload if args.workload != "adaptive" else "particle"
+            res["cpu_baseline"] = cpu_baseline_record(w, args.delta, args.cpu_sample if w == "particle" else min(args.cpu_sample, 2048))
         sys.stdout.flush()
         os.dup2(fd_out, 1)
         print(json.dumps(res), flush=True)

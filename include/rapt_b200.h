@@ -264,6 +264,14 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
                                int32_t *nstored, int32_t *nseg, int32_t *mode_out, double *fin,
                                int32_t *counters, int32_t *status, int32_t *epochs_out);
 
+/* What the last rapt_b200_adaptive_advance of the calling thread did, for the roofline of the mix it executed
+ * (bench.py --workload adaptive): out[0..14] = epochs, particle-kernel launches, guiding-centre-kernel launches,
+ * tracers handed to particle launches (sum over epochs), same for guiding-centre launches, particle-mode attempted
+ * steps, accepted steps, solver calls (= rows), guiding-centre attempted steps, solver calls, and the device time in ms
+ * of the particle kernels, the guiding-centre kernels (the two run concurrently on two streams), the switch/regroup
+ * kernels, and of the whole epoch loop; out[14] reserved. */
+int rapt_b200_adaptive_last_stats(double *out, int n);
+
 /* ---- mode-switch transforms, exposed for callers that drive segments themselves:
  * GuidingCenter.init(Particle) (GuidingCenter.py:168-186, utils.py:251-326) and
  * Particle.init(GuidingCenter) (Particle.py:149-164, utils.py:376-433; t_eval = the new Particle's tcur). */
@@ -274,6 +282,21 @@ int rapt_b200_switch_g2p(const rapt_field_t *f, int arith, int64_t n, const doub
 /* isadiabatic predicates (Particle.py:345-384, GuidingCenter.py:287-327): out[i] = 0/1 */
 int rapt_b200_isadiabatic(const rapt_field_t *f, const rapt_params_t *p, int mode, int64_t n, const double *rows,
                           int64_t row_stride, const double *mu, const double *mass, const double *charge, int32_t *out);
+
+/* ---- final-state diagnostics of one shard (multi-GPU runs; SURVEY.md section 8b `rapt_b200_allgather_final` /
+ * `rapt_b200_histogram`, BASELINE.json north_star "NCCL ... only to all-gather final states and diagnostics (histograms,
+ * invariants)").  The reference has no counterpart beyond its per-object getters: kind 0 bins log10 of
+ * Particle.getke() in eV (Particle.py:442-454), kind 1 bins the radial distance in Earth radii (getr, GuidingCenter.py:
+ * 470-473).  ONE kernel pass over the DEVICE state columns cols[0..ncol) (t,x,y,z,px,py,pz or t,X,Y,Z,ppar):
+ *   packed  (optional) receives the [n][ncol] rows that the caller's all-gather sends (it may point INTO the gather
+ *           buffer at this rank's slot, so no second copy is made);
+ *   hist    int64[nbins], ACCUMULATED (zero it first): counts of q in [lo, hi], bins as numpy.histogram;
+ *   stats   double[4], ACCUMULATED: tracers with status 1, sum q, sum q^2 over those, tracers outside [lo, hi].
+ * The collective itself (NCCL all-gather of `packed`, sum-all-reduce of hist/stats) is issued by the host layer on the
+ * same stream through torch.distributed (rapt_b200/dist.py).  `cols` is a HOST array of device pointers. */
+int rapt_b200_final_diagnostics_dev(int kind, int64_t n, int ncol, const double *const *cols, const double *mass,
+                                    const int32_t *status, double *packed, int nbins, double lo, double hi,
+                                    int64_t *hist, double *stats, void *stream);
 
 /* kernel launches performed by this library since load (for bench.py's gpu_launches) */
 int64_t rapt_b200_launch_count(void);

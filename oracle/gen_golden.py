@@ -588,7 +588,61 @@ def case_fail():
          traj=g.trajectory, counters=Lg, tcur=g.tcur, mu=g.mu)
 
 
+def case_e2long():
+    """First 32 protons of config 2 at the BENCH horizon, advance(10.0) (BASELINE.json configs[1]): final state, row
+    count, (nfcn, nstep, naccpt, nrejct) totals per proton.  ~3e3 steps per proton-second."""
+    n = 32
+    ic = synth.config2_protons(n)
+    fin, nrows, tot, tcur = [], [], [], []
+    f = rf.EarthDipole()
+    for i in range(n):
+        pos = (ic["x"][i], ic["y"][i], ic["z"][i]); vel = (ic["vx"][i], ic["vy"][i], ic["vz"][i])
+        p, L = run_particle(pos, vel, m_pr, e, f, 10.0, cyclotronresolution=20)
+        fin.append(p.trajectory[-1]); nrows.append(p.trajectory.shape[0]); tot.append(L.sum(0)); tcur.append(p.tcur)
+    save("e2_config2_first32_10s", n=n, seed=20260201, delta=10.0, params=parjson(cyclotronresolution=20),
+         final=np.array(fin), nrows=np.array(nrows), totals=np.array(tot), tcur=np.array(tcur))
+
+
+def case_g1long():
+    """A few hundred gyroperiods (north_star's short horizon): the g1b proton for 40 s = ~325 gyroperiods, 6.5e3 rows.
+    Stored: every 16th row + the last, per-call counters, totals."""
+    v = ru.speedfromKE(1e6, m_pr, 'ev')
+    pos = (3.1 * Re, 2.3 * Re, 0.7 * Re)
+    vel = (v * 0.31, -v * 0.52, v * np.sqrt(1 - 0.31 ** 2 - 0.52 ** 2))
+    p, L = run_particle(pos, vel, m_pr, e, rf.EarthDipole(), 40, cyclotronresolution=20)
+    tr = p.trajectory
+    save("g1c_325_gyroperiods", pos=np.array(pos), vel=np.array(vel), mass=m_pr, charge=e, delta=40.0,
+         params=parjson(cyclotronresolution=20), nrows=tr.shape[0], every=16, traj_dec=tr[::16], last=tr[-1],
+         counters=L.astype(np.int16), tcur=p.tcur,
+         gyroperiods=40.0 / ru.cyclotron_period(0.0, np.array(pos), np.array(vel), rf.EarthDipole(), m_pr, e))
+
+
+def case_getters():
+    """N2 getters over stored trajectories: Particle.guidingcenter / mu (Particle.py:463-482) and GuidingCenter.getB /
+    getgamma / getBm / getke (GuidingCenter.py:486-591), UNMODIFIED reference, on the g1b proton (1 s, DoubleDipole and
+    EarthDipole) and the g2-type electron."""
+    v = ru.speedfromKE(1e6, m_pr, 'ev')
+    pos = (3.1 * Re, 2.3 * Re, 0.7 * Re)
+    vel = (v * 0.31, -v * 0.52, v * np.sqrt(1 - 0.31 ** 2 - 0.52 ** 2))
+    out = {}
+    for tag, f in (("ed", rf.EarthDipole()), ("dd", rf.DoubleDipole())):
+        p, _ = run_particle(pos, vel, m_pr, e, f, 1.0, cyclotronresolution=20)
+        out[f"p_{tag}_traj"] = p.trajectory
+        out[f"p_{tag}_gc"] = p.guidingcenter()
+        out[f"p_{tag}_mu"] = p.mu()
+        out[f"p_{tag}_cycrad"] = p.cycrad(); out[f"p_{tag}_cycper"] = p.cycper()
+    ve = ru.speedfromKE(1e6, m_el)
+    for tag, f, ke in (("dd", rf.DoubleDipole(), 1e6), ("ed_nr", rf.EarthDipole(), 0.3)):     # relativistic / gamma-1 < 1e-6
+        vv = ru.speedfromKE(ke, m_el)
+        g, _ = run_gc((6 * Re, 0.4 * Re, 0.3 * Re), vv, 40, m_el, -e, f, 3.0, GCtimestep=0.05)
+        out[f"g_{tag}_traj"] = g.trajectory; out[f"g_{tag}_mu"] = g.mu; out[f"g_{tag}_v"] = vv
+        out[f"g_{tag}_B"] = g.getB(); out[f"g_{tag}_gamma"] = g.getgamma(); out[f"g_{tag}_Bm"] = g.getBm()
+        out[f"g_{tag}_ke"] = g.getke(); out[f"g_{tag}_cycrad"] = g.cycrad()
+    save("getters", pos=np.array(pos), vel=np.array(vel), mass_p=m_pr, mass_e=m_el, charge=e, **out)
+
+
 CASES = {
+    "e2long": case_e2long, "g1long": case_g1long, "getters": case_getters,
     "fail": case_fail,
     "g1": case_g1, "g1b": case_g1b, "pfields": case_pfields, "g2": case_g2, "gcfields": case_gcfields,
     "g3": case_g3, "e4": case_e4, "adip": case_adaptive_dipole, "e2": case_e2, "e3": case_e3,

@@ -202,6 +202,19 @@ def particle_advance(f, par, state, mass, charge, delta, check_adiab=False, stor
                 status=status, tcur=tcur, dt=dt, percall=percall[:max(int(nrows[0]) - 1, 0)] if want_percall else None)
 
 
+def errgap(fn, n, *a, **k):
+    """Run oracle.particle_advance / gc_advance (fn) and also return, per tracer, the smallest |err - 1| over all its
+    step attempts: how close its nearest accept/reject decision was (parity report, tests/test_gpu_properties.py)."""
+    gap = np.full(n, 1e300)
+    lib().oracle_set_errgap_out(_p(gap))
+    try:
+        o = fn(*a, **k)
+    finally:
+        lib().oracle_set_errgap_out(None)
+    o["errgap"] = gap
+    return o
+
+
 def gc_construct(f, t0, pos, v, pa, mass):
     pos = _d(pos).reshape(-1, 3); n = len(pos)
     t0 = np.broadcast_to(_d(t0), (n,)).copy(); v = np.broadcast_to(_d(v), (n,)).copy()

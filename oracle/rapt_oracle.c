@@ -58,6 +58,11 @@ typedef struct {
 /* set when a Grid field is evaluated outside its bounds: the reference raises ValueError there
  * (scipy RegularGridInterpolator, bounds_error=True) and the advance in progress is abandoned */
 static __thread int g_field_err = 0;
+/* diagnostics for the parity report: the smallest |err - 1| over all step attempts of the tracer being integrated
+ * (how close its nearest accept/reject decision was), written to g_errgap_out[i] when that is set */
+static __thread double tl_errgap = 1e300;
+static double *g_errgap_out = 0;
+void oracle_set_errgap_out(double *p) { g_errgap_out = p; }
 
 typedef struct {
     double rtol, atol;              /* params["solvertolerances"] __init__.py:27 */
@@ -376,6 +381,7 @@ static int dop853(int n, rhs_fn f, void *ctx, double *xio, double *y, double xen
         double deno = err + 0.01 * err2;
         if (deno <= 0.0) deno = 1.0;
         err = fabs(h) * err * sqrt(1.0 / (n * deno));
+        if (fabs(err - 1.0) < tl_errgap) tl_errgap = fabs(err - 1.0);
         double fac11 = pow(err, expo1);
         double fac = fac11 / pow(facold, beta);
         fac = fmax(facc2, fmin(facc1, fac / safe));
@@ -449,6 +455,7 @@ static int dopri5(int n, rhs_fn f, void *ctx, double *xio, double *y, double xen
             err += (k4[i] / sk) * (k4[i] / sk);
         }
         err = sqrt(err / n);
+        if (fabs(err - 1.0) < tl_errgap) tl_errgap = fabs(err - 1.0);
         double fac11 = pow(err, expo1);
         double fac = fac11 / pow(facold, beta);
         fac = fmax(facc2, fmin(facc1, fac / safe));
@@ -1049,13 +1056,14 @@ void oracle_particle_advance(const ofield_t *f, const oparams_t *p, long n,
     for (long i = 0; i < n; i++) {
         double st[7] = { t[i], x[i], y[i], z[i], px[i], py[i], pz[i] };
         ocount_t c = { 0, 0, 0, 0 };
-        g_field_err = 0;
+        g_field_err = 0; tl_errgap = 1e300;
         long ri = 0, ns = 0, nc = 0;
         double *r = rows ? rows + (size_t)i * max_rows * 8 : NULL;
         if (r && store_every > 0 && max_rows > 0) { memcpy(r, st, sizeof st); r[7] = 0; ns = 1; }
         status[i] = particle_advance_one(f, p, st, mass[i], charge[i], delta, check_adiab, r, max_rows, store_every,
                                          &ri, &ns, n == 1 ? percall : NULL, max_calls, &nc, &c, &tcur[i], &dt[i]);
         t[i] = st[0]; x[i] = st[1]; y[i] = st[2]; z[i] = st[3]; px[i] = st[4]; py[i] = st[5]; pz[i] = st[6];
+        if (g_errgap_out) g_errgap_out[i] = tl_errgap;
         nrows[i] = ri + 1; nstored[i] = ns;
         counters[4 * i] = c.nfcn; counters[4 * i + 1] = c.nstep; counters[4 * i + 2] = c.naccpt; counters[4 * i + 3] = c.nrejct;
     }
@@ -1083,13 +1091,14 @@ void oracle_gc_advance(const ofield_t *f, const oparams_t *p, int eom, long n,
     for (long i = 0; i < n; i++) {
         double st[5] = { t[i], x[i], y[i], z[i], ppar[i] };
         ocount_t c = { 0, 0, 0, 0 };
-        g_field_err = 0;
+        g_field_err = 0; tl_errgap = 1e300;
         long ri = 0, ns = 0, nc = 0;
         double *r = rows ? rows + (size_t)i * max_rows * 8 : NULL;
         if (r && store_every > 0 && max_rows > 0) { memcpy(r, st, sizeof st); r[5] = mu[i]; r[6] = 0; r[7] = 0; ns = 1; }
         status[i] = gc_advance_one(f, p, eom, st, mu[i], v[i], mass[i], charge[i], dt[i], delta, check_adiab,
                                    r, max_rows, store_every, &ri, &ns, n == 1 ? percall : NULL, max_calls, &nc, &c, &tcur[i]);
         t[i] = st[0]; x[i] = st[1]; y[i] = st[2]; z[i] = st[3]; ppar[i] = st[4];
+        if (g_errgap_out) g_errgap_out[i] = tl_errgap;
         nrows[i] = ri + 1; nstored[i] = ns;
         counters[4 * i] = c.nfcn; counters[4 * i + 1] = c.nstep; counters[4 * i + 2] = c.naccpt; counters[4 * i + 3] = c.nrejct;
     }

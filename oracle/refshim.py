@@ -1,8 +1,9 @@
 """Import the UNMODIFIED reference (mkozturk/rapt, /root/reference) in this container.
 
-TEST INFRASTRUCTURE ONLY.  Used by oracle/gen_golden.py to produce tests/golden/*.npz
-and by nothing else; /root/reference does not exist on the GPU box, so nothing in
-tests/, smoke() or bench.py imports this module at run time.
+TEST INFRASTRUCTURE ONLY.  Used by oracle/gen_golden.py to produce tests/golden/*.npz and by
+oracle/refbench.py, the timing of the reference's own CPU path that bench.py reports as its baseline
+(`cpu_baseline`, `--impl reference`).  /root/reference does not exist on the GPU box; there the copy that
+`__graft_entry__.build()` pip-installed into oracle/_ref/ is imported.  No test reads either at run time.
 
 Two non-invasive shims (no reference file is modified), see SURVEY.md §8(c):
   1. scipy.misc.derivative is gone in scipy >= 1.12 but rapt/flutils.py:19 imports it at
@@ -15,7 +16,15 @@ counters (nfcn, nstep, naccpt, nrejct = iwork[16:20]) of every solver call.
 import sys, types
 import numpy as np
 
-REFERENCE_PATH = "/root/reference"
+import os
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the source tree in the build container; on the GPU box only the copy that __graft_entry__.build() installed with pip
+# into oracle/_ref/ (git-ignored build output, travels with the snapshot) exists
+REFERENCE_PATH = "/root/reference" if os.path.isdir("/root/reference/rapt") else os.path.join(_HERE, "_ref")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_PATH, "rapt"))
 SOLVER_LOG = []          # one (nfcn, nstep, naccpt, nrejct) tuple per r.integrate() call
 
 

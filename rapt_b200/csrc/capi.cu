@@ -26,7 +26,15 @@ thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 int g_device = -1, g_sms = 0;
 int *g_queue = nullptr;          // device work counters (ring of 64 ints so async calls do not collide)
-int g_queue_slot = 0;
+std::atomic<int> g_queue_slot{0};
+
+// what the last rapt_b200_adaptive_advance of this thread did (rapt_b200_adaptive_last_stats)
+struct AdaptiveStats {
+    long long epochs = 0, launches_p = 0, launches_g = 0, tracer_launches_p = 0, tracer_launches_g = 0;
+    long long steps_p = 0, accepted_p = 0, calls_p = 0, steps_g = 0, calls_g = 0;
+    double ms_particle = 0, ms_gc = 0, ms_switch = 0, ms_epochs = 0, ms_total = 0;
+};
+thread_local AdaptiveStats g_adaptive_stats;
 
 // scratch for the longest-first work ordering (grown on demand, reused across calls)
 struct SortScratch {
@@ -59,9 +67,26 @@ int ensure_init()
     return rapt_b200_init(0);
 }
 
+// device-pointer entry points: the state must live on the device the library is bound to (its work counters, sort
+// scratch and launches are there); anything else is reported instead of faulting inside the kernel
+int check_on_bound_device(const void *p, const char *what)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return RAPT_OK; }
+    if (at.type == cudaMemoryTypeDevice && at.device != g_device)
+        return fail(RAPT_E_ARG, "%s: the state lives on device %d but librapt_b200 is bound to device %d -- call "
+                                "rapt_b200_init(%d) (one process per GPU)", what, at.device, g_device, at.device);
+    if (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeUnregistered)
+        return fail(RAPT_E_ARG, "%s: host pointer passed to a device-pointer entry point", what);
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != g_device) cudaSetDevice(g_device);
+    return RAPT_OK;
+}
+
 int *next_queue(cudaStream_t s)
 {
-    int *q = g_queue + (g_queue_slot++ & 63);
+    int *q = g_queue + (g_queue_slot.fetch_add(1) & 63);
     cudaMemsetAsync(q, 0, sizeof(int), s);
     return q;
 }
@@ -335,6 +360,62 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, doubl
     if (s == 12345.678) out[0] = s;   // never true; keeps the chains alive
 }
 
+// Final-state diagnostics of a shard in ONE pass over the state columns (BASELINE.json north_star: "all-gather final
+// states and diagnostics (histograms, invariants)"): packs the SoA columns into the [n][ncol] rows the all-gather sends,
+// bins a per-tracer quantity into a shared-memory histogram (one global atomic per bin and block) and accumulates the
+// sums of an invariant.  kind 0: log10 of the kinetic energy in eV from (px, py, pz, mass) -- Particle.getke,
+// Particle.py:442-454; kind 1: radial distance in Earth radii (drift-shell occupation of a guiding-centre ensemble).
+// stats: [0] tracers with status 1, [1] sum q, [2] sum q^2, [3] tracers outside [lo, hi).
+__global__ void __launch_bounds__(256) k_final_diagnostics(int kind, long long n, int ncol, rapt::DiagCols c,
+                                                           const double *__restrict__ mass, const int *__restrict__ status,
+                                                           double *__restrict__ packed, int nbins, double lo, double hi,
+                                                           unsigned long long *__restrict__ hist, double *__restrict__ stats)
+{
+    extern __shared__ unsigned int sh_hist[];
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) sh_hist[b] = 0;
+    __syncthreads();
+    double s_ok = 0, s_q = 0, s_q2 = 0, s_out = 0;
+    const double scale = nbins / (hi - lo);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (k < ncol) ? c.col[k][i] : 0.0;
+        if (packed) {
+            double *row = packed + i * ncol;
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k < ncol) row[k] = v[k];
+        }
+        double q;
+        if (kind == 0) {
+            const double m = mass[i], mc = m * 299792458.0;
+            const double p2 = v[4] * v[4] + v[5] * v[5] + v[6] * v[6];
+            const double g = sqrt(1.0 + p2 / (mc * mc));
+            const double ke = (g - 1.0 < 1e-6) ? 0.5 * p2 / m : (g - 1.0) * mc * 299792458.0;
+            q = log10(ke / 1.602176565e-19);
+        } else {
+            q = sqrt(v[1] * v[1] + v[2] * v[2] + v[3] * v[3]) / 6378137.0;
+        }
+        const bool ok = !status || status[i] == 1;
+        if (ok) { s_ok += 1; s_q += q; s_q2 += q * q; }
+        const int b = (int)floor((q - lo) * scale);
+        if (q >= lo && b < nbins) atomicAdd(&sh_hist[b], 1u);
+        else if (q == hi) atomicAdd(&sh_hist[nbins - 1], 1u);        // closed last bin, as numpy.histogram
+        else s_out += 1;
+    }
+    // warp-reduce the four sums, one atomic per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s_ok += __shfl_xor_sync(0xffffffffu, s_ok, o); s_q += __shfl_xor_sync(0xffffffffu, s_q, o);
+        s_q2 += __shfl_xor_sync(0xffffffffu, s_q2, o); s_out += __shfl_xor_sync(0xffffffffu, s_out, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&stats[0], s_ok); atomicAdd(&stats[1], s_q); atomicAdd(&stats[2], s_q2); atomicAdd(&stats[3], s_out);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x)
+        if (sh_hist[b]) atomicAdd(&hist[b], (unsigned long long)sh_hist[b]);
+}
+
 }  // namespace
 
 extern "C" {
@@ -364,9 +445,12 @@ int rapt_b200_init(int device)
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (g_device != device) {
+        // (re)bind the library to this device: the work counters and the sort scratch live in its memory.  One process
+        // drives one GPU; a later call with another device moves the binding, it does not share it.
         g_queue = nullptr;
         CK(cudaMalloc(&g_queue, 64 * sizeof(int)));
         CK(cudaMemset(g_queue, 0, 64 * sizeof(int)));
+        g_sort = SortScratch();
     }
     g_device = device;
     g_sms = prop.multiProcessorCount;
@@ -524,6 +608,7 @@ int rapt_b200_particle_advance_dev(const rapt_field_t *f, const rapt_params_t *p
     if (!(p->rtol > 0) || !(p->atol > 0) || !(p->cyclotronresolution > 0))
         return fail(RAPT_E_ARG, "particle_advance: solvertolerances and cyclotronresolution must be positive");
     if (n == 0) return RAPT_OK;
+    if (int rc = check_on_bound_device(t, "particle_advance_dev")) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rapt::AdvArgs a;
     if (int rc = fill_common(a, f, p)) return rc;
@@ -599,6 +684,7 @@ int rapt_b200_gc_advance_dev(const rapt_field_t *f, const rapt_params_t *p, int 
     if (eom < 0 || eom > 2) return fail(RAPT_E_ARG, "unknown eom %d", eom);
     if (!(p->rtol > 0) || !(p->atol > 0)) return fail(RAPT_E_ARG, "gc_advance: solvertolerances must be positive");
     if (n == 0) return RAPT_OK;
+    if (int rc = check_on_bound_device(t, "gc_advance_dev")) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rapt::AdvArgs a;
     if (int rc = fill_common(a, f, p)) return rc;
@@ -1079,7 +1165,13 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
     const double *h[9] = {x, y, z, vx, vy, vz, t0, mass, charge};
     for (int k = 0; k < 9; k++) CK(up(in[k], h[k], nb, s0));
     DevBuf ps[7], gs[7], dmode, dst, dnseg, dtag, dnst, dtvar, drem, dtcur, drows, dlp, dlg, dcounts, dcnt, ddtg, ddtp;
-    DevBuf dsts, dsx, dsdt, dsrow;
+    DevBuf dsts, dsx, dsdt, dsrow, dcntg;
+    CK(dcntg.alloc(4 * ni)); CK(cudaMemsetAsync(dcntg.p, 0, 4 * ni, s0));
+    AdaptiveStats stt;
+    cudaEvent_t ev[6];
+    for (auto &e : ev) CK(cudaEventCreate(&e));
+    struct EventGuard { cudaEvent_t *e; ~EventGuard() { for (int k = 0; k < 6; k++) cudaEventDestroy(e[k]); } } eguard{ev};
+    CK(cudaEventRecord(ev[4], s0));
     for (int k = 0; k < 7; k++) { CK(ps[k].alloc(nb)); CK(gs[k].alloc(nb)); CK(cudaMemsetAsync(gs[k].p, 0, nb, s0)); CK(cudaMemsetAsync(ps[k].p, 0, nb, s0)); }
     CK(dmode.alloc(ni)); CK(dst.alloc(ni)); CK(dnseg.alloc(ni)); CK(dtag.alloc(ni)); CK(dnst.alloc(ni));
     CK(dtvar.alloc(nb)); CK(drem.alloc(nb)); CK(dtcur.alloc(nb));
@@ -1151,8 +1243,10 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
             a.nstored = sw.nstored; a.nrows = nullptr; a.counters = dcnt.as<int>(); a.status = sw.status;
             a.tcur = sw.tcur; a.dt_out = ddtp.as<double>(); a.segtag = sw.segtag; a.append = 1;
             a.seg_tstop = sw.seg_tstop; a.seg_x = sw.seg_x; a.seg_dt = sw.seg_dt; a.seg_row = sw.seg_row; a.slice_end = slice_end;
+            CK(cudaEventRecord(ev[0], s1));
             if (int rc = launch_any(f, strict, UK_PARTICLE, &a, cnt[0], std::min(gp, (cnt[0] + 127) / 128), s1)) return rc;
-            g_launches++;
+            CK(cudaEventRecord(ev[1], s1));
+            g_launches++; stt.launches_p++; stt.tracer_launches_p += cnt[0];
         }
         if (cnt[1] > 0) {
             rapt::AdvArgs a;
@@ -1162,22 +1256,46 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
             a.mass = sw.mass; a.charge = sw.charge; a.mu = sw.mu; a.v = sw.v; a.dtin = ddtg.as<double>();
             a.delta = 0; a.delta_arr = sw.rem; a.eom = RAPT_EOM_TAOCHANBRIZARD;
             a.store_every = want_rows ? std::max<int64_t>(store_every, 1) : 0; a.max_rows = sw.max_rows; a.rows = sw.rows;
-            a.nstored = sw.nstored; a.nrows = nullptr; a.counters = dcnt.as<int>(); a.status = sw.status;
+            a.nstored = sw.nstored; a.nrows = nullptr; a.counters = dcntg.as<int>(); a.status = sw.status;
             a.tcur = sw.tcur; a.segtag = sw.segtag; a.append = 1;
             a.seg_tstop = sw.seg_tstop; a.seg_x = sw.seg_x; a.seg_dt = sw.seg_dt; a.seg_row = sw.seg_row; a.slice_end = slice_end;
+            CK(cudaEventRecord(ev[2], s2));
             if (int rc = launch_any(f, strict, UK_GC, &a, cnt[1], std::min(gg, (cnt[1] + 127) / 128), s2)) return rc;
-            g_launches++;
+            CK(cudaEventRecord(ev[3], s2));
+            g_launches++; stt.launches_g++; stt.tracer_launches_g += cnt[1];
         }
         CK(cudaStreamSynchronize(s1)); CK(cudaStreamSynchronize(s2));
+        float ms = 0;
+        if (cnt[0] > 0 && cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) stt.ms_particle += ms;
+        if (cnt[1] > 0 && cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) stt.ms_gc += ms;
+        CK(cudaEventRecord(ev[0], s0));
         if (int rc = launch_any(f, strict, UK_ADAPT, &sw, n, 0, s0)) return rc;
+        CK(cudaEventRecord(ev[1], s0));
+        CK(cudaEventSynchronize(ev[1]));
+        if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) stt.ms_switch += ms;
         g_launches++;
     }
+    CK(cudaEventRecord(ev[5], s0));
     if (epochs_out) *epochs_out = epochs;
     // results
-    std::vector<int> hmode((size_t)n);
+    std::vector<int> hmode((size_t)n), hcg(4 * (size_t)n), hcp(4 * (size_t)n);
     CK(cudaMemcpyAsync(hmode.data(), dmode.p, ni, cudaMemcpyDeviceToHost, s0));
     CK(down(nstored, dnst, ni, s0)); CK(down(nseg, dnseg, ni, s0)); CK(down(status, dst, ni, s0));
-    CK(down(counters, dcnt, 4 * ni, s0));
+    CK(cudaMemcpyAsync(hcp.data(), dcnt.p, 4 * ni, cudaMemcpyDeviceToHost, s0));
+    CK(cudaMemcpyAsync(hcg.data(), dcntg.p, 4 * ni, cudaMemcpyDeviceToHost, s0));
+    CK(cudaStreamSynchronize(s0));
+    {   // per-mode totals for the roofline of the executed mix; the ABI's counters are the sum, as the reference counts
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ev[4], ev[5]) == cudaSuccess) stt.ms_epochs = ms;
+        for (int64_t i = 0; i < n; i++) {
+            const int *cp = &hcp[4 * i], *cg = &hcg[4 * i];
+            stt.steps_p += cp[1]; stt.accepted_p += cp[2]; stt.calls_p += (cp[0] - 11LL * cp[1] - cp[2]) / 2;
+            stt.steps_g += cg[1]; stt.calls_g += (cg[0] - 6LL * cg[1]) / 2;
+            if (counters) for (int k = 0; k < 4; k++) counters[4 * i + k] = cp[k] + cg[k];
+        }
+        stt.epochs = epochs;
+        g_adaptive_stats = stt;
+    }
     if (want_rows) CK(down(rows, drows, (size_t)n * max_rows * 8 * sizeof(double), s0));
     std::vector<double> hp[7], hg[7];
     if (fin) {
@@ -1196,6 +1314,40 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
             else { for (int k = 0; k < 5; k++) o[k] = hg[k][i]; o[5] = hg[5][i]; o[6] = hg[6][i]; o[7] = 1; }
         }
     }
+    return RAPT_OK;
+}
+
+int rapt_b200_adaptive_last_stats(double *out, int n)
+{
+    if (!out || n < 15) return fail(RAPT_E_ARG, "adaptive_last_stats: need room for 15 doubles");
+    const AdaptiveStats &a = g_adaptive_stats;
+    const double v[15] = {(double)a.epochs, (double)a.launches_p, (double)a.launches_g, (double)a.tracer_launches_p,
+                          (double)a.tracer_launches_g, (double)a.steps_p, (double)a.accepted_p, (double)a.calls_p,
+                          (double)a.steps_g, (double)a.calls_g, a.ms_particle, a.ms_gc, a.ms_switch, a.ms_epochs, 0.0};
+    for (int k = 0; k < 15; k++) out[k] = v[k];
+    return RAPT_OK;
+}
+
+int rapt_b200_final_diagnostics_dev(int kind, int64_t n, int ncol, const double *const *cols, const double *mass,
+                                    const int32_t *status, double *packed, int nbins, double lo, double hi,
+                                    int64_t *hist, double *stats, void *stream)
+{
+    if (int rc = ensure_init()) return rc;
+    if (n < 0 || ncol < 4 || ncol > 8 || !cols || nbins < 1 || nbins > 8192 || !(hi > lo) || !hist || !stats)
+        return fail(RAPT_E_ARG, "final_diagnostics: need 4 <= ncol <= 8 state columns, 1 <= nbins <= 8192, hi > lo, hist and stats");
+    if (kind != 0 && kind != 1) return fail(RAPT_E_ARG, "final_diagnostics: kind %d (0 = log10 KE[eV], 1 = r / Re)", kind);
+    if (kind == 0 && (ncol < 7 || !mass)) return fail(RAPT_E_ARG, "final_diagnostics: the kinetic-energy histogram needs 7 columns and mass");
+    if (n == 0) return RAPT_OK;
+    rapt::DiagCols c;
+    for (int k = 0; k < 8; k++) c.col[k] = k < ncol ? cols[k] : nullptr;
+    for (int k = 0; k < ncol; k++) if (!c.col[k]) return fail(RAPT_E_ARG, "final_diagnostics: null column %d", k);
+    if (int rc = check_on_bound_device(c.col[0], "final_diagnostics_dev")) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = (int)std::min<long long>((long long)g_sms * 8, (n + 255) / 256);
+    k_final_diagnostics<<<grid, 256, nbins * sizeof(unsigned int), s>>>(kind, n, ncol, c, mass, status, packed, nbins, lo, hi,
+                                                                       reinterpret_cast<unsigned long long *>(hist), stats);
+    CK(cudaGetLastError());
+    g_launches++;
     return RAPT_OK;
 }
 

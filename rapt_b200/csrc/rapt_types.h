@@ -59,6 +59,9 @@ struct AdvArgs {
     double slice_end;
 };
 
+// state columns handed to the final-diagnostics kernel (capi.cu:k_final_diagnostics)
+struct DiagCols { const double *col[8]; };
+
 // batched _Field operators
 struct OpsArgs {
     FieldP f;

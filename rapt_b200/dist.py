@@ -7,7 +7,66 @@ shard with NO data-path collective, and at the end the final states are all-gath
 diagnostics (histograms, invariant statistics) all-reduced -- NCCL over NVLink on GPUs, gloo in the CPU
 tests.  Nothing here launches kernels; it only moves results.
 """
+import os
+
 import numpy as np
+
+
+def world_rank(group=None):
+    """(world size, rank) of the torch.distributed job this process belongs to; (1, 0) outside one."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(group), dist.get_rank(group)
+    except ImportError:
+        pass
+    return 1, 0
+
+
+def local_device():
+    """The GPU of this rank: cuda:LOCAL_RANK under torchrun, cuda:0 otherwise."""
+    return f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}"
+
+
+def _on_device_backend(group=None):
+    import torch.distributed as dist
+    return "nccl" in str(dist.get_backend(group))
+
+
+def gather_rows(buf, rank, n_total, group=None):
+    """All-gather of per-rank final-state rows.  buf: (world, n_max, k) tensor whose slot [rank] already holds this
+    rank's rows (rapt_b200_final_diagnostics_dev packs them there, so the send buffer IS the receive slot: NCCL's
+    in-place all-gather, no staging copy).  Returns the (n_total, k) tensor in global member order on every rank.
+    With a host backend (gloo, the CPU tests and single-GPU boxes) the slot is staged through host memory."""
+    import torch
+    import torch.distributed as dist
+    world = buf.shape[0]
+    if world > 1:
+        if _on_device_backend(group) or not buf.is_cuda:
+            dist.all_gather_into_tensor(buf.view(-1), buf[rank].reshape(-1), group=group)
+        else:
+            h = torch.empty(buf.shape, dtype=buf.dtype)
+            dist.all_gather_into_tensor(h.view(-1), buf[rank].reshape(-1).cpu(), group=group)
+            buf.copy_(h)
+    sizes = shard_sizes(n_total, world)
+    out = torch.empty((n_total, buf.shape[2]), dtype=buf.dtype, device=buf.device)
+    for r in range(world):
+        out[r::world] = buf[r, :sizes[r]]
+    return out
+
+
+def reduce_diagnostics(hist, stats, group=None):
+    """Sum-all-reduce of the fixed-size diagnostics (histogram counts int64, invariant sums float64), in place."""
+    import torch.distributed as dist
+    world, _ = world_rank(group)
+    if world == 1:
+        return hist, stats
+    for t in (hist, stats):
+        if _on_device_backend(group) or not t.is_cuda:
+            dist.all_reduce(t, group=group)
+        else:
+            h = t.cpu(); dist.all_reduce(h, group=group); t.copy_(h)
+    return hist, stats
 
 
 def shard_slice(n_total, world, rank):

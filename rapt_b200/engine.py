@@ -457,8 +457,12 @@ def adaptive_advance(field, pos, vel, t0, mass, charge, delta, gc_dt, store_ever
         C.byref(f), C.byref(p), C.c_int64(n), *[ptr(c_) for c_ in cols], ptr(t0), ptr(mass), ptr(charge),
         C.c_double(gc_dt), C.c_double(delta), C.c_int64(store_every), C.c_int64(max_rows), ptr(rows),
         ptr(nstored), ptr(nseg), ptr(mode), ptr(fin), ptr(counters), ptr(status), C.byref(epochs)))
+    st = np.zeros(15)
+    check(_lib.load().rapt_b200_adaptive_last_stats(ptr(st), C.c_int(15)))
+    keys = ("epochs", "launches_particle", "launches_gc", "tracer_launches_particle", "tracer_launches_gc", "steps_particle",
+            "accepted_particle", "calls_particle", "steps_gc", "calls_gc", "ms_particle", "ms_gc", "ms_switch", "ms_epochs")
     return dict(rows=rows, nstored=nstored, nseg=nseg, mode=mode, final=fin, counters=counters, status=status,
-                epochs=epochs.value)
+                epochs=epochs.value, stats={k: float(v) for k, v in zip(keys, st)})
 
 
 # ------------------------------------------------------------------------------------------------
@@ -494,6 +498,18 @@ def gc_advance_dev(field, cols, mu, v, mass, charge, dt, delta, out, eom="TaoCha
         ptr(mu), ptr(v), ptr(mass), ptr(charge), ptr(dt), C.c_double(delta),
         C.c_int64(store_every), C.c_int64(max_rows), ptr(rows), ptr(out["nrows"]), ptr(out["nstored"]),
         ptr(out["counters"]), ptr(out["status"]), ptr(out["tcur"]), _stream_ptr()))
+
+
+def final_diagnostics_dev(kind, cols, mass, status, packed, nbins, lo, hi, hist, stats):
+    """One kernel pass over device-resident final-state columns (rapt_b200_final_diagnostics_dev): packs them into
+    `packed` ([n][ncol], may be this rank's slot of the all-gather buffer), accumulates the histogram of
+    kind 0: log10 kinetic energy [eV] / kind 1: r / Re into `hist` (int64 [nbins]) and (ok count, sum q, sum q^2,
+    out of range) into `stats` (float64 [4]).  All CUDA tensors; launched on torch's current stream."""
+    n = cols[0].numel()
+    arr = (C.c_void_p * len(cols))(*[c_.data_ptr() for c_ in cols])
+    check(_lib.load().rapt_b200_final_diagnostics_dev(
+        C.c_int({"ke": 0, "r": 1}.get(kind, kind)), C.c_int64(n), C.c_int(len(cols)), arr, ptr(mass), ptr(status), ptr(packed),
+        C.c_int(nbins), C.c_double(lo), C.c_double(hi), ptr(hist), ptr(stats), _stream_ptr()))
 
 
 def alloc_outputs(n, device):

@@ -19,6 +19,119 @@ def _arr(a, n=None):
     return np.ascontiguousarray(a).copy()
 
 
+class _Resident:
+    """Residency, sharding and result collection shared by ParticleEnsemble and GuidingCenterEnsemble.
+
+    Multi-GPU: one process per GPU under torchrun.  Every rank builds the SAME ensemble and
+    calls `.shard()`: rank r keeps members r, r+W, r+2W, ... (round-robin, so every GPU sees the same mix of orbit
+    lengths) on cuda:LOCAL_RANK.  `advance()` then runs the same kernels on the shard with no data-path collective.
+    `.gather()` packs the final states and bins the diagnostics in one kernel pass, all-gathers the rows (NCCL over
+    NVLink, in place into this rank's slot) and sum-all-reduces the fixed-size histogram / invariant sums."""
+
+    _MEMBER_ARRAYS = ()          # per-member host arrays a shard slices
+    _DIAG = "ke"
+
+    def shard(self, group=None, device=None):
+        from . import dist as rd
+        world, rank = rd.world_rank(group)
+        self._group, self.world, self.rank, self.n_total = group, world, rank, self.n
+        if world > 1:
+            sl = rd.shard_slice(self.n, world, rank)
+            for name in self._MEMBER_ARRAYS:
+                a = getattr(self, name, None)
+                if a is not None:
+                    setattr(self, name, np.ascontiguousarray(a[sl]))
+            self.n = len(self.state)
+        return self.cuda(device or rd.local_device())
+
+    def load_state(self, cols):
+        """Overwrite the device-resident state columns with the given CUDA tensors (e.g. to restart from the same
+        initial conditions); stream-ordered copies, no host traffic."""
+        for dst, src in zip(self._dev.cols, cols):
+            dst.copy_(src)
+        return self
+
+    def _bind(self, device):
+        """One process drives one GPU: bind the library and torch to the device the state goes to."""
+        import torch
+        self._host_counters = np.array(self.counters, dtype=np.int64)
+        from . import _lib
+        dev = torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        _lib.init(idx)
+        torch.cuda.set_device(idx)
+        return torch.device("cuda", idx)
+
+    def _rows_buffer(self, store_every, max_rows):
+        import torch
+        d = self._dev
+        if store_every > 0 and max_rows > 0:
+            if d.rows is None or tuple(d.rows.shape) != (self.n, max_rows, 8):
+                d.rows = torch.empty((self.n, max_rows, 8), dtype=torch.float64, device=d.device)
+            d.rows_valid = True
+            return d.rows
+        d.rows_valid = False
+        return None
+
+    def pull(self):
+        """Copy the device-resident results to the host attributes (state, status, tcur, counters, nrows and, when
+        the last advance() stored rows, trajectory / nstored); the ensemble stays on the device."""
+        import torch
+        d = self._dev
+        if d is None:
+            return self
+        torch.cuda.synchronize(d.device)
+        self.state = np.column_stack([cc.cpu().numpy() for cc in d.cols])
+        o = d.out
+        self.status = o["status"].cpu().numpy(); self.tcur = o["tcur"].cpu().numpy()
+        if "dt" in o and hasattr(self, "dt"):
+            self.dt = o["dt"].cpu().numpy()
+        self.last_counters = o["counters"].cpu().numpy().astype(np.int64)
+        self.counters = self._host_counters + d.cum_counters.cpu().numpy()
+        self.nrows = o["nrows"].cpu().numpy().astype(np.int64)
+        if d.rows is not None and d.rows_valid:
+            self.trajectory = d.rows.cpu().numpy(); self.nstored = o["nstored"].cpu().numpy()
+        return self
+
+    def cpu(self):
+        if self._dev is not None:
+            self.pull()
+            self._dev = None
+        return self
+
+    def gather(self, nbins=64, lo=None, hi=None, kind=None):
+        """Final states of the WHOLE ensemble in member order on every rank + all-reduced diagnostics.
+        Returns dict(final=(n_total, ncol) CUDA tensor, hist=int64 [nbins], edges, stats=dict(ok, mean, var, outside)).
+        kind 'ke': log10 kinetic energy [eV] (Particle.getke); 'r': radial distance [Re]."""
+        import torch
+        from . import dist as rd
+        d = self._dev
+        if d is None:
+            raise RuntimeError("gather() works on device-resident ensembles: call .shard() or .cuda() first")
+        kind = kind or self._DIAG
+        lo = (4.0 if kind == "ke" else 0.0) if lo is None else lo
+        hi = (8.0 if kind == "ke" else 16.0) if hi is None else hi
+        world, rank = getattr(self, "world", 1), getattr(self, "rank", 0)
+        n_total = getattr(self, "n_total", self.n)
+        n_max = max(rd.shard_sizes(n_total, world))
+        ncol = len(d.cols)
+        if d.gather_buf is None or tuple(d.gather_buf.shape) != (world, n_max, ncol):
+            d.gather_buf = torch.zeros((world, n_max, ncol), dtype=torch.float64, device=d.device)
+            d.hist = torch.zeros(nbins, dtype=torch.int64, device=d.device)
+            d.stats = torch.zeros(4, dtype=torch.float64, device=d.device)
+        if d.hist.numel() != nbins:
+            d.hist = torch.zeros(nbins, dtype=torch.int64, device=d.device)
+        d.hist.zero_(); d.stats.zero_()
+        engine.final_diagnostics_dev(kind, d.cols, d.extras["mass"], d.out["status"], d.gather_buf[rank], nbins, lo, hi,
+                                     d.hist, d.stats)
+        final = rd.gather_rows(d.gather_buf, rank, n_total, getattr(self, "_group", None))
+        rd.reduce_diagnostics(d.hist, d.stats, getattr(self, "_group", None))
+        st = d.stats.cpu().numpy()
+        ok = max(st[0], 1.0)
+        return dict(final=final, hist=d.hist, edges=np.linspace(lo, hi, nbins + 1), kind=kind,
+                    stats=dict(ok=int(st[0]), mean=st[1] / ok, var=st[2] / ok - (st[1] / ok) ** 2, outside=int(st[3])))
+
+
 class _DeviceState:
     """Device-resident columns (torch CUDA float64 tensors) + output scratch."""
 
@@ -28,10 +141,14 @@ class _DeviceState:
         self.cols = [torch.as_tensor(np.ascontiguousarray(cc), device=self.device) for cc in cols]
         self.extras = {k: torch.as_tensor(np.ascontiguousarray(v), device=self.device) for k, v in extras.items()}
         self.out = engine.alloc_outputs(self.cols[0].numel(), self.device)
-        self.rows = None
+        self.rows = None; self.rows_valid = False
+        self.pending_advances = 0
+        # cumulative (nfcn, nstep, naccpt, nrejct) over the device-resident advance() calls, accumulated on the stream
+        self.cum_counters = torch.zeros((self.cols[0].numel(), 4), dtype=torch.int64, device=self.device)
+        self.gather_buf = None; self.hist = None; self.stats = None
 
 
-class ParticleEnsemble:
+class ParticleEnsemble(_Resident):
     """n full-orbit tracers: Particle(pos, vel, t0, mass, charge, field) with array arguments
     (reference constructor: rapt/Particle.py:59-109).
 
@@ -57,42 +174,27 @@ class ParticleEnsemble:
         self.check_adiabaticity = False
         self._dev = None
 
+    _MEMBER_ARRAYS = ("state", "mass", "charge", "tcur", "dt", "counters", "status", "nrows")
+    _DIAG = "ke"
+
     # ---- residency
     def cuda(self, device="cuda:0"):
-        self._dev = _DeviceState([self.state[:, i] for i in range(7)], dict(mass=self.mass, charge=self.charge), device)
+        self._dev = _DeviceState([self.state[:, i] for i in range(7)], dict(mass=self.mass, charge=self.charge),
+                                 self._bind(device))
         return self
-
-    def cpu(self):
-        if self._dev is not None:
-            import torch
-            torch.cuda.synchronize(self._dev.device)
-            self.state = np.column_stack([cc.cpu().numpy() for cc in self._dev.cols])
-            self._pull_outputs()
-            self._dev = None
-        return self
-
-    def _pull_outputs(self):
-        o = self._dev.out
-        self.status = o["status"].cpu().numpy()
-        self.tcur = o["tcur"].cpu().numpy()
-        self.dt = o["dt"].cpu().numpy()
-        self.last_counters = o["counters"].cpu().numpy().astype(np.int64)
-        self.nrows = o["nrows"].cpu().numpy().astype(np.int64)
 
     # ---- the hot path
     def advance(self, delta, store_every=0, max_rows=0, **over):
         """Particle.advance(delta) for every member (rapt/Particle.py:230-309).
         store_every = k keeps every k-th output row (0: final state only) in `trajectory`."""
         if self._dev is not None:
-            import torch
             d = self._dev
-            if store_every > 0 and max_rows > 0:
-                if d.rows is None or tuple(d.rows.shape) != (self.n, max_rows, 8):
-                    d.rows = torch.empty((self.n, max_rows, 8), dtype=torch.float64, device=d.device)
+            rows = self._rows_buffer(store_every, max_rows)
             engine.particle_advance_dev(self.field, d.cols, d.extras["mass"], d.extras["charge"], float(delta), d.out,
-                                        store_every=store_every, max_rows=max_rows,
-                                        rows=d.rows if store_every > 0 and max_rows > 0 else None,
+                                        store_every=store_every, max_rows=max_rows, rows=rows,
                                         check_adiabaticity=self.check_adiabaticity, **over)
+            d.cum_counters += d.out["counters"]    # stream-ordered, no synchronisation
+            d.pending_advances += 1
             return self
         o = engine.particle_advance(self.field, self.state, self.mass, self.charge, float(delta), store_every=store_every,
                                     max_rows=max_rows, check_adiabaticity=self.check_adiabaticity, **over)
@@ -115,7 +217,7 @@ class ParticleEnsemble:
         return np.where(g - 1 < 1e-6, 0.5 * p2 / self.mass, (g - 1) * self.mass * c * c)
 
 
-class GuidingCenterEnsemble:
+class GuidingCenterEnsemble(_Resident):
     """n guiding centres: GuidingCenter(pos, v, pa, ppar, t0, mass, charge, field) with array arguments
     (reference constructor: rapt/GuidingCenter.py:63-133).  `state` is (n,5): t,X,Y,Z,p_parallel."""
 
@@ -145,7 +247,8 @@ class GuidingCenterEnsemble:
         self.check_adiabaticity = False
         self._dev = None
 
-    HOST_QUADRATURE_MAX = 4096
+    _MEMBER_ARRAYS = ("state", "v", "mass", "charge", "mu", "tcur", "counters", "status", "nrows")
+    _DIAG = "r"
 
     def bounceperiod(self, method="quadpack"):
         """GuidingCenter.bounceperiod of every member (rapt/GuidingCenter.py:593-606).
@@ -162,40 +265,39 @@ class GuidingCenterEnsemble:
     def _dt(self):
         if params["GCtimestep"] != 0:                                # GuidingCenter.py:443-446
             return np.full(self.n, float(params["GCtimestep"]))
+        if self._dev is not None and self._dev.pending_advances:
+            self.pull()     # the reference recomputes the bounce period from trajectory[-1] at every advance (:446)
+            self._dev.pending_advances = 0
         return self.bounceperiod() / params["bounceresolution"]
 
     def cuda(self, device="cuda:0"):
         self._dev = _DeviceState([self.state[:, i] for i in range(5)],
-                                 dict(mass=self.mass, charge=self.charge, mu=self.mu, v=self.v), device)
-        return self
-
-    def cpu(self):
-        if self._dev is not None:
-            import torch
-            torch.cuda.synchronize(self._dev.device)
-            self.state = np.column_stack([cc.cpu().numpy() for cc in self._dev.cols])
-            o = self._dev.out
-            self.status = o["status"].cpu().numpy(); self.tcur = o["tcur"].cpu().numpy()
-            self.last_counters = o["counters"].cpu().numpy().astype(np.int64)
-            self.nrows = o["nrows"].cpu().numpy().astype(np.int64)
-            self._dev = None
+                                 dict(mass=self.mass, charge=self.charge, mu=self.mu, v=self.v), self._bind(device))
         return self
 
     def advance(self, delta, eom="TaoChanBrizardEOM", store_every=0, max_rows=0, dt=None, **over):
         """GuidingCenter.advance(delta, eom) for every member (rapt/GuidingCenter.py:397-458)."""
-        dt = self._dt() if dt is None else _arr(dt, self.n)
+        if dt is None and params["GCtimestep"] != 0:                 # GuidingCenter.py:443-444
+            dt = float(params["GCtimestep"])
+        uniform = float(dt) if np.isscalar(dt) else None
         if self._dev is not None:
             import torch
             d = self._dev
-            d.extras["dt"] = torch.as_tensor(dt, device=d.device)
-            if store_every > 0 and max_rows > 0:
-                if d.rows is None or tuple(d.rows.shape) != (self.n, max_rows, 8):
-                    d.rows = torch.empty((self.n, max_rows, 8), dtype=torch.float64, device=d.device)
+            if "dt" not in d.extras or d.extras["dt"].numel() != self.n:
+                d.extras["dt"] = torch.empty(self.n, dtype=torch.float64, device=d.device)
+                d.dt_uniform = None
+            if uniform is None or getattr(d, "dt_uniform", None) != uniform:     # a repeated uniform step stays resident
+                dt = self._dt() if dt is None else _arr(dt, self.n)
+                d.extras["dt"].copy_(torch.as_tensor(dt), non_blocking=False)
+                d.dt_uniform = uniform
+            rows = self._rows_buffer(store_every, max_rows)
             engine.gc_advance_dev(self.field, d.cols, d.extras["mu"], d.extras["v"], d.extras["mass"], d.extras["charge"],
                                   d.extras["dt"], float(delta), d.out, eom=eom, store_every=store_every, max_rows=max_rows,
-                                  rows=d.rows if store_every > 0 and max_rows > 0 else None,
-                                  check_adiabaticity=self.check_adiabaticity, **over)
+                                  rows=rows, check_adiabaticity=self.check_adiabaticity, **over)
+            d.cum_counters += d.out["counters"]
+            d.pending_advances += 1
             return self
+        dt = self._dt() if dt is None else _arr(dt, self.n)
         o = engine.gc_advance(self.field, self.state, self.mu, self.v, self.mass, self.charge, dt, float(delta), eom=eom,
                               store_every=store_every, max_rows=max_rows, check_adiabaticity=self.check_adiabaticity, **over)
         self.state = o["state"]; self.tcur = o["tcur"]; self.status = o["status"]

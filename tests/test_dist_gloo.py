@@ -29,6 +29,17 @@ def _worker(rank, world, port, n, out_dir):
     p = torch.tensor(np.linalg.norm(o["state"][:, 4:7], axis=1))
     h = rd.all_reduce_histogram(torch.log10(p), 16, -21.0, -19.0)
     stats = rd.all_reduce_stats(p)
+    # the product's collection path (rapt_b200/ensemble.py:gather): this rank's rows already sit in its slot of the
+    # gather buffer (on the GPU the packing kernel writes them there), in-place all-gather, reduce of hist + sums
+    n_max = max(rd.shard_sizes(n, world))
+    buf = torch.zeros((world, n_max, 8), dtype=torch.float64)
+    buf[rank, :local.shape[0]] = local
+    full2 = rd.gather_rows(buf, rank, n)
+    hist = torch.histc(torch.log10(p), bins=16, min=-21.0, max=-19.0).to(torch.int64)
+    sums = torch.tensor([float(len(p)), float(p.sum()), float((p * p).sum()), 0.0], dtype=torch.float64)
+    rd.reduce_diagnostics(hist, sums)
+    assert torch.equal(full2, full) and torch.equal(hist.to(torch.float64), h) and int(sums[0]) == n
+    assert rd.world_rank() == (world, rank)
     if rank == 0:
         np.savez(os.path.join(out_dir, "gathered.npz"), full=full.numpy(), hist=h.numpy(),
                  stats=np.array([stats["count"], stats["mean"], stats["min"], stats["max"]]))

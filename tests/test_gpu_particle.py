@@ -90,6 +90,64 @@ def test_config2_first32_vs_reference(eng, arith):
 
 
 @pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_config2_first32_bench_horizon_vs_reference(eng, arith):
+    """First 32 protons of config 2 at the BENCH horizon, advance(10 s): the headline workload itself against the
+    reference (fixture e2_config2_first32_10s; 98 k attempted steps).  Bars: final state 1e-8, row counts equal,
+    (nfcn, nstep, naccpt, nrejct) equal for every proton in the strict flavour; the fast flavour reports how many
+    protons differ (an accept/reject decision whose err is within the flavour's round-off of 1.0)."""
+    from rapt_b200 import synth
+    d, par = H.load("e2_config2_first32_10s")
+    n = int(d["n"])
+    ic = synth.config2_protons(n)
+    vel = np.column_stack([ic["vx"], ic["vy"], ic["vz"]])
+    st = np.column_stack([ic["t0"], ic["x"], ic["y"], ic["z"], eng.particle_momentum(vel, ic["mass"])])
+    o = eng.particle_advance(H.gpu_field("EarthDipole", ()), st, ic["mass"], ic["charge"], float(d["delta"]),
+                             store_every=0, arith=arith, **par)
+    fin = d["final"]
+    assert np.all(o["status"] == 1)
+    assert np.array_equal(o["nrows"], d["nrows"])
+    assert H.relerr(o["state"][:, 0], fin[:, 0]) < 1e-12
+    assert H.vec_relerr(o["state"][:, 1:4], fin[:, 1:4]) < 1e-8
+    assert H.vec_relerr(o["state"][:, 4:7], fin[:, 4:7]) < 1e-8
+    same = np.all(o["counters"] == d["totals"], axis=1)
+    print(f"[{arith}] config 2 x 10 s: {int(same.sum())}/{n} protons with scipy's exact counters; "
+          f"nstep sum {int(o['counters'][:, 1].sum())} vs {int(d['totals'][:, 1].sum())}")
+    if arith == "strict":
+        assert same.all(), "per-proton (nfcn,nstep,naccpt,nrejct) equal scipy's over the whole 10 s"
+    else:
+        assert same.sum() >= n - 2
+        assert abs(int(o["counters"][:, 1].sum()) - int(d["totals"][:, 1].sum())) <= 4
+    assert np.allclose(o["tcur"], d["tcur"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_particle_325_gyroperiods_vs_reference(eng, arith):
+    """north_star's short horizon, 'a few hundred gyroperiods': the g1b proton for 40 s = 324 gyroperiods, 6486 rows
+    (fixture g1c_325_gyroperiods holds every 16th row, the last row and all per-call counters)."""
+    d, par = H.load("g1c_325_gyroperiods")
+    assert 300 < float(d["gyroperiods"]) < 350
+    every = int(d["every"]); nrows = int(d["nrows"])
+    st0 = d["traj_dec"][0]
+    o = eng.particle_advance(H.gpu_field("EarthDipole", ()), st0, float(d["mass"]), float(d["charge"]), float(d["delta"]),
+                             store_every=every, max_rows=len(d["traj_dec"]) + 8, arith=arith, **par)
+    assert o["status"][0] == 1 and o["nrows"][0] == nrows
+    k = int(o["nstored"][0])
+    assert k == len(d["traj_dec"])
+    rows = o["rows"][0, :k]
+    assert H.relerr(rows[:, 0], d["traj_dec"][:, 0], floor=1e-3) < 1e-12
+    assert H.vec_relerr(rows[:, 1:4], d["traj_dec"][:, 1:4]) < 1e-8
+    assert H.vec_relerr(rows[:, 4:7], d["traj_dec"][:, 4:7]) < 1e-8
+    assert H.vec_relerr(o["state"][0, 1:4], d["last"][1:4]) < 1e-8 and H.vec_relerr(o["state"][0, 4:7], d["last"][4:7]) < 1e-8
+    ref = d["counters"].astype(np.int64)
+    assert tuple(o["counters"][0]) == tuple(ref.sum(0)), "6499 attempted steps, all accepted, as scipy counts them"
+    # cumulative attempted steps stored with each decimated row == scipy's running total at that row
+    assert np.array_equal(rows[1:, 7].astype(np.int64), np.cumsum(ref[:, 1])[every - 1::every][:k - 1])
+    # |p| (energy in a static B) drifts exactly as much as the reference's own integration lets it
+    p0 = np.linalg.norm(st0[4:7]); dr = np.linalg.norm(d["last"][4:7]) / p0 - 1; dg = np.linalg.norm(o["state"][0, 4:7]) / p0 - 1
+    assert abs(dg - dr) < 1e-10 and abs(dg) < 1e-5
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
 def test_config2_ensemble_vs_oracle(eng, arith):
     """4096 protons of config 2, advance(0.25 s): CUDA vs the CPU oracle on identical inputs, with
     decimated trajectory storage (store_every = 7)."""

@@ -509,3 +509,35 @@ def test_kernel_source_solver_failure_row(arith, rkn):
         assert o["tcur"][0] == float(d["tcur"])
     else:   # 501 attempts of a stiff bounce motion at GCtimestep = 50 s: the time reached depends on every accept/reject
         assert abs(o["rows"][0, 1, 0] / traj[1, 0] - 1) < 0.05
+
+
+@pytest.mark.parametrize("arith,rkn", [("strict", False), ("fast", False), ("fast", True)])
+def test_kernel_source_config2_bench_horizon_and_325_gyroperiods(arith, rkn):
+    """The two long fixtures of the headline path on the kernel source: the first 32 protons of config 2 for the bench
+    horizon (10 s) and one proton for 324 gyroperiods.  Strict: bit for bit / exact counters; fast: the GPU bars."""
+    from rapt_b200 import engine, synth
+    d, par = H.load("e2_config2_first32_10s")
+    n = int(d["n"]); ic = synth.config2_protons(n)
+    vel = np.column_stack([ic["vx"], ic["vy"], ic["vz"]])
+    st = np.column_stack([ic["t0"], ic["x"], ic["y"], ic["z"], engine.particle_momentum(vel, ic["mass"])])
+    o = K.particle_advance(H.gpu_field("EarthDipole", ()), st, ic["mass"], ic["charge"], float(d["delta"]), store_every=0,
+                           rkn=rkn, nthreads=8, arith=arith, **par)
+    assert np.array_equal(o["nrows"], d["nrows"]) and np.all(o["status"] == 1)
+    same = np.all(o["counters"] == d["totals"], axis=1)
+    if arith == "strict":
+        assert np.array_equal(o["state"], d["final"]) and same.all() and np.array_equal(o["tcur"], d["tcur"])
+    else:
+        assert H.vec_relerr(o["state"][:, 1:4], d["final"][:, 1:4]) < 1e-8 and H.vec_relerr(o["state"][:, 4:7], d["final"][:, 4:7]) < 1e-8
+        assert same.sum() >= n - 2
+    d, par = H.load("g1c_325_gyroperiods")
+    every = int(d["every"])
+    o = K.particle_advance(H.gpu_field("EarthDipole", ()), d["traj_dec"][0], float(d["mass"]), float(d["charge"]), float(d["delta"]),
+                           store_every=every, max_rows=len(d["traj_dec"]) + 8, rkn=rkn, nthreads=1, arith=arith, **par)
+    k = int(o["nstored"][0])
+    assert o["nrows"][0] == int(d["nrows"]) and k == len(d["traj_dec"])
+    assert tuple(o["counters"][0]) == tuple(d["counters"].astype(np.int64).sum(0))
+    if arith == "strict":
+        assert np.array_equal(o["rows"][0, :k, :7], d["traj_dec"]) and np.array_equal(o["state"][0], d["last"])
+    else:
+        assert H.vec_relerr(o["rows"][0, :k, 1:4], d["traj_dec"][:, 1:4]) < 1e-8
+        assert H.vec_relerr(o["rows"][0, :k, 4:7], d["traj_dec"][:, 4:7]) < 1e-8
