@@ -338,13 +338,20 @@ def time_workload(args, workload, n_per_gpu, world, rank, dev, steps, warmup, wa
                          dtype=torch.float64, device=dev)
     per_rank = None
     if world > 1:
-        allt = torch.empty((world, 5), dtype=torch.float64, device=dev)
+        # one more collection outside the timed region, with events between its parts
+        dist.barrier()
+        tm = ens.gather(nbins=64, profile=True)["timing_ms"]
+        times = torch.cat([times, torch.tensor([tm["pack_hist"], tm["allgather_unshard"], tm["allreduce"]], dtype=torch.float64, device=dev)])
+        allt = torch.empty((world, 8), dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(allt.view(-1), times)
         dist.all_reduce(stats)
         ms = float(allt[:, 0].max())
         per_rank = {"kernel_ms_per_step": [round(float(v) / steps, 3) for v in allt[:, 1]],
                     "collect_ms_per_step": [round(float(v) / steps, 3) for v in allt[:, 2]],
                     "sm_mhz": [float(v) for v in allt[:, 3]], "power_w": [float(v) for v in allt[:, 4]],
+                    "collect_split_ms_after_barrier": {"pack_hist_kernel": [round(float(v), 3) for v in allt[:, 5]],
+                                                       "allgather_plus_unshard": [round(float(v), 3) for v in allt[:, 6]],
+                                                       "allreduce": [round(float(v), 3) for v in allt[:, 7]]},
                     "note": "collect = pack/histogram kernel + NCCL all-gather + all-reduce, including the wait for the slowest rank"}
     nstep, naccpt, ncalls, nok, nall = (float(stats[i]) for i in range(5))
     ms_per_step = ms / steps

@@ -269,7 +269,8 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
  * tracers handed to particle launches (sum over epochs), same for guiding-centre launches, particle-mode attempted
  * steps, accepted steps, solver calls (= rows), guiding-centre attempted steps, solver calls, and the device time in ms
  * of the particle kernels, the guiding-centre kernels (the two run concurrently on two streams), the switch/regroup
- * kernels, and of the whole epoch loop; out[14] reserved. */
+ * kernels, and of the whole epoch loop; out[14] reserved; then, while room (n > 15), four numbers per epoch: tracers in
+ * particle mode, tracers in guiding-centre mode, particle-kernel ms, guiding-centre-kernel ms. */
 int rapt_b200_adaptive_last_stats(double *out, int n);
 
 /* ---- mode-switch transforms, exposed for callers that drive segments themselves:
@@ -297,6 +298,10 @@ int rapt_b200_isadiabatic(const rapt_field_t *f, const rapt_params_t *p, int mod
 int rapt_b200_final_diagnostics_dev(int kind, int64_t n, int ncol, const double *const *cols, const double *mass,
                                     const int32_t *status, double *packed, int nbins, double lo, double hi,
                                     int64_t *hist, double *stats, void *stream);
+
+/* The all-gathered rows, gathered[world][n_max][ncol] with rank r holding members r, r + world, ... (round-robin shards,
+ * rapt_b200/dist.py), rearranged into global member order out[n_total][ncol].  DEVICE pointers. */
+int rapt_b200_unshard_dev(int world, int64_t n_max, int ncol, int64_t n_total, const double *gathered, double *out, void *stream);
 
 /* kernel launches performed by this library since load (for bench.py's gpu_launches) */
 int64_t rapt_b200_launch_count(void);

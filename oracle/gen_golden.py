@@ -603,6 +603,28 @@ def case_e2long():
          final=np.array(fin), nrows=np.array(nrows), totals=np.array(tot), tcur=np.array(tcur))
 
 
+def case_e2fail():
+    """The one member of the 1 M-proton headline ensemble (BASELINE.json configs[1]) whose row loop ends on scipy's
+    nsteps = 500 limit: member 408359 of synth.config2_protons(1 << 20) (bench.py reports it as solver_failures: 1,
+    failed_members_rank0: [408359]).  The reference on the same proton: rows until the failed call, its appended row,
+    the totals."""
+    i = 408359
+    ic = synth.config2_protons(1 << 20)
+    pos = (ic["x"][i], ic["y"][i], ic["z"][i]); vel = (ic["vx"][i], ic["vy"][i], ic["vz"][i])
+    refshim.reset_params(rapt, cyclotronresolution=20)
+    refshim.SOLVER_LOG.clear()
+    p = rapt.Particle(pos=pos, vel=vel, t0=0, mass=m_pr, charge=e, field=rf.EarthDipole())
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        p.advance(10.0)
+    L = take_log()
+    msgs = [str(x.message) for x in w]
+    print("  rows", p.trajectory.shape, "tcur", p.tcur, "last call", L[-1], "warnings", msgs[-1:] )
+    save("e2_config2_member408359", member=i, n_total=1 << 20, seed=20260201, delta=10.0, params=parjson(cyclotronresolution=20),
+         pos=np.array(pos), vel=np.array(vel), mass=m_pr, charge=e, nrows=p.trajectory.shape[0], last_rows=p.trajectory[-3:],
+         totals=L.sum(0), last_call=L[-1], tcur=p.tcur, warned=np.array(any("nsteps" in m for m in msgs)), ke_ev=ic["ke_ev"][i])
+
+
 def case_g1long():
     """A few hundred gyroperiods (north_star's short horizon): the g1b proton for 40 s = ~325 gyroperiods, 6.5e3 rows.
     Stored: every 16th row + the last, per-call counters, totals."""
@@ -642,7 +664,7 @@ def case_getters():
 
 
 CASES = {
-    "e2long": case_e2long, "g1long": case_g1long, "getters": case_getters,
+    "e2long": case_e2long, "e2fail": case_e2fail, "g1long": case_g1long, "getters": case_getters,
     "fail": case_fail,
     "g1": case_g1, "g1b": case_g1b, "pfields": case_pfields, "g2": case_g2, "gcfields": case_gcfields,
     "g3": case_g3, "e4": case_e4, "adip": case_adaptive_dipole, "e2": case_e2, "e3": case_e3,

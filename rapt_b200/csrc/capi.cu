@@ -33,6 +33,7 @@ struct AdaptiveStats {
     long long epochs = 0, launches_p = 0, launches_g = 0, tracer_launches_p = 0, tracer_launches_g = 0;
     long long steps_p = 0, accepted_p = 0, calls_p = 0, steps_g = 0, calls_g = 0;
     double ms_particle = 0, ms_gc = 0, ms_switch = 0, ms_epochs = 0, ms_total = 0;
+    std::vector<float> per_epoch;      // (tracers in particle mode, in guiding-centre mode, particle-kernel ms, gc-kernel ms) x epochs
 };
 thread_local AdaptiveStats g_adaptive_stats;
 
@@ -414,6 +415,19 @@ __global__ void __launch_bounds__(256) k_final_diagnostics(int kind, long long n
     __syncthreads();
     for (int b = threadIdx.x; b < nbins; b += blockDim.x)
         if (sh_hist[b]) atomicAdd(&hist[b], (unsigned long long)sh_hist[b]);
+}
+
+// all-gathered rows [world][n_max][ncol] (rank r holds members r, r + world, ...) -> member order [n_total][ncol]:
+// coalesced writes, reads from `world` streams that advance together
+__global__ void __launch_bounds__(256) k_unshard(int world, long long n_max, int ncol, long long n_total,
+                                                const double *__restrict__ buf, double *__restrict__ out)
+{
+    const long long total = n_total * ncol;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long m = e / ncol; const int c = (int)(e - m * ncol);
+        const long long i = m / world; const int r = (int)(m - i * world);
+        out[e] = buf[((long long)r * n_max + i) * ncol + c];
+    }
 }
 
 }  // namespace
@@ -1266,8 +1280,10 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
         }
         CK(cudaStreamSynchronize(s1)); CK(cudaStreamSynchronize(s2));
         float ms = 0;
-        if (cnt[0] > 0 && cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) stt.ms_particle += ms;
-        if (cnt[1] > 0 && cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) stt.ms_gc += ms;
+        float msp = 0, msg = 0;
+        if (cnt[0] > 0 && cudaEventElapsedTime(&msp, ev[0], ev[1]) == cudaSuccess) stt.ms_particle += msp;
+        if (cnt[1] > 0 && cudaEventElapsedTime(&msg, ev[2], ev[3]) == cudaSuccess) stt.ms_gc += msg;
+        stt.per_epoch.insert(stt.per_epoch.end(), {(float)cnt[0], (float)cnt[1], msp, msg});
         CK(cudaEventRecord(ev[0], s0));
         if (int rc = launch_any(f, strict, UK_ADAPT, &sw, n, 0, s0)) return rc;
         CK(cudaEventRecord(ev[1], s0));
@@ -1317,6 +1333,21 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
     return RAPT_OK;
 }
 
+int rapt_b200_unshard_dev(int world, int64_t n_max, int ncol, int64_t n_total, const double *gathered, double *out, void *stream)
+{
+    if (int rc = ensure_init()) return rc;
+    if (world < 1 || n_max < 0 || ncol < 1 || n_total < 0 || n_total > (int64_t)world * n_max || !gathered || !out)
+        return fail(RAPT_E_ARG, "unshard: bad argument");
+    if (n_total == 0) return RAPT_OK;
+    if (int rc = check_on_bound_device(gathered, "unshard_dev")) return rc;
+    const long long total = n_total * ncol;
+    const int grid = (int)std::min<long long>((long long)g_sms * 16, (total + 255) / 256);
+    k_unshard<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(world, n_max, ncol, n_total, gathered, out);
+    CK(cudaGetLastError());
+    g_launches++;
+    return RAPT_OK;
+}
+
 int rapt_b200_adaptive_last_stats(double *out, int n)
 {
     if (!out || n < 15) return fail(RAPT_E_ARG, "adaptive_last_stats: need room for 15 doubles");
@@ -1325,6 +1356,7 @@ int rapt_b200_adaptive_last_stats(double *out, int n)
                           (double)a.tracer_launches_g, (double)a.steps_p, (double)a.accepted_p, (double)a.calls_p,
                           (double)a.steps_g, (double)a.calls_g, a.ms_particle, a.ms_gc, a.ms_switch, a.ms_epochs, 0.0};
     for (int k = 0; k < 15; k++) out[k] = v[k];
+    for (size_t k = 0; k < a.per_epoch.size() && 15 + (int)k < n; k++) out[15 + k] = a.per_epoch[k];
     return RAPT_OK;
 }
 

@@ -14,6 +14,9 @@
 #ifndef RAPT_NS
 #define RAPT_NS rapt_fast
 #endif
+#ifndef RAPT_DIPOLE_SERIES
+#define RAPT_DIPOLE_SERIES 1     /* 1: c r^-5 of the scaled dipole straight from the MUFU seed (see Field<0>::Bs) */
+#endif
 
 #define RAPT_C_LIGHT 299792458.0           /* rapt/__init__.py:8  */
 #define RAPT_EARTH_B0 3.07e-5              /* rapt/__init__.py:9  */
@@ -121,6 +124,16 @@ RAPT_DEV double fast_rsqrt(double x)
     // cost 6 % of the config-2 run time (profiles/r1_particle_history.md).
     return fma(y * e, fma(0.375, e, 0.5), y);
 #endif
+}
+
+// c / r^5 from r2 = r^2 in one go from the 22-bit MUFU seed y0 ~ 1/r: with e = 1 - r2 y0^2 (|e| < 2^-21),
+// r^-5 = y0^5 (1 - e)^(-5/2) = y0^5 (1 + e (5/2 + 35/8 e)) + O(e^3 ~ 1e-19).  5 DMUL + 3 DFMA; the rsqrt + powers form is 6 + 3.
+RAPT_DEV double fast_c_over_r5(double c, double r2)
+{
+    const double y0 = mufu_rsqrt(r2), u = y0 * y0;
+    const double e = fma(-r2, u, 1.0);
+    const double y5 = (c * y0) * (u * u);
+    return fma(y5 * e, fma(4.375, e, 2.5), y5);
 }
 
 #ifdef RAPT_USER_FIELD
@@ -289,8 +302,12 @@ template <int KIND> struct Field {
     }
     static RAPT_DEV void Bspace(const FieldP &f, double tf, double x, double y, double z, double &bx, double &by, double &bz)
     {
+#if RAPT_DIPOLE_SERIES
+        const double w = fast_c_over_r5(tf, x * x + y * y + z * z);
+#else
         const double ir = fast_rsqrt(x * x + y * y + z * z), ir2 = ir * ir;
         const double w = tf * (ir2 * ir2 * ir);
+#endif
         const double tz = 3 * z;
         bx = w * (tz * x); by = w * (tz * y); bz = w * fma(2 * z, z, -fma(x, x, y * y));
     }
@@ -304,8 +321,12 @@ template <int KIND> struct Field {
             double s = f.prm[0] / pow(r2, 2.5);
             bx = s * (x * z); by = s * (y * z); bz = s * (z * z - r2 / 3);
 #else
+#if RAPT_DIPOLE_SERIES
+            double s = fast_c_over_r5(f.prm[0], r2);
+#else
             double ir = fast_rsqrt(r2), ir2 = ir * ir;
             double s = f.prm[0] * (ir2 * ir2 * ir);
+#endif
             bx = s * (x * z); by = s * (y * z); bz = s * (z * z - r2 * (1.0 / 3.0));
 #endif
         } else if (KIND == 1) {             // DoubleDipole, fields.py:358-362
@@ -318,10 +339,14 @@ template <int KIND> struct Field {
             bx = f.prm[0] * (a0 + b0); by = f.prm[0] * (a1 + b1); bz = f.prm[0] * (a2 + b2);
 #else
             double yz2 = y * y + z * z, zz2 = 2 * z * z - y * y;
+            // B0 folded into the two weights (B0 and B0 k are invariants of the launch): 2 multiplies less per evaluation
+#if RAPT_DIPOLE_SERIES
+            double w1 = fast_c_over_r5(f.prm[0], x * x + yz2), w2 = fast_c_over_r5(f.prm[0] * k, x2 * x2 + yz2);
+#else
             double r1 = fast_rsqrt(x * x + yz2), r2_ = fast_rsqrt(x2 * x2 + yz2);
             double q1 = r1 * r1, q2 = r2_ * r2_;
-            // B0 folded into the two weights (B0 and B0 k are invariants of the launch): 2 multiplies less per evaluation
             double w1 = (f.prm[0] * r1) * (q1 * q1), w2 = ((f.prm[0] * k) * r2_) * (q2 * q2);
+#endif
             double tz = 3 * z;
             bx = tz * (x * w1 + x2 * w2);
             by = (tz * y) * (w1 + w2);
@@ -366,10 +391,19 @@ template <int KIND> struct Field {
 #if !RAPT_STRICT
         if (KIND == 0) {
             const double r2 = x * x + y * y + z * z;
+#if RAPT_DIPOLE_SERIES
+            const double w = fast_c_over_r5(sc * f.prm[0], r2);
+#else
             const double ir = fast_rsqrt(r2), ir2 = ir * ir;
             const double w = (sc * f.prm[0] * ir) * (ir2 * ir2);
+#endif
             const double wz = w * z;
             bx = wz * x; by = wz * y; bz = w * fma(z, z, -(1.0 / 3.0) * r2);
+            return;
+        }
+        if (KIND == 5) {                    // Parabolic: B0/d is an invariant of the launch (no division per evaluation)
+            bx = (fabs(z) <= 1.0) ? (sc * (f.prm[0] / f.prm[2])) * z : sc * (sgn(z) * RAPT_EARTH_B0);
+            by = 0; bz = sc * f.prm[1];
             return;
         }
 #endif
@@ -492,6 +526,20 @@ template <int KIND> struct Field {
         return magB(f, t, x, y, z) / m;
     }
     // fields.py:277-280
+    // max_ij |B_i(x + d e_j) - B_i(x - d e_j)| = 2 d max|J_ij|: the denominator of lengthscale() without its nine divisions
+    // (fast-flavour adiabaticity predicates compare products instead of quotients)
+    static RAPT_DEV double max_central_difference(const FieldP &f, double t, double x, double y, double z)
+    {
+        if (UNIFORM) return 0.0;
+        const double d = f.gradstep;
+        double ax, ay, az, bx, by, bz, m;
+        B(f, t, x + d, y, z, ax, ay, az); B(f, t, x - d, y, z, bx, by, bz);
+        m = fmax(fmax(fabs(ax - bx), fabs(ay - by)), fabs(az - bz));
+        B(f, t, x, y + d, z, ax, ay, az); B(f, t, x, y - d, z, bx, by, bz);
+        m = fmax(m, fmax(fmax(fabs(ax - bx), fabs(ay - by)), fabs(az - bz)));
+        B(f, t, x, y, z + d, ax, ay, az); B(f, t, x, y, z - d, bx, by, bz);
+        return fmax(m, fmax(fmax(fabs(ax - bx), fabs(ay - by)), fabs(az - bz)));
+    }
     static RAPT_DEV double timescale(const FieldP &f, double t, double x, double y, double z)
     {
         return magB(f, t, x, y, z) / fabs(dBdt(f, t, x, y, z));

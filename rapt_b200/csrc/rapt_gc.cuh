@@ -206,6 +206,24 @@ RAPT_DEV bool gc_isadiabatic(const FieldP &f, const ParamsP &p, double t, const 
                              double mu, double mass, double q)
 {
     const double pp = y[3];
+#if !RAPT_STRICT
+    // fast flavour: rho / L < epss without the reference's chain of quotients.  (gamma m)^2 (v^2 - v_par^2) = 2 m mu B in
+    // both of its branches, times the 1 / (1 - v^2 / c^2) of cyclotron_radius2 in the non-relativistic one (quirk kept), so
+    //   rho / L < epss  <=>  2 m mu G maxdiff^2 < (epss |q| 2d)^2 B^3.
+    {
+        double bx, by, bz; F::B(f, t, y[0], y[1], y[2], bx, by, bz);
+        const double B2 = dot3(bx, by, bz, bx, by, bz), B1 = B2 * fast_rsqrt(B2);
+        const double ic = 1.0 / RAPT_C_LIGHT, im = fast_rcp(mass);
+        const double pmc = pp * im * ic, w = 2 * mu * B1 * im;                 // w = 2 mu B / m
+        const double g2 = fma(pmc, pmc, fma(w, ic * ic, 1.0));
+        double G = 1.0;
+        if (g2 < 1.000002000001) G = fast_rcp(1.0 - fma(pp * im, pp * im, w) * (ic * ic));   // gamma - 1 < 1e-6 (:521-523)
+        const double md = F::max_central_difference(f, t, y[0], y[1], y[2]);
+        const double lim = p.epss * fabs(q) * (2 * f.gradstep);
+        const bool sp = (2 * mass * mu * G) * (md * md) < (lim * lim) * (B2 * B1);
+        if (f.is_static || !sp) return sp;
+    }
+#endif
     const double Bmag = F::magB(f, t, y[0], y[1], y[2]);
     const double pmc = pp / mass / RAPT_C_LIGHT;
     const double gamma = sqrt(1 + 2 * mu * Bmag / (mass * RAPT_C_LIGHT * RAPT_C_LIGHT) + pmc * pmc);
@@ -339,6 +357,12 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
                 }
                 break;
             case 2:
+                if (hin && F::CAN_FAIL && !(kout[0] == kout[0] && kout[3] == kout[3])) {
+                    // gridded field: the probe point lies outside the grid, where the reference's interpolator raises from
+                    // inside r.integrate() (no row for this call, the rows so far are kept)
+                    st = RAPT_ST_FIELD; skip = true; active = false;
+                    break;
+                }
                 if (hin) {
                     double der2 = 0;
 #pragma unroll

@@ -69,6 +69,22 @@ RAPT_DEV void particle_rhs(const FieldP &f, double q, double mass, double &gm, d
 template <class F>
 RAPT_DEV bool particle_isadiabatic(const FieldP &f, const ParamsP &p, double t, const double (&y)[6], double mass, double q)
 {
+#if !RAPT_STRICT
+    // fast flavour: the same inequality without a square root or a division.  gamma m v_perp = p_perp,
+    // p_perp^2 B^2 = p^2 B^2 - (p.B)^2, L = |B| / max|J| and max|J| = maxdiff / (2 d), so
+    //   rho / L < epss  <=>  p_perp maxdiff < epss |q| 2d B^2  <=>  (p^2 B^2 - (p.B)^2) maxdiff^2 < (epss |q| 2d)^2 (B^2)^3.
+    // The reference's quotient form costs ~20 fp64 divisions / square roots per row, executed by the few lanes that
+    // finish a row in the same iteration (profiles/r2_adaptive.md).
+    {
+        double bx, by, bz; F::B(f, t, y[0], y[1], y[2], bx, by, bz);
+        const double B2 = dot3(bx, by, bz, bx, by, bz), pB = dot3(y[3], y[4], y[5], bx, by, bz);
+        const double pp2B2 = fma(dot3(y[3], y[4], y[5], y[3], y[4], y[5]), B2, -pB * pB);
+        const double md = F::max_central_difference(f, t, y[0], y[1], y[2]);
+        const double lim = p.epss * fabs(q) * (2 * f.gradstep);
+        const bool sp = pp2B2 * (md * md) < (lim * lim) * (B2 * B2 * B2);
+        if (f.is_static || !sp) return sp;
+    }
+#endif
     double gm = sqrt(mass * mass + dot3(y[3], y[4], y[5], y[3], y[4], y[5]) / (RAPT_C_LIGHT * RAPT_C_LIGHT));
     double vx = y[3] / gm, vy = y[4] / gm, vz = y[5] / gm;
     double vsq = dot3(vx, vy, vz, vx, vy, vz);
@@ -231,6 +247,7 @@ __global__ void __launch_bounds__(128, 2) k_particle_dop853(const AdvArgs a)
                 }
                 break;
             case 2:
+                if (skip) break;                 // HINIT left the grid
                 // step prologue (every lane): failure checks, clip the step to the row end
                 if (nstep_row > 500) st = ST_NMAX;
                 else if (0.1 * fabs(h) <= fabs(x) * uround) st = ST_HSMALL;
@@ -285,6 +302,9 @@ __global__ void __launch_bounds__(128, 2) k_particle_dop853(const AdvArgs a)
                         der2 += d_ * d_;
 #endif
                     }
+                    // gridded field: the probe point may lie outside the grid, where the reference's interpolator raises
+                    // from inside r.integrate() (no row for this call, the rows so far are kept)
+                    if (F::CAN_FAIL && !(der2 == der2)) { st = RAPT_ST_FIELD; skip = true; break; }
                     der2 = sqrt(der2) / h;
                     double der12 = fmax(fabs(der2), sqrt(dnf));
                     // h1 = (0.01/der12)^(1/8) only matters when it is the smallest of the three candidates;

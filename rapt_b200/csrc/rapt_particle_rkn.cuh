@@ -26,6 +26,9 @@
 #ifndef RAPT_RKN_THREADS
 #define RAPT_RKN_THREADS 128
 #endif
+#ifndef RAPT_RKN_CTRL
+#define RAPT_RKN_CTRL 1      /* 1: the accepted-step controller multiplies by 1/fac (no fp64 division on the ~3-lane path) */
+#endif
 #ifndef RAPT_RKN_HK
 #define RAPT_RKN_HK 1        /* 1: stage vectors scaled by h (see the step body); 0: the unscaled form measured in round 1 */
 #endif
@@ -198,9 +201,15 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
                 // branch-free polynomial forms (~3e-14): this path runs at ~3 lanes in 9 of 10 iterations,
                 // so its length matters
                 const double lg = fast_log(fmax(err, 1e-300));
+#if RAPT_RKN_CTRL
+                // 1/fac directly: min(fac2, max(fac1, safe * facold^beta / err^expo1)) -- no division on this ~3-lane path
+                const double rfac = fmin(fac2, fmax(fac1, safe * fast_exp(fma(-expo1, lg, lfacold))));
+                double hnew = h * rfac;
+#else
                 double fac = fast_exp(fma(expo1, lg, -lfacold));
                 fac = fmax(facc2, fmin(facc1, fac / safe));
                 double hnew = h / fac;
+#endif
                 if (fabs(hnew) > hmax) hnew = hmax;
                 if (reject) hnew = fmin(fabs(hnew), fabs(h));
                 lfacold = beta * fmax(lg, -9.210340371976182);       // facold = max(err, 1e-4)
@@ -334,6 +343,9 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
             for (int i = 0; i < 3; i++) { const double c_ = (Kp[i] - K1[i]) * iskp[i]; d2 = fma(c_, c_, d2); }
             const double hi = h0 * igm;
             d2 = fma(hi * hi, s1, d2);
+            // gridded field: the probe point may lie outside the grid, where the reference's interpolator raises from
+            // inside r.integrate() (no row for this call, the rows so far are kept)
+            if (F::CAN_FAIL && !(d2 == d2)) { st = RAPT_ST_FIELD; continue; }
             // der2 = sqrt(d2)/h0, der12 = max(der2, sqrt(dnf)), h1 = (0.01/der12)^(1/8): compared in squares, the
             // root is only taken when h1 could be the minimum
             const double ih0 = fast_rcp(h0);
@@ -343,7 +355,7 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
             else {
                 const double hm2 = hmax * hmax, hm4 = hm2 * hm2, hm8 = hm4 * hm4, hm16 = hm8 * hm8;
                 if (hm16 > 1e-280 && d12 * hm16 * 1.000003 < 1e-4) h1 = hmax;      // h1 > hmax: not the minimum
-                else h1 = pow(0.01 / sqrt(d12), 1.0 / 8.0);
+                else h1 = fast_exp(0.125 * fma(-0.5, fast_log(d12), -4.605170185988091));   // (0.01 / sqrt(d12))^(1/8), branch-free
             }
             h = fmin(fmin(100 * h0, h1), hmax);
             lfacold = lf0; last = false; reject = false; nstep_row = 0; naccpt_row = 0;   // facold = 1e-4

