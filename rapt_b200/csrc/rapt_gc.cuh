@@ -248,10 +248,31 @@ RAPT_DEV bool gc_isadiabatic(const FieldP &f, const ParamsP &p, double t, const 
 #define RAPT_GC_POW(x, e) exp((e) * log(x))     // x > 0; ~1e-15 relative, no slow paths
 #endif
 
+#ifndef RAPT_GC_DEFER
+#define RAPT_GC_DEFER 0      /* 1: two tracers per lane, HINIT probes batched across the warp (see k_gc_dopri5); measured, does not pay: profiles/r2_gc_batched_probes.md */
+#endif
+#ifndef RAPT_GC_DEFER_MIN
+#define RAPT_GC_DEFER_MIN 16 /* lanes of a warp that must wait for a probe before the probe slot is run */
+#endif
+#define RAPT_GC_PARK_WORDS 27
+
 // MINB = resident CTAs per SM the register allocation is tuned for (2: 255 regs, no spills; 3: 168 regs; 4: 128 regs, ~0.5 KB of spill traffic per step, fastest: profiles/r1_other_configs.md)
+//
+// Batched HINIT probes (RAPT_GC_DEFER = 1; fast flavour, analytic fields; OFF by default).  A row takes ~9 steps, so in
+// every iteration ~11 % of the lanes of a warp start a row and need HINIT's Euler probe -- one more right-hand side, which
+// the whole warp then sits through at ~3.5 of 32 lanes (ncu: the right-hand side ran 7.25 times per iteration at 26.8
+// lanes, profiles/r2_01_gc_ncu_summary.txt).  With the switch on every lane owns TWO tracers: one in registers, one parked
+// in shared memory.  A lane whose tracer reaches a row boundary parks it and steps its other tracer; the probe slot is only
+// run when RAPT_GC_DEFER_MIN lanes of the warp have a tracer waiting (or lanes would idle otherwise).  Every tracer's
+// arithmetic is unchanged -- only WHEN its probe runs (tests/test_kernel_host.py: same bits as the build without it).
+// Measured in three A/B calls (profiles/r2_gc_batched_probes.md): the right-hand side runs 7.5 % less often at 28.9 lanes
+// and the kernel executes 5 % fewer instructions, but the 27 KB of parking space per block come out of the L1 that this
+// kernel's 0.4 KB/thread of register spills live in, and the exchange code pushes the hot loop past the instruction cache:
+// FP64 pipe 80.5 % -> 69-71 % active, 1.5-3.7 % SLOWER on config 3, 0.2-4.6 % on config 5.  Kept as a switch.
 template <class F, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
 {
+    constexpr bool DEFER = RAPT_GC_DEFER && !RAPT_STRICT && !F::CAN_FAIL;
     if (F::CAN_FAIL) grid_cache_reset();     // gridded field: per-thread cell cache (rapt_fields.cuh)
     const double rtol = a.p.rtol, atol = a.p.atol;
     const int eqf = a.p.enforce_equatorial, eom = a.eom;
@@ -267,9 +288,33 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
     int rowidx = 0, nst = 0, st = RAPT_ST_OK;
     bool last = false, reject = false, need_row = false, have = false;
     double *myrows = nullptr;
+    // the parked tracer of this lane: word w of thread i at park[w * blockDim + i] (conflict-free)
+    __shared__ double park[DEFER ? RAPT_GC_PARK_WORDS * 128 : 1];
+    bool phave = false, pneed = false;           // a tracer is parked / it waits for its HINIT probe (else it is mid-row)
+    (void)pf0;
 
+#define GC_SWD(v, w) { double *s_ = &park[(w) * 128 + threadIdx.x]; const double t_ = *s_; *s_ = (v); (v) = t_; }
+#define GC_SWI(i0, i1, w) { double *s_ = &park[(w) * 128 + threadIdx.x]; const double t_ = *s_;                      \
+                            *s_ = __hiloint2double((i0), (i1)); (i0) = __double2hiint(t_); (i1) = __double2loint(t_); }
+    // exchange the register tracer with the parked one (either may be empty)
+#define GC_SWAP_SLOTS()                                                                                                       \
+    {                                                                                                                         \
+        GC_SWD(y[0], 0) GC_SWD(y[1], 1) GC_SWD(y[2], 2) GC_SWD(y[3], 3)                                                       \
+        GC_SWD(k1[0], 4) GC_SWD(k1[1], 5) GC_SWD(k1[2], 6) GC_SWD(k1[3], 7)                                                   \
+        GC_SWD(x, 8) GC_SWD(h, 9) GC_SWD(xend, 10) GC_SWD(tstop, 11) GC_SWD(tlim, 12) GC_SWD(dt, 13) GC_SWD(facold, 14)       \
+        GC_SWD(hmax, 15) GC_SWD(gc.mass, 16) GC_SWD(gc.q, 17) GC_SWD(gc.mu, 18) GC_SWD(gc.v, 19)                              \
+        { double mr_ = __longlong_as_double((long long)(size_t)myrows); GC_SWD(mr_, 20)                                       \
+          myrows = (double *)(size_t)__double_as_longlong(mr_); }                                                             \
+        GC_SWI(pid, nstep, 21) GC_SWI(naccpt, nrejct, 22) GC_SWI(ncalls, nstep_row, 23) GC_SWI(naccpt_row, rowidx, 24)        \
+        GC_SWI(nst, st, 25)                                                                                                   \
+        { int fl_ = (last ? 1 : 0) | (reject ? 2 : 0), zero_ = 0; GC_SWI(fl_, zero_, 26)                                      \
+          last = (fl_ & 1) != 0; reject = (fl_ & 2) != 0; }                                                                   \
+        { const bool h_ = have, n_ = need_row; have = phave; need_row = pneed; phave = h_; pneed = n_; }                      \
+    }
+
+    bool done = false, more_work = true;
     for (;;) {
-        // ---- (A) guiding centre finished?  write it back and fetch the next one
+        // ---- (A) guiding centre finished?  write it back
         if (have && need_row && !(st == RAPT_ST_OK && x < tlim)) {
             if (a.seg_tstop) {                                   // sliced adaptive epoch
                 a.seg_row[pid] = rowidx;
@@ -286,45 +331,83 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
             a.nstored[pid] = nst;
             have = false;
         }
-        if (!have) {
-            int w = atomicAdd(a.queue, 1);
-            if (w >= a.nwork) break;
-            pid = a.order ? a.order[w] : w;
-            x = a.t[pid];
-            y[0] = a.s1[pid]; y[1] = a.s2[pid]; y[2] = a.s3[pid]; y[3] = a.s4[pid];
-            gc.mass = a.mass[pid]; gc.q = a.charge[pid]; gc.mu = a.mu[pid]; gc.v = a.v[pid];
-            dt = a.dtin[pid];
-            double delta = a.delta_arr ? a.delta_arr[pid] : a.delta;
-            tstop = x + delta;                                   // GuidingCenter.py:452
-            tlim = tstop;
-            int row0 = 0;
-            if (a.seg_tstop) { tstop = a.seg_tstop[pid]; tlim = fmin(tstop, a.slice_end); row0 = a.seg_row[pid]; }
-            nstep = naccpt = nrejct = ncalls = 0; rowidx = row0; st = RAPT_ST_OK;
-            myrows = a.rows ? a.rows + (size_t)pid * (size_t)a.max_rows * 8 : nullptr;
-            if (a.append) nst = a.nstored[pid];
-            else {
-                nst = 0;
-                if (myrows && a.store_every > 0 && a.max_rows > 0) {
-                    double2 *r = reinterpret_cast<double2 *>(myrows);
-                    r[0] = make_double2(x, y[0]); r[1] = make_double2(y[1], y[2]);
-                    r[2] = make_double2(y[3], gc.mu); r[3] = make_double2(0.0, 0.0);
-                    nst = 1;
+        // ---- (A') two tracers per lane.  ONE exchange per iteration in front of the fetch (each expansion of the exchange
+        // is ~100 instructions and the hot loop sits at the instruction-cache size):
+        //  * the register tracer waits for its probe and the park slot is free while more than one tracer per lane is
+        //    still queued: park it, the fetch below brings another one;
+        //  * the register tracer waits for its probe and the parked one is mid-row: step that one;
+        //  * the register slot is empty: continue with the parked tracer, unless it waits for a probe and another tracer
+        //    can be fetched first.
+        if (DEFER) {
+            // the queue counter is only looked at by a lane that has to decide (a read of that contended line every
+            // iteration cost 0.8 long-scoreboard stalls per issue), and never again once little work is left
+            if (more_work && ((have && need_row && !phave) || (!have && phave && pneed)))
+                more_work = (a.nwork - *(volatile int *)a.queue) > (int)(gridDim.x * blockDim.x);
+            if ((have && need_row && (phave ? !pneed : more_work)) || (!have && phave && (!pneed || !more_work))) GC_SWAP_SLOTS()
+        }
+        if (!have && !done) {
+            bool got = false;
+            if (!DEFER || !phave || more_work) {
+                int w = atomicAdd(a.queue, 1);
+                if (w < a.nwork) {
+                    got = true;
+                    pid = a.order ? a.order[w] : w;
+                    x = a.t[pid];
+                    y[0] = a.s1[pid]; y[1] = a.s2[pid]; y[2] = a.s3[pid]; y[3] = a.s4[pid];
+                    gc.mass = a.mass[pid]; gc.q = a.charge[pid]; gc.mu = a.mu[pid]; gc.v = a.v[pid];
+                    dt = a.dtin[pid];
+                    double delta = a.delta_arr ? a.delta_arr[pid] : a.delta;
+                    tstop = x + delta;                                   // GuidingCenter.py:452
+                    tlim = tstop;
+                    int row0 = 0;
+                    if (a.seg_tstop) { tstop = a.seg_tstop[pid]; tlim = fmin(tstop, a.slice_end); row0 = a.seg_row[pid]; }
+                    nstep = naccpt = nrejct = ncalls = 0; rowidx = row0; st = RAPT_ST_OK;
+                    myrows = a.rows ? a.rows + (size_t)pid * (size_t)a.max_rows * 8 : nullptr;
+                    if (a.append) nst = a.nstored[pid];
+                    else {
+                        nst = 0;
+                        if (myrows && a.store_every > 0 && a.max_rows > 0) {
+                            double2 *r = reinterpret_cast<double2 *>(myrows);
+                            r[0] = make_double2(x, y[0]); r[1] = make_double2(y[1], y[2]);
+                            r[2] = make_double2(y[3], gc.mu); r[3] = make_double2(0.0, 0.0);
+                            nst = 1;
+                        }
+                    }
+                    have = true; need_row = true;
+                    // degenerate output step (B = 0 or inf, bad resolution): the reference would never return;
+                    // delta <= 0 (or beyond this slice): nothing to do.  Both are retired at the top of the next iteration.
+                    if (!(dt > 0.0) || dt > 1e300) st = RAPT_ST_HSMALL;
+                    else if (x < tlim) gc_rhs<F>(a.f, gc, eom, eqf, x, y, k1);              // k1 = f(x, y)
                 }
             }
-            have = true; need_row = true;
-            if (!(dt > 0.0) || dt > 1e300) { st = RAPT_ST_HSMALL; continue; }   // degenerate output step (B = 0 or inf, bad
-                                                                             // resolution): the reference would never return
-            if (!(x < tlim)) continue;                           // delta <= 0 (or beyond this slice)
-            gc_rhs<F>(a.f, gc, eom, eqf, x, y, k1);              // k1 = f(x, y)
+            // nothing fetched: with a parked tracer (it waits for a probe: the probe slot below brings it in) the lane goes on
+            if (!got && !(DEFER && phave)) done = true;
+        }
+        if (DEFER) {
+            if (__all_sync(0xffffffffu, done)) break;            // lanes leave together (the votes below are warp-wide)
+        } else if (done) break;
+        // a tracer that was just fetched but cannot run (bad dt, nothing to do) waits for its retirement
+        const bool dead = have && need_row && !(st == RAPT_ST_OK && x < tlim);
+        // ---- (V) does this iteration run the probe slot?
+        bool do_probe = true;
+        if (DEFER) {
+            const bool a_np = have && need_row && !dead;
+            const unsigned m_np = __ballot_sync(0xffffffffu, a_np || (phave && pneed));
+            const unsigned m_rd = __ballot_sync(0xffffffffu, have && !need_row);
+            const unsigned m_any = __ballot_sync(0xffffffffu, (have && !dead) || phave);
+            // lanes that cannot step this iteration unless the probe runs (no second tracer to turn to)
+            const unsigned m_idle = __ballot_sync(0xffffffffu, (a_np || (phave && pneed)) && !(have && !need_row));
+            do_probe = m_np != 0 && (__popc(m_np) >= RAPT_GC_DEFER_MIN || __popc(m_idle) >= 4 || 2 * __popc(m_rd) < __popc(m_any));
+            if (do_probe && !a_np && !dead && phave && pneed) GC_SWAP_SLOTS()      // this lane's parked tracer takes the probe
         }
         // ---- (B) one step attempt; stage 1 = HINIT's Euler probe for lanes that start an output row
-        bool skip = false, hin = false, rowdone = false;
+        bool skip = !have || dead || (need_row && !do_probe), hin = false, rowdone = false;
 #pragma unroll 1
-        for (int s = 1; s <= 7; s++) {
+        for (int s = (DEFER && !do_probe) ? 2 : 1; s <= 7; s++) {
             bool active = !skip;
             switch (s) {
             case 1:
-                active = need_row;
+                active = !skip && need_row;
                 if (active) {
                     // new output row = new solver call: HINIT part 1
                     xend = x + dt;                               // GuidingCenter.py:453
@@ -357,6 +440,7 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
                 }
                 break;
             case 2:
+                if (skip) break;
                 if (hin && F::CAN_FAIL && !(kout[0] == kout[0] && kout[3] == kout[3])) {
                     // gridded field: the probe point lies outside the grid, where the reference's interpolator raises from
                     // inside r.integrate() (no row for this call, the rows so far are kept)
@@ -535,6 +619,9 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
             need_row = true;
         }
     }
+#undef GC_SWD
+#undef GC_SWI
+#undef GC_SWAP_SLOTS
 }
 
 }  // namespace RAPT_NS

@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
     const double rtol = a.p.rtol, atol = a.p.atol;
     const double beta = 0.1, safe = 0.9, fac1 = 0.3, fac2 = 6.0, uround = 2.3e-16;
     const double expo1 = 1.0 / 8.0 - beta * 0.2, facc1 = 1.0 / fac1, facc2 = 1.0 / fac2;
+    (void)facc2;
     const double lf0 = beta * -9.210340371976182;            // beta * log(1e-4): log of facold^beta at the start of a call
 
     double x[3], p[3], K1[3], X[3], P[3];

@@ -34,6 +34,7 @@ static inline double __hiloint2double(int hi, int lo)
 }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline unsigned __ballot_sync(unsigned, int pred) { return pred ? 1u : 0u; }   // a "warp" of one lane
+static inline int __all_sync(unsigned, int pred) { return pred ? 1 : 0; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline void __syncthreads() {}
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }   // work queue

@@ -13,7 +13,8 @@ _libs = {}
 def lib(arith="fast"):
     """fast: libkernelhost.so (FMA contraction on); strict: libkernelhost_strict.so (the reference's operation order)."""
     if arith not in _libs:
-        _libs[arith] = C.CDLL(os.path.join(_DIR, "libkernelhost_strict.so" if arith == "strict" else "libkernelhost.so"))
+        name = {"strict": "libkernelhost_strict.so", "fast-defer": "libkernelhost_defer.so"}.get(arith, "libkernelhost.so")
+        _libs[arith] = C.CDLL(os.path.join(_DIR, name))
     return _libs[arith]
 
 

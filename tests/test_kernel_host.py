@@ -563,3 +563,32 @@ def test_kernel_source_config2_solver_failure_member(arith, rkn):
         # this proton mirrors at 0.83 Re, inside the planet, where the dipole field and its gradient are so large that the
         # step size collapses: the last rows before the failure are already ill-conditioned (7.7e-7 between flavours)
         assert H.vec_relerr(rows[:, 1:4], d["last_rows"][:, 1:4]) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", ["config3", "config5"])
+def test_gc_kernel_source_probe_batching_changes_no_bits(cfg):
+    """With RAPT_GC_DEFER k_gc_dopri5 keeps two tracers per lane and batches HINIT probes across the warp (an option that
+    was measured and is off by default, profiles/r2_gc_batched_probes.md): only the time at which a tracer's probe runs
+    changes, so every result must equal the default build bit for bit (states, rows, counters, status), with a
+    store-every-3 row buffer and ragged lane loads."""
+    from rapt_b200 import synth
+    import oracle as O
+    n = 1500
+    if cfg == "config3":
+        ic = synth.config3_electrons(n); f = H.gpu_field("DoubleDipole", ()); of = O.make_field("DoubleDipole"); dt = 0.1
+    else:
+        ic = synth.config5_belt(n); f = H.gpu_field("VarEarthDipole", (0.1, 10)); of = O.make_field("VarEarthDipole", 0.1, 10); dt = 0.05
+    pos = np.column_stack([ic["x"], ic["y"], ic["z"]])
+    ppar, mu = O.gc_construct(of, ic["t0"], pos, ic["v"], ic["pa"], ic["mass"])
+    st = np.column_stack([ic["t0"], pos, ppar])
+    outs = []
+    for arith, nth in (("fast", 8), ("fast-defer", 8), ("fast-defer", 1)):
+        o = K.gc_advance(f, st, mu, ic["v"], ic["mass"], ic["charge"], dt, 1.5, store_every=3, max_rows=16, nthreads=nth,
+                         arith=arith, check_adiabaticity=(cfg == "config3"))
+        outs.append(o)
+    for o in outs[1:]:
+        for k in ("state", "nrows", "nstored", "counters", "status", "tcur"):
+            assert np.array_equal(outs[0][k], o[k]), k
+        for i in range(n):
+            assert np.array_equal(outs[0]["rows"][i, :outs[0]["nstored"][i]], o["rows"][i, :o["nstored"][i]])
+    assert outs[0]["counters"][:, 1].sum() > 10 * n
