@@ -304,7 +304,7 @@ def time_workload(args, workload, n_per_gpu, world, rank, dev, steps, warmup, wa
         if ev is not None:
             ev[1].record()
         if world > 1:
-            ens.gather(nbins=64)                                         # pack + histogram kernel, all-gather, all-reduce
+            ens.gather(nbins=64, sync=False)                             # pack + histogram kernel, all-gather, all-reduce
         if ev is not None:
             ev[2].record()
 

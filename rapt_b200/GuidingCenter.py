@@ -2,8 +2,8 @@
 
 `advance()` runs on the GPU (per-thread DOPRI5, three selectable equations of motion on the
 finite-difference field operators: rapt_b200/csrc/rapt_gc.cuh).  The output step is
-params['GCtimestep'] or bounceperiod()/params['bounceresolution'], where the bounce period's
-field-line trace runs on the device and its spline/root/quadrature leg uses scipy as the reference does.
+params['GCtimestep'] or bounceperiod()/params['bounceresolution']; the bounce period (field-line trace, then
+scipy's quadratic spline, brentq and QUADPACK QAGS restated per thread) is computed on the device as well.
 """
 import pickle
 import numpy as np

@@ -99,12 +99,16 @@ class _Resident:
             self._dev = None
         return self
 
-    def gather(self, nbins=64, lo=None, hi=None, kind=None, profile=False):
+    def gather(self, nbins=64, lo=None, hi=None, kind=None, profile=False, sync=True):
         """Final states of the WHOLE ensemble in member order on every rank + all-reduced diagnostics.
         Returns dict(final=(n_total, ncol) CUDA tensor, hist=int64 [nbins], edges, stats=dict(ok, mean, var, outside)).
         kind 'ke': log10 kinetic energy [eV] (Particle.getke); 'r': radial distance [Re].
         profile=True adds timing_ms = device time of the pack+histogram kernel, the all-gather (+ un-interleave) and the
-        all-reduce (CUDA events on the current stream)."""
+        all-reduce (CUDA events on the current stream).
+        sync=False returns without touching the host: `stats` is then the raw CUDA tensor (ok count, sum q, sum q^2,
+        outside) and nothing is synchronised, so a caller that advances again can queue its next launches behind the
+        collectives (measured on 8 GPUs: the host round trip per step let the ranks drift apart by ~4 ms, which the
+        slowest rank then paid inside the next all-gather: profiles/r2_multi_gpu.md)."""
         import torch
         from . import dist as rd
         d = self._dev
@@ -133,10 +137,13 @@ class _Resident:
         if ev: ev[2].record()
         rd.reduce_diagnostics(d.hist, d.stats, getattr(self, "_group", None))
         if ev: ev[3].record()
-        st = d.stats.cpu().numpy()
-        ok = max(st[0], 1.0)
-        res = dict(final=final, hist=d.hist, edges=np.linspace(lo, hi, nbins + 1), kind=kind,
-                   stats=dict(ok=int(st[0]), mean=st[1] / ok, var=st[2] / ok - (st[1] / ok) ** 2, outside=int(st[3])))
+        if sync:
+            st = d.stats.cpu().numpy()
+            ok = max(st[0], 1.0)
+            stats = dict(ok=int(st[0]), mean=st[1] / ok, var=st[2] / ok - (st[1] / ok) ** 2, outside=int(st[3]))
+        else:
+            stats = d.stats
+        res = dict(final=final, hist=d.hist, edges=np.linspace(lo, hi, nbins + 1), kind=kind, stats=stats)
         if ev:
             ev[3].synchronize()
             res["timing_ms"] = dict(pack_hist=ev[0].elapsed_time(ev[1]), allgather_unshard=ev[1].elapsed_time(ev[2]),
@@ -263,14 +270,13 @@ class GuidingCenterEnsemble(_Resident):
     _DIAG = "r"
 
     def bounceperiod(self, method="quadpack"):
-        """GuidingCenter.bounceperiod of every member (rapt/GuidingCenter.py:593-606).
-        "quadpack" (default): all on the device -- field-line trace, scipy's spline, brentq and QUADPACK QAGS
-            restated per thread: the reference's value to ~1e-9;
-        "closed-form": all on the device, mirror points and integral in closed form (within the error of the
-            reference's QUADPACK call: 1e-7 typical, 2e-5 worst seen);
-        "scipy": device traces + scipy's own interp1d/brentq/quad in a host loop (~5 ms per member; kept as a cross-check)."""
-        if method == "scipy":
-            return engine.bounceperiod(self.field, self.state, self.mu, self.mass, params["fieldlineresolution"])
+        """GuidingCenter.bounceperiod of every member (rapt/GuidingCenter.py:593-606), all on the device.
+        "quadpack" (default): field-line trace, then scipy's spline, brentq and QUADPACK QAGS restated per thread: the
+            reference's value to ~1e-9;
+        "closed-form": mirror points and integral in closed form (within the error of the reference's QUADPACK call:
+            1e-7 typical, 2e-5 worst seen)."""
+        if method not in ("quadpack", "closed-form"):
+            raise ValueError("method is 'quadpack' or 'closed-form' (the scipy cross-check lives in tests/scipy_legs.py)")
         return engine.bounceperiod_device(self.field, self.state, self.mu, self.mass, params["fieldlineresolution"],
                                           quadrature="closed" if method == "closed-form" else "quadpack")
 
