@@ -634,7 +634,10 @@ int rapt_b200_particle_advance_dev(const rapt_field_t *f, const rapt_params_t *p
     const bool strict = p->arith == 1;
     const int rkn = !strict && f->is_static && !p->enforce_equatorial && f->kind != RAPT_FIELD_USER && !getenv("RAPT_B200_NO_RKN");
     const int grid = grid_for(n, FLAVOUR(strict, particle_blocks_per_sm, rkn));
-    if (p->sort_by_work && n > (long long)grid * 128) { if (int rc = build_order(f, a, strict, s)) return rc; }
+    if (p->sort_by_work && n > (long long)grid * 128) {
+        if (int rc = build_order(f, a, strict, s)) return rc;
+        if (rkn && !getenv("RAPT_B200_NO_SPREAD")) a.spread_first_wave = grid * 128;     // n > lanes: the first wave is full
+    }
     if (int rc = launch_any(f, strict, UK_PARTICLE, &a, n, grid, s)) return rc;
     g_launches++;
     return RAPT_OK;

@@ -26,6 +26,9 @@
 #ifndef RAPT_RKN_THREADS
 #define RAPT_RKN_THREADS 128
 #endif
+#ifndef RAPT_RKN_LOCKSTEP
+#define RAPT_RKN_LOCKSTEP 0  /* k > 0: the warps of a block meet at a barrier every k iterations (see the end of the loop) */
+#endif
 #ifndef RAPT_RKN_CTRL
 #define RAPT_RKN_CTRL 1      /* 1: the accepted-step controller multiplies by 1/fac (no fp64 division on the ~3-lane path) */
 #endif
@@ -73,6 +76,14 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
     int rowidx = 0, nst = 0, st = ST_OK;
     bool last = false, reject = false, need_row = false, have = false;
     double *myrows = nullptr;
+    bool done = false;
+    (void)done;
+#if RAPT_RKN_LOCKSTEP
+    unsigned iter = 0;
+#endif
+#ifdef RAPT_RKN_TRACE_TIMES
+    double t_fetch = 0;
+#endif
 
     for (;;) {
         // ---- (A) one step attempt: failure checks, clip the step to the row end.  The loop is ordered
@@ -268,12 +279,25 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
             a.tcur[pid] = t + dt;                            // Particle.py:306
             if (a.nrows) a.nrows[pid] = rowidx + 1;
             a.nstored[pid] = nst;
+#ifdef RAPT_RKN_TRACE_TIMES      /* profiling build only: when was this tracer fetched and retired (global ns timer) */
+            { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); a.tcur[pid] = (double)g_; a.dt_out[pid] = t_fetch; }
+#endif
             have = false;
         }
-        if (!have) {
+        if (!have && !done) {
             int w = atomicAdd(a.queue, 1);
+#if RAPT_RKN_LOCKSTEP
+            if (w >= a.nwork) { done = true; w = 0; }
+            else {
+#else
             if (w >= a.nwork) break;
+            {
+#endif
+            if (w < a.spread_first_wave) w = (w & 31) * (a.spread_first_wave >> 5) + (w >> 5);   // rapt_types.h: AdvArgs
             pid = a.order ? a.order[w] : w;
+#ifdef RAPT_RKN_TRACE_TIMES
+            { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); t_fetch = (double)g_; }
+#endif
             t = a.t[pid];
             x[0] = a.s1[pid]; x[1] = a.s2[pid]; x[2] = a.s3[pid];
             p[0] = a.s4[pid]; p[1] = a.s5[pid]; p[2] = a.s6[pid];
@@ -317,9 +341,10 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
             // delta <= 0 (or beyond this slice): nothing to do
             if (!(dt > 0.0) || dt > 1e300) st = RAPT_ST_HSMALL;
             else if (t < tlim) lorentz_K<F>(a.f, q, qg, t, x, p, K1);          // k1 = f(t, y)
+            }
         }
         // ---- (C) a new output row is a new solver call: xend, hmax, HINIT
-        if (need_row && st == ST_OK && t < tlim) {
+        if (have && need_row && st == ST_OK && t < tlim) {
             xend = t + dt;                                   // Particle.py:305 (also the row's time label)
             hmax = fabs(xend - t);
             double iskx[3], iskp[3];
@@ -346,7 +371,8 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
             d2 = fma(hi * hi, s1, d2);
             // gridded field: the probe point may lie outside the grid, where the reference's interpolator raises from
             // inside r.integrate() (no row for this call, the rows so far are kept)
-            if (F::CAN_FAIL && !(d2 == d2)) { st = RAPT_ST_FIELD; continue; }
+            if (F::CAN_FAIL && !(d2 == d2)) st = RAPT_ST_FIELD;      // need_row stays set: retired at (B) of the next iteration
+            else {
             // der2 = sqrt(d2)/h0, der12 = max(der2, sqrt(dnf)), h1 = (0.01/der12)^(1/8): compared in squares, the
             // root is only taken when h1 could be the minimum
             const double ih0 = fast_rcp(h0);
@@ -362,7 +388,14 @@ __global__ void __launch_bounds__(RAPT_RKN_THREADS, RAPT_RKN_MINB) k_particle_rk
             lfacold = lf0; last = false; reject = false; nstep_row = 0; naccpt_row = 0;   // facold = 1e-4
             ncalls++;
             need_row = false;
+            }
         }
+#if RAPT_RKN_LOCKSTEP
+        // The hardware warp scheduler is not fair: per-tracer fetch/retire times show warps of the same SM advancing at
+        // 3.1 ... 13 us per step for the whole kernel (profiles/r2_tail.md), and the orbits that happen to sit in a starved
+        // warp are the tail of the launch.  A barrier every k iterations makes the warps of a block advance together.
+        if ((++iter % RAPT_RKN_LOCKSTEP) == 0 && __syncthreads_and(done)) break;
+#endif
     }
 }
 

@@ -57,6 +57,10 @@ struct AdvArgs {
     double *seg_dt;               // Particle: output step chosen at the start of the call (0: not chosen yet)
     int *seg_row;                 // output-row index within the call (decimation phase)
     double slice_end;
+    // work order of the first wave: with `order` sorted longest-first the 32 lanes of a warp would start on 32 NEIGHBOURS of
+    // the sorted list, i.e. whole warps of the very longest tracers.  spread_first_wave = L (lanes of the launch, a multiple
+    // of 32) hands lane j of the k-th warp the item j * (L / 32) + k instead: every warp starts with the same mix.
+    int spread_first_wave;
 };
 
 // state columns handed to the final-diagnostics kernel (capi.cu:k_final_diagnostics)

@@ -37,6 +37,7 @@ static inline unsigned __ballot_sync(unsigned, int pred) { return pred ? 1u : 0u
 static inline int __all_sync(unsigned, int pred) { return pred ? 1 : 0; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline void __syncthreads() {}
+static inline int __syncthreads_and(int pred) { return pred ? 1 : 0; }
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }   // work queue
 using std::min; using std::max;
 using std::fabs; using std::fmax; using std::fmin; using std::sqrt; using std::fma; using std::rint;

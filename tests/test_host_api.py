@@ -268,3 +268,27 @@ def test_integration_doc_covers_every_entry_point():
     declared = set(re.findall(r"\b(rapt_b200_[a-z0-9_]+)\s*\(", hdr))
     missing = sorted(s for s in declared if s not in doc)
     assert not missing, missing
+
+
+def test_gpu_test_files_only_call_functions_that_exist():
+    """Static check, runs without a GPU: every `eng.X` / `engine.X` / `scipy_legs.X` / `rd.X` attribute the -m gpu test
+    files (and bench.py, smoke()) touch exists in the module it names -- a renamed or moved helper is caught here, not on
+    the B200 box."""
+    import ast
+    import glob
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    targets = {"eng": "rapt_b200.engine", "engine": "rapt_b200.engine", "scipy_legs": "scipy_legs", "rd": "rapt_b200.dist",
+               "synth": "rapt_b200.synth", "_lib": "rapt_b200._lib"}
+    mods = {k: importlib.import_module(v) for k, v in targets.items()}
+    files = glob.glob(os.path.join(ROOT, "tests", "test_gpu_*.py")) + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py"),
+                                                                     os.path.join(ROOT, "tools", "count_parity_report.py"),
+                                                                     os.path.join(ROOT, "tools", "tail_profile.py")]
+    missing = []
+    for fn in files:
+        for node in ast.walk(ast.parse(open(fn).read())):
+            if isinstance(node, ast.Attribute) and isinstance(node.value, ast.Name) and node.value.id in mods:
+                if not hasattr(mods[node.value.id], node.attr):
+                    missing.append(f"{os.path.basename(fn)}:{node.lineno} {node.value.id}.{node.attr}")
+    assert not missing, missing
