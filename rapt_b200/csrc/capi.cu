@@ -205,6 +205,7 @@ int nvrtc_compile(const UserField &uf, bool strict, std::string &cubin, std::str
     src += std::string("#define RAPT_USER_HAS_E ") + (uf.has_E ? "1" : "0") + "\n";
     src += std::string("#define RAPT_STRICT ") + (strict ? "1" : "0") + "\n";
     src += "#define RAPT_NS rapt_user\n";
+    src += "#define RAPT_GC_THREADS 128\n";           // user kernels are launched with 128-thread blocks (launch_any)
     src += "#include \"rapt_bc.cuh\"\n";
     src += "namespace rapt_user {\n"
            "template <class F> __global__ void k_particle_dt(const rapt::AdvArgs a, double *key, int *idx) {\n"
@@ -636,7 +637,7 @@ int rapt_b200_particle_advance_dev(const rapt_field_t *f, const rapt_params_t *p
     const int grid = grid_for(n, FLAVOUR(strict, particle_blocks_per_sm, rkn));
     if (p->sort_by_work && n > (long long)grid * 128) {
         if (int rc = build_order(f, a, strict, s)) return rc;
-        if (rkn && !getenv("RAPT_B200_NO_SPREAD")) a.spread_first_wave = grid * 128;     // n > lanes: the first wave is full
+        if (rkn && getenv("RAPT_B200_SPREAD")) a.spread_first_wave = grid * 128;        // opt-in: measured, no gain (profiles/r2_tail.md)
     }
     if (int rc = launch_any(f, strict, UK_PARTICLE, &a, n, grid, s)) return rc;
     g_launches++;

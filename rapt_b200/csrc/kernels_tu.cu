@@ -13,6 +13,17 @@ template <class K> static size_t grid_cache_bytes(const rapt::AdvArgs &a, K kern
     return bytes;
 }
 
+// Block shape of the persistent advance kernels.  A launch that fills the GPU runs ONE big block per SM: the warps of one block
+// share the SM's issue slots evenly, the warps of four 128-thread blocks do not (profiles/r2_tail.md: -10 % on config 2).
+// A launch with fewer tracers than lanes (the late epochs of an adaptive run, single objects) is latency-bound and wants
+// its warps spread over as many SMs as possible: 128-thread blocks.  Both shapes are launches of the same kernel.
+static int block_threads(int grid128, int big)
+{
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    return ((long long)grid128 * 128 >= (long long)sms * big) ? big : 128;
+}
+
 #ifdef RAPT_TU_PARTICLE
 #include "rapt_particle.cuh"
 #if !RAPT_STRICT
@@ -26,9 +37,10 @@ static bool use_rkn(const rapt::AdvArgs &a) { return a.f.is_static && !a.p.enfor
 template <int KIND> static cudaError_t go_particle(const rapt::AdvArgs &a, int grid, cudaStream_t s)
 {
 #if !RAPT_STRICT
-    if (use_rkn(a)) k_particle_rkn<Field<KIND>><<<(grid * 128 + RAPT_RKN_THREADS - 1) / RAPT_RKN_THREADS, RAPT_RKN_THREADS,
-                                                  grid_cache_bytes(a, k_particle_rkn<Field<KIND>>, RAPT_RKN_THREADS), s>>>(a);
-    else
+    if (use_rkn(a)) {
+        const int T = block_threads(grid, RAPT_RKN_THREADS);
+        k_particle_rkn<Field<KIND>><<<(grid * 128 + T - 1) / T, T, grid_cache_bytes(a, k_particle_rkn<Field<KIND>>, T), s>>>(a);
+    } else
 #endif
     k_particle_dop853<Field<KIND>><<<grid, 128, grid_cache_bytes(a, k_particle_dop853<Field<KIND>>, 128), s>>>(a);
     return cudaGetLastError();
@@ -70,9 +82,11 @@ namespace RAPT_NS {
 static int gc_minb() { const char *e = getenv("RAPT_B200_GC_BLOCKS"); return e ? atoi(e) : RAPT_GC_DEFAULT_BLOCKS; }
 template <int KIND> static cudaError_t go_gc(const rapt::AdvArgs &a, int grid, cudaStream_t s)
 {
-    if (gc_minb() >= 4) k_gc_dopri5<Field<KIND>, 4><<<grid, 128, grid_cache_bytes(a, k_gc_dopri5<Field<KIND>, 4>, 128), s>>>(a);
-    else if (gc_minb() == 3) k_gc_dopri5<Field<KIND>, 3><<<grid, 128, grid_cache_bytes(a, k_gc_dopri5<Field<KIND>, 3>, 128), s>>>(a);
-    else k_gc_dopri5<Field<KIND>, 2><<<grid, 128, grid_cache_bytes(a, k_gc_dopri5<Field<KIND>, 2>, 128), s>>>(a);
+    // `grid` counts 128-lane units (capi.cu:grid_for); the kernel runs RAPT_GC_THREADS threads per block
+    const int T = block_threads(grid, RAPT_GC_THREADS), nb = (grid * 128 + T - 1) / T;
+    if (gc_minb() >= 4) k_gc_dopri5<Field<KIND>, 4><<<nb, T, grid_cache_bytes(a, k_gc_dopri5<Field<KIND>, 4>, T), s>>>(a);
+    else if (gc_minb() == 3) k_gc_dopri5<Field<KIND>, 3><<<nb, T, grid_cache_bytes(a, k_gc_dopri5<Field<KIND>, 3>, T), s>>>(a);
+    else k_gc_dopri5<Field<KIND>, 2><<<nb, T, grid_cache_bytes(a, k_gc_dopri5<Field<KIND>, 2>, T), s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_gc(const rapt::AdvArgs &a, int grid, cudaStream_t s)
@@ -91,10 +105,11 @@ cudaError_t launch_gc(const rapt::AdvArgs &a, int grid, cudaStream_t s)
 int gc_blocks_per_sm()
 {
     int nb = 0;
-    if (gc_minb() >= 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gc_dopri5<Field<1>, 4>, 128, 0);
-    else if (gc_minb() == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gc_dopri5<Field<1>, 3>, 128, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gc_dopri5<Field<1>, 2>, 128, 0);
-    return nb;
+    const int T = RAPT_GC_THREADS;
+    if (gc_minb() >= 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gc_dopri5<Field<1>, 4>, T, 0);
+    else if (gc_minb() == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gc_dopri5<Field<1>, 3>, T, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gc_dopri5<Field<1>, 2>, T, 0);
+    return (nb * T + 127) / 128;      // in units of 128 lanes
 }
 }  // namespace RAPT_NS
 #endif

@@ -255,6 +255,10 @@ RAPT_DEV bool gc_isadiabatic(const FieldP &f, const ParamsP &p, double t, const 
 #define RAPT_GC_DEFER_MIN 16 /* lanes of a warp that must wait for a probe before the probe slot is run */
 #endif
 #define RAPT_GC_PARK_WORDS 27
+#ifndef RAPT_GC_THREADS
+#define RAPT_GC_THREADS 512  /* threads per block of a launch that fills the GPU (kernels_tu.cu:block_threads); MINB counts resident 128-thread
+                                units per SM, so 512 is one block per SM at MINB = 4: 212.4 vs 215.6 ms on config 3, 383.5 vs 389.4 on config 5 */
+#endif
 
 // MINB = resident CTAs per SM the register allocation is tuned for (2: 255 regs, no spills; 3: 168 regs; 4: 128 regs, ~0.5 KB of spill traffic per step, fastest: profiles/r1_other_configs.md)
 //
@@ -270,7 +274,7 @@ RAPT_DEV bool gc_isadiabatic(const FieldP &f, const ParamsP &p, double t, const 
 // kernel's 0.4 KB/thread of register spills live in, and the exchange code pushes the hot loop past the instruction cache:
 // FP64 pipe 80.5 % -> 69-71 % active, 1.5-3.7 % SLOWER on config 3, 0.2-4.6 % on config 5.  Kept as a switch.
 template <class F, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
+__global__ void __launch_bounds__(RAPT_GC_THREADS, (MINB * 128 >= RAPT_GC_THREADS) ? (MINB * 128) / RAPT_GC_THREADS : 1) k_gc_dopri5(const AdvArgs a)
 {
     constexpr bool DEFER = RAPT_GC_DEFER && !RAPT_STRICT && !F::CAN_FAIL;
     if (F::CAN_FAIL) grid_cache_reset();     // gridded field: per-thread cell cache (rapt_fields.cuh)
@@ -289,12 +293,12 @@ __global__ void __launch_bounds__(128, MINB) k_gc_dopri5(const AdvArgs a)
     bool last = false, reject = false, need_row = false, have = false;
     double *myrows = nullptr;
     // the parked tracer of this lane: word w of thread i at park[w * blockDim + i] (conflict-free)
-    __shared__ double park[DEFER ? RAPT_GC_PARK_WORDS * 128 : 1];
+    __shared__ double park[DEFER ? RAPT_GC_PARK_WORDS * RAPT_GC_THREADS : 1];
     bool phave = false, pneed = false;           // a tracer is parked / it waits for its HINIT probe (else it is mid-row)
     (void)pf0;
 
-#define GC_SWD(v, w) { double *s_ = &park[(w) * 128 + threadIdx.x]; const double t_ = *s_; *s_ = (v); (v) = t_; }
-#define GC_SWI(i0, i1, w) { double *s_ = &park[(w) * 128 + threadIdx.x]; const double t_ = *s_;                      \
+#define GC_SWD(v, w) { double *s_ = &park[(w) * RAPT_GC_THREADS + threadIdx.x]; const double t_ = *s_; *s_ = (v); (v) = t_; }
+#define GC_SWI(i0, i1, w) { double *s_ = &park[(w) * RAPT_GC_THREADS + threadIdx.x]; const double t_ = *s_;                      \
                             *s_ = __hiloint2double((i0), (i1)); (i0) = __double2hiint(t_); (i1) = __double2loint(t_); }
     // exchange the register tracer with the parked one (either may be empty)
 #define GC_SWAP_SLOTS()                                                                                                       \

@@ -20,11 +20,15 @@
 #pragma once
 #include "rapt_particle.cuh"
 
+// ONE 512-thread block per SM (16 warps, 128 registers): measured 222.5 ms against 245.9 ms for four 128-thread blocks on
+// config 2 (profiles/r2_tail.md).  Per-tracer fetch/retire times showed why: with four blocks per SM the warps of one SM
+// advanced at 3.1 ... 13 us per step for the whole kernel (the hardware scheduler does not share issue slots evenly between
+// warps of different blocks), and the orbits that sat in a starved warp were a 36 ms tail on < 500 lanes.
 #ifndef RAPT_RKN_MINB
-#define RAPT_RKN_MINB 4
+#define RAPT_RKN_MINB 1
 #endif
 #ifndef RAPT_RKN_THREADS
-#define RAPT_RKN_THREADS 128
+#define RAPT_RKN_THREADS 512
 #endif
 #ifndef RAPT_RKN_LOCKSTEP
 #define RAPT_RKN_LOCKSTEP 0  /* k > 0: the warps of a block meet at a barrier every k iterations (see the end of the loop) */
