@@ -127,8 +127,9 @@ def gc_field(workload):
     return fields.DoubleDipole() if workload == "gc" else fields.VarEarthDipole(0.1, 10)
 
 
-def build_ensemble(workload, n_total, world, rank):
-    """The seeded ensemble of `workload` as the product's ensemble object, sharded onto this rank's GPU."""
+def build_ensemble(workload, n_total, world, rank, weights=None, keep_full=False):
+    """The seeded ensemble of `workload` as the product's ensemble object, sharded onto this rank's GPU
+    (weights: rapt_b200/dist.py:ShardPlan; None = round-robin)."""
     import rapt_b200 as R
     from rapt_b200 import synth
     big = n_total > 20_000_000      # 100 M-tracer ensembles: every rank draws its own shard (seed + rank) instead of
@@ -146,8 +147,9 @@ def build_ensemble(workload, n_total, world, rank):
     if big:
         ens.world, ens.rank, ens.n_total, ens._group = world, rank, ens.n * world, None
         from rapt_b200 import dist as rd
+        ens._plan = rd.ShardPlan(ens.n_total, world)
         return ens.cuda(rd.local_device())
-    return ens.shard()
+    return ens.shard(weights=weights, keep_full=keep_full)
 
 
 def run_advance(ens, workload, delta, arith):
@@ -289,14 +291,17 @@ def time_workload(args, workload, n_per_gpu, world, rank, dev, steps, warmup, wa
     import torch.distributed as dist
     from rapt_b200 import engine, _lib
     n_total = n_per_gpu * world if args.scaling == "weak" else n_per_gpu
-    ens = build_ensemble(workload, n_total, world, rank)
-    n = ens.n
-    d = ens._dev
-    pristine = [c.clone() for c in d.cols]
+    rebalance = bool(args.rebalance) and world > 1 and n_total <= 20_000_000
+    ens = build_ensemble(workload, n_total, world, rank, weights=np.ones(world) if rebalance else None, keep_full=rebalance)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    cur = {}
+
+    def attach():
+        cur["d"] = ens._dev
+        cur["pristine"] = [c.clone() for c in ens._dev.cols]
 
     def one_step(ev=None):
-        ens.load_state(pristine)
+        ens.load_state(cur["pristine"])
         flush.fill_(1)                                                   # L2 flush between steps
         if ev is not None:
             ev[0].record()
@@ -307,6 +312,34 @@ def time_workload(args, workload, n_per_gpu, world, rank, dev, steps, warmup, wa
             ens.gather(nbins=64, sync=False)                             # pack + histogram kernel, all-gather, all-reduce
         if ev is not None:
             ev[2].record()
+
+    attach()
+    shard_history = None
+    if rebalance:
+        # Speed-weighted shards: the GPUs of one box run the same shard up to a few per cent apart (profiles/r2_multi_gpu.md)
+        # and a step ends with the slowest.  Before the warm-up: time the kernel on every rank, give every rank a share of
+        # each 4096-member period proportional to its measured tracers per second, and repeat once (the second cut moves
+        # only the ends of the runs).  Not part of the timed region; the shard sizes are reported in per_rank.
+        shard_history = []
+        weights = np.ones(world)
+        for _ in range(int(args.rebalance)):
+            one_step()
+            cev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            one_step(cev)
+            torch.cuda.synchronize()
+            mine = torch.tensor([cev[0].elapsed_time(cev[1]), float(ens.n)], dtype=torch.float64, device=dev)
+            allm = torch.empty((world, 2), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allm.view(-1), mine)
+            allm = allm.cpu().numpy()
+            shard_history.append({"sizes": [int(v) for v in allm[:, 1]], "kernel_ms": [round(float(v), 3) for v in allm[:, 0]]})
+            speed = allm[:, 1] / allm[:, 0]
+            weights = speed / speed.mean()
+            cur.clear()
+            ens.reshard(weights)
+            attach()
+    n = ens.n
+    d = ens._dev
+    pristine = cur["pristine"]
 
     for _ in range(warmup):
         one_step()
@@ -357,9 +390,15 @@ def time_workload(args, workload, n_per_gpu, world, rank, dev, steps, warmup, wa
     nstep, naccpt, ncalls, nok, nall = (float(stats[i]) for i in range(5))
     ms_per_step = ms / steps
     rec = dict(value=nstep / (ms_per_step * 1e-3), ms_per_step=ms_per_step, nstep=nstep, naccpt=naccpt, ncalls=ncalls,
-               failures=int(nall - nok), failed_members_rank0=[int(i) * world + rank for i in failed], clocks=clocks,
+               failures=int(nall - nok), failed_members_rank0=[int(ens._plan.indices(rank)[int(i)]) for i in failed], clocks=clocks,
                launches=int(launches), wall=wall, per_rank=per_rank, n=n, n_total=n_total,
-               kernel_ms_rank0=ms_kernel / steps)
+               kernel_ms_rank0=ms_kernel / steps,
+               shards=("round-robin" if not rebalance else
+                       f"speed-weighted (rapt_b200/dist.py:ShardPlan, {int(args.rebalance)} calibration rounds before the warm-up)"))
+    if per_rank is not None:
+        per_rank["shard_sizes"] = ens._plan.sizes()
+        if shard_history:
+            per_rank["shard_calibration"] = shard_history
 
     # ---- end to end through the host-buffer C ABI (pinned inputs, H2D + D2H inside the timed region)
     if want_e2e:
@@ -410,6 +449,7 @@ def time_workload(args, workload, n_per_gpu, world, rank, dev, steps, warmup, wa
         rec["e2e"] = {"value": float(st2[0]) * steps / float(tt[0]), "unit": "particle-steps/s",
                       "h2d_bytes_per_step": n * n_in * 8,
                       "d2h_bytes_per_step": n * (ncol * 8 + (2 if workload == "particle" else 1) * 8 + 4 * 4 + 3 * 4)}
+    cur.clear()
     del ens, pristine, flush
     torch.cuda.empty_cache()
     return rec
@@ -457,6 +497,8 @@ def main():
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU,
                     help="tracers per GPU (--scaling weak) or in total (--scaling strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--rebalance", type=int, default=0,
+                    help="N > 1: calibration rounds of speed-weighted shards before the warm-up (0: round-robin shards)")
     ap.add_argument("--delta", type=float, default=DELTA)
     ap.add_argument("--cpu-sample", type=int, default=8192, help="tracers of the C oracle-port sample")
     ap.add_argument("--ref-sample", type=int, default=0, help="tracers per step of the Python-reference sample (0: sized for ~150 s)")
@@ -538,7 +580,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD_NAME[args.workload], "particles_per_gpu": n, "particles_total": r["n_total"],
-                           "delta_s": args.delta, "arith": args.arith,
+                           "delta_s": args.delta, "arith": args.arith, "shards": r["shards"],
                            "l2": "512 MiB flush write between steps (inputs < L2)",
                            "particle_steps_per_bench_step": r["nstep"], "accepted": r["naccpt"], "output_rows": r["ncalls"],
                            # members whose row loop ended on scipy's nsteps = 500 limit, as the reference's does for the

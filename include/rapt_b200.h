@@ -299,9 +299,13 @@ int rapt_b200_final_diagnostics_dev(int kind, int64_t n, int ncol, const double 
                                     const int32_t *status, double *packed, int nbins, double lo, double hi,
                                     int64_t *hist, double *stats, void *stream);
 
-/* The all-gathered rows, gathered[world][n_max][ncol] with rank r holding members r, r + world, ... (round-robin shards,
- * rapt_b200/dist.py), rearranged into global member order out[n_total][ncol].  DEVICE pointers. */
-int rapt_b200_unshard_dev(int world, int64_t n_max, int ncol, int64_t n_total, const double *gathered, double *out, void *stream);
+/* The all-gathered rows, gathered[world][n_max][ncol], rearranged into global member order out[n_total][ncol].  Shards are
+ * periodic: of every `period` consecutive members those at positions [offsets[r], offsets[r+1]) belong to rank r, in order
+ * (offsets: HOST array of world + 1 ints from 0 to period).  offsets == NULL: round-robin (rank r holds members r,
+ * r + world, ...).  rapt_b200/dist.py:ShardPlan builds the table; unequal runs give faster GPUs more tracers.
+ * gathered / out: DEVICE pointers. */
+int rapt_b200_unshard_dev(int world, int period, const int32_t *offsets, int64_t n_max, int ncol, int64_t n_total,
+                          const double *gathered, double *out, void *stream);
 
 /* kernel launches performed by this library since load (for bench.py's gpu_launches) */
 int64_t rapt_b200_launch_count(void);

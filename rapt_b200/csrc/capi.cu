@@ -418,15 +418,22 @@ __global__ void __launch_bounds__(256) k_final_diagnostics(int kind, long long n
         if (sh_hist[b]) atomicAdd(&hist[b], (unsigned long long)sh_hist[b]);
 }
 
-// all-gathered rows [world][n_max][ncol] (rank r holds members r, r + world, ...) -> member order [n_total][ncol]:
-// coalesced writes, reads from `world` streams that advance together
-__global__ void __launch_bounds__(256) k_unshard(int world, long long n_max, int ncol, long long n_total,
+// all-gathered rows [world][n_max][ncol] -> member order [n_total][ncol].  Shards are periodic: of every `period` consecutive
+// members, those at positions [off[r], off[r+1]) belong to rank r (round-robin is period = world, one position each;
+// speed-weighted shards use a longer period with unequal runs: rapt_b200/dist.py:ShardPlan); the last, partial period
+// (block index `full`) is cut at off2 (the same proportions scaled to its length).  Coalesced writes.
+struct ShardTable { int period, world; long long full; int off[65], off2[65]; };
+__global__ void __launch_bounds__(256) k_unshard(ShardTable tb, long long n_max, int ncol, long long n_total,
                                                 const double *__restrict__ buf, double *__restrict__ out)
 {
     const long long total = n_total * ncol;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long m = e / ncol; const int c = (int)(e - m * ncol);
-        const long long i = m / world; const int r = (int)(m - i * world);
+        const long long blk = m / tb.period; const int j = (int)(m - blk * tb.period);
+        const int *o = (blk == tb.full) ? tb.off2 : tb.off;
+        int r = 0;
+        while (r + 1 < tb.world && j >= o[r + 1]) r++;
+        const long long i = blk * (tb.off[r + 1] - tb.off[r]) + (j - o[r]);
         out[e] = buf[((long long)r * n_max + i) * ncol + c];
     }
 }
@@ -1337,16 +1344,35 @@ int rapt_b200_adaptive_advance(const rapt_field_t *f, const rapt_params_t *p, in
     return RAPT_OK;
 }
 
-int rapt_b200_unshard_dev(int world, int64_t n_max, int ncol, int64_t n_total, const double *gathered, double *out, void *stream)
+int rapt_b200_unshard_dev(int world, int period, const int32_t *offsets, int64_t n_max, int ncol, int64_t n_total,
+                          const double *gathered, double *out, void *stream)
 {
     if (int rc = ensure_init()) return rc;
-    if (world < 1 || n_max < 0 || ncol < 1 || n_total < 0 || n_total > (int64_t)world * n_max || !gathered || !out)
-        return fail(RAPT_E_ARG, "unshard: bad argument");
+    if (world < 1 || world > 64 || n_max < 0 || ncol < 1 || n_total < 0 || n_total > (int64_t)world * n_max || !gathered || !out)
+        return fail(RAPT_E_ARG, "unshard: bad argument (1 <= world <= 64)");
+    ShardTable tb;
+    memset(&tb, 0, sizeof tb);
+    tb.world = world;
+    if (offsets) {
+        if (period < world || offsets[0] != 0 || offsets[world] != period) return fail(RAPT_E_ARG, "unshard: offsets must run from 0 to period");
+        for (int r = 0; r <= world; r++) {
+            if (r && offsets[r] < offsets[r - 1]) return fail(RAPT_E_ARG, "unshard: offsets must ascend");
+            tb.off[r] = offsets[r];
+        }
+        tb.period = period;
+    } else {                                         // round-robin
+        tb.period = world;
+        for (int r = 0; r <= world; r++) tb.off[r] = r;
+    }
+    tb.full = n_total / tb.period;
+    const long long rem = n_total - tb.full * tb.period;
+    for (int r = 0; r <= world; r++)                 // ShardPlan._tail: proportional cut; round-robin: the first rem ranks
+        tb.off2[r] = offsets ? (int)(((long long)tb.off[r] * rem) / tb.period) : (int)std::min<long long>(r, rem);
     if (n_total == 0) return RAPT_OK;
     if (int rc = check_on_bound_device(gathered, "unshard_dev")) return rc;
     const long long total = n_total * ncol;
     const int grid = (int)std::min<long long>((long long)g_sms * 16, (total + 255) / 256);
-    k_unshard<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(world, n_max, ncol, n_total, gathered, out);
+    k_unshard<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(tb, n_max, ncol, n_total, gathered, out);
     CK(cudaGetLastError());
     g_launches++;
     return RAPT_OK;

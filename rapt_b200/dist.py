@@ -33,15 +33,73 @@ def _on_device_backend(group=None):
     return "nccl" in str(dist.get_backend(group))
 
 
-def gather_rows(buf, rank, n_total, group=None, out=None):
+class ShardPlan:
+    """Which member lives on which rank.  Shards are periodic: of every `period` consecutive members those at positions
+    [off[r], off[r+1]) belong to rank r, in order.  weights None: period = world, one position each = round-robin (every
+    GPU sees the same mix of orbit lengths).  With weights (one positive number per rank, e.g. the measured tracers per
+    second of every GPU: `ens.shard(weights=...)`, `ens.reshard(...)`) the period is 4096 and the runs are proportional
+    to the weights, so a slower GPU gets fewer tracers of the same mix; a small change of the weights moves only the
+    members at the ends of the runs.  The last, partial period is cut in the same proportions."""
+
+    PERIOD = 4096
+
+    def __init__(self, n_total, world, weights=None):
+        self.n_total, self.world = int(n_total), int(world)
+        if weights is None or world == 1:
+            self.period = self.world
+            self.off = np.arange(self.world + 1, dtype=np.int32)
+            self.uniform = True
+        else:
+            w = np.asarray(weights, dtype=np.float64).ravel()
+            if len(w) != world or not np.all(np.isfinite(w)) or not np.all(w > 0):
+                raise ValueError("ShardPlan: one positive weight per rank")
+            self.period = max(min(self.PERIOD, self.n_total), self.world)
+            exact = w / w.sum() * self.period
+            cnt = np.maximum(np.floor(exact).astype(np.int64), 1)
+            for k in np.argsort(-(exact - np.floor(exact)), kind="stable")[:max(self.period - int(cnt.sum()), 0)]:
+                cnt[k] += 1
+            while cnt.sum() > self.period:               # only when a floor was lifted to 1
+                cnt[np.argmax(cnt)] -= 1
+            self.off = np.concatenate(([0], np.cumsum(cnt))).astype(np.int32)
+            self.uniform = False
+
+    def _tail(self):
+        """Cut of the last, partial period (n_total % period members): the same proportions, offsets scaled down --
+        floor(off * rem / period), the arithmetic rapt_b200_unshard_dev repeats."""
+        full, rem = divmod(self.n_total, self.period)
+        return full, (self.off.astype(np.int64) * rem) // self.period
+
+    def sizes(self):
+        if self.uniform:
+            return [len(range(r, self.n_total, self.world)) for r in range(self.world)]
+        full, off2 = self._tail()
+        return [int(full * (self.off[r + 1] - self.off[r]) + off2[r + 1] - off2[r]) for r in range(self.world)]
+
+    def indices(self, rank):
+        """Global member indices of `rank`'s shard, in shard order."""
+        if self.uniform:
+            return np.arange(rank, self.n_total, self.world, dtype=np.int64)
+        full, off2 = self._tail()
+        base = np.arange(self.off[rank], self.off[rank + 1], dtype=np.int64)
+        idx = (np.arange(full, dtype=np.int64)[:, None] * self.period + base[None, :]).ravel()
+        return np.concatenate([idx, full * self.period + np.arange(off2[rank], off2[rank + 1], dtype=np.int64)])
+
+    def table(self):
+        """(period, offsets) for rapt_b200_unshard_dev; offsets None = round-robin."""
+        return (self.period, None) if self.uniform else (self.period, self.off)
+
+
+def gather_rows(buf, rank, n_total, group=None, out=None, plan=None):
     """All-gather of per-rank final-state rows.  buf: (world, n_max, k) tensor whose slot [rank] already holds this
     rank's rows (rapt_b200_final_diagnostics_dev packs them there, so the send buffer IS the receive slot: NCCL's
     in-place all-gather, no staging copy).  Returns the (n_total, k) tensor in global member order on every rank
-    (one un-interleaving kernel, rapt_b200_unshard_dev; `out` is reused when given).
+    (one un-interleaving kernel, rapt_b200_unshard_dev; `out` is reused when given).  `plan`: the ShardPlan the shards
+    were cut with (default: round-robin).
     With a host backend (gloo: the CPU tests and single-GPU boxes) the slot is staged through host memory."""
     import torch
     import torch.distributed as dist
     world = buf.shape[0]
+    plan = plan or ShardPlan(n_total, world)
     if world > 1:
         if _on_device_backend(group) or not buf.is_cuda:
             dist.all_gather_into_tensor(buf.view(-1), buf[rank].reshape(-1), group=group)
@@ -53,11 +111,12 @@ def gather_rows(buf, rank, n_total, group=None, out=None):
         out = torch.empty((n_total, buf.shape[2]), dtype=buf.dtype, device=buf.device)
     if buf.is_cuda:
         from . import engine
-        engine.unshard_dev(buf, out, n_total)
+        period, off = plan.table()
+        engine.unshard_dev(buf, out, n_total, period, off)
     else:                                              # host tensors (gloo tests of the plumbing)
-        sizes = shard_sizes(n_total, world)
+        sizes = plan.sizes()
         for r in range(world):
-            out[r::world] = buf[r, :sizes[r]]
+            out[torch.as_tensor(plan.indices(r))] = buf[r, :sizes[r]]
     return out
 
 

@@ -436,11 +436,13 @@ def final_diagnostics_dev(kind, cols, mass, status, packed, nbins, lo, hi, hist,
         C.c_int(nbins), C.c_double(lo), C.c_double(hi), ptr(hist), ptr(stats), _stream_ptr()))
 
 
-def unshard_dev(gathered, out, n_total):
-    """gathered (world, n_max, ncol) round-robin shards -> out (n_total, ncol) in member order (rapt_b200_unshard_dev)."""
+def unshard_dev(gathered, out, n_total, period=0, offsets=None):
+    """gathered (world, n_max, ncol) periodic shards -> out (n_total, ncol) in member order (rapt_b200_unshard_dev).
+    offsets None: round-robin; else the ShardPlan's table (world + 1 ints from 0 to period)."""
     world, n_max, ncol = gathered.shape
-    check(_lib.load().rapt_b200_unshard_dev(C.c_int(world), C.c_int64(n_max), C.c_int(ncol), C.c_int64(n_total), ptr(gathered),
-                                            ptr(out), _stream_ptr()))
+    off = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.int32)
+    check(_lib.load().rapt_b200_unshard_dev(C.c_int(world), C.c_int(int(period)), ptr(off), C.c_int64(n_max), C.c_int(ncol),
+                                            C.c_int64(n_total), ptr(gathered), ptr(out), _stream_ptr()))
 
 
 def alloc_outputs(n, device):

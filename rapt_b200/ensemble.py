@@ -24,25 +24,44 @@ class _Resident:
 
     Multi-GPU: one process per GPU under torchrun.  Every rank builds the SAME ensemble and
     calls `.shard()`: rank r keeps members r, r+W, r+2W, ... (round-robin, so every GPU sees the same mix of orbit
-    lengths) on cuda:LOCAL_RANK.  `advance()` then runs the same kernels on the shard with no data-path collective.
+    lengths; with `weights`, runs of a 4096-member period proportional to each GPU's speed: dist.ShardPlan) on
+    cuda:LOCAL_RANK.  `advance()` then runs the same kernels on the shard with no data-path collective.
     `.gather()` packs the final states and bins the diagnostics in one kernel pass, all-gathers the rows (NCCL over
     NVLink, in place into this rank's slot) and sum-all-reduces the fixed-size histogram / invariant sums."""
 
     _MEMBER_ARRAYS = ()          # per-member host arrays a shard slices
     _DIAG = "ke"
 
-    def shard(self, group=None, device=None):
+    def shard(self, group=None, device=None, weights=None, keep_full=False):
+        """Keep this rank's members and move them to its GPU.  weights: one positive number per rank (relative speed of
+        its GPU); None = round-robin.  keep_full=True keeps the whole ensemble's host arrays so that `reshard()` can cut
+        the shards again (e.g. after measuring every rank's kernel time: bench.py --rebalance)."""
         from . import dist as rd
         world, rank = rd.world_rank(group)
-        self._group, self.world, self.rank, self.n_total = group, world, rank, self.n
+        full = getattr(self, "_full", None)
+        if full is None:
+            full = {name: getattr(self, name) for name in self._MEMBER_ARRAYS if getattr(self, name, None) is not None}
+            self.n_total = self.n
+        self._group, self.world, self.rank = group, world, rank
+        self._plan = rd.ShardPlan(self.n_total, world, weights)
         if world > 1:
-            sl = rd.shard_slice(self.n, world, rank)
-            for name in self._MEMBER_ARRAYS:
-                a = getattr(self, name, None)
-                if a is not None:
-                    setattr(self, name, np.ascontiguousarray(a[sl]))
-            self.n = len(self.state)
+            idx = self._plan.indices(rank)
+            sl = rd.shard_slice(self.n_total, world, rank) if self._plan.uniform else idx
+            for name, a in full.items():
+                setattr(self, name, np.ascontiguousarray(a[sl]))
+            self.n = len(idx)
+        self._full = full if (keep_full and world > 1) else None
         return self.cuda(device or rd.local_device())
+
+    def reshard(self, weights):
+        """Cut the shards again with new weights from the ensemble as it was when `.shard(keep_full=True)` was called
+        (the device-resident results of the old shards are dropped)."""
+        if getattr(self, "_full", None) is None:
+            if getattr(self, "world", 1) == 1:
+                return self
+            raise RuntimeError("reshard() needs .shard(keep_full=True)")
+        self._dev = None
+        return self.shard(self._group, None, weights, keep_full=True)
 
     def load_state(self, cols):
         """Overwrite the device-resident state columns with the given CUDA tensors (e.g. to restart from the same
@@ -119,7 +138,8 @@ class _Resident:
         hi = (8.0 if kind == "ke" else 16.0) if hi is None else hi
         world, rank = getattr(self, "world", 1), getattr(self, "rank", 0)
         n_total = getattr(self, "n_total", self.n)
-        n_max = max(rd.shard_sizes(n_total, world))
+        plan = getattr(self, "_plan", None) or rd.ShardPlan(n_total, world)
+        n_max = max(plan.sizes())
         ncol = len(d.cols)
         if d.gather_buf is None or tuple(d.gather_buf.shape) != (world, n_max, ncol):
             d.gather_buf = torch.zeros((world, n_max, ncol), dtype=torch.float64, device=d.device)
@@ -133,7 +153,7 @@ class _Resident:
         engine.final_diagnostics_dev(kind, d.cols, d.extras["mass"], d.out["status"], d.gather_buf[rank], nbins, lo, hi,
                                      d.hist, d.stats)
         if ev: ev[1].record()
-        final = rd.gather_rows(d.gather_buf, rank, n_total, getattr(self, "_group", None), out=d.final)
+        final = rd.gather_rows(d.gather_buf, rank, n_total, getattr(self, "_group", None), out=d.final, plan=plan)
         if ev: ev[2].record()
         rd.reduce_diagnostics(d.hist, d.stats, getattr(self, "_group", None))
         if ev: ev[3].record()

@@ -40,6 +40,15 @@ def _worker(rank, world, port, n, out_dir):
     rd.reduce_diagnostics(hist, sums)
     assert torch.equal(full2, full) and torch.equal(hist.to(torch.float64), h) and int(sums[0]) == n
     assert rd.world_rank() == (world, rank)
+    # speed-weighted shards (dist.ShardPlan): another cut of the same ensemble, same gathered result
+    plan = rd.ShardPlan(n, world, [1.0, 0.6])
+    idx = plan.indices(rank)
+    ow = O.particle_advance(O.make_field("EarthDipole"), O.make_params(cyclotronresolution=20), st[idx], ic["mass"][idx],
+                            ic["charge"][idx], 0.05, store_every=0)
+    bufw = torch.zeros((world, max(plan.sizes()), 8), dtype=torch.float64)
+    bufw[rank, :len(idx)] = torch.tensor(np.column_stack([ow["state"], ow["counters"][:, 1].astype(np.float64)]))
+    assert len(idx) == plan.sizes()[rank] and plan.sizes()[0] > plan.sizes()[1]
+    assert torch.equal(rd.gather_rows(bufw, rank, n, plan=plan), full)
     if rank == 0:
         np.savez(os.path.join(out_dir, "gathered.npz"), full=full.numpy(), hist=h.numpy(),
                  stats=np.array([stats["count"], stats["mean"], stats["min"], stats["max"]]))
@@ -81,3 +90,34 @@ def test_shard_helpers():
             parts.append(pad[:, None])
         if n:
             assert np.array_equal(rd.unshard(parts, n, w)[:, 0], idx)
+
+
+def test_shard_plan():
+    """ShardPlan: every member on exactly one rank, sizes() = len(indices()), runs proportional to the weights, and the
+    index arithmetic of the device un-interleave kernel (capi.cu:k_unshard) restated in numpy inverts it."""
+    from rapt_b200 import dist as rd
+    for n, w, weights in ((10, 4, None), (101, 2, [1, 1]), (101, 2, [1.0, 0.6]), (5000, 3, [1, 2, 3]), (20000, 8, 1 + 0.03 * np.arange(8)),
+                          (4096, 8, np.ones(8)), (3, 4, [1, 1, 1, 1]), (0, 2, [1, 2]), (100000, 64, np.linspace(1, 2, 64))):
+        plan = rd.ShardPlan(n, w, weights)
+        sizes = plan.sizes()
+        parts = [plan.indices(r) for r in range(w)]
+        assert [len(p) for p in parts] == sizes and sum(sizes) == n
+        assert np.array_equal(np.sort(np.concatenate(parts)) if n else np.zeros(0), np.arange(n))
+        assert plan.off[0] == 0 and plan.off[-1] == plan.period and np.all(np.diff(plan.off) >= (0 if n < w else 1))
+        if weights is not None and n >= 4096:
+            wn = np.asarray(weights, float) / np.sum(weights)
+            assert np.max(np.abs(np.array(sizes) / n - wn)) < 2.0 / 4096 + 2.0 / n
+        # k_unshard: member m -> (rank r, row i of r's shard)
+        m = np.arange(n)
+        full, rem = divmod(n, plan.period)
+        off2 = (plan.off.astype(np.int64) * rem) // plan.period if weights is not None else np.minimum(plan.off, rem)
+        blk, j = m // plan.period, m % plan.period
+        tail = blk == full
+        r = np.where(tail, np.searchsorted(off2[1:], j, side="right"), np.searchsorted(plan.off[1:], j, side="right"))
+        i = np.where(tail, full * (plan.off[r + 1] - plan.off[r]) + (j - off2[r]), blk * (plan.off[r + 1] - plan.off[r]) + (j - plan.off[r]))
+        for rr in range(w):
+            assert np.array_equal(parts[rr][i[r == rr]], m[r == rr])
+    with pytest.raises(ValueError):
+        rd.ShardPlan(10, 2, [1, 0])
+    with pytest.raises(ValueError):
+        rd.ShardPlan(10, 2, [1, 2, 3])

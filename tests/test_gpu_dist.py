@@ -45,6 +45,14 @@ def _worker(rank, world, port, n, out_dir, two_gpus):
         res[which + "_final"] = g["final"].cpu().numpy(); res[which + "_hist"] = g["hist"].cpu().numpy()
         res[which + "_stats"] = np.array([g["stats"]["ok"], g["stats"]["mean"], g["stats"]["var"], g["stats"]["outside"]])
         res[which + "_nlocal"] = np.array([ens.n, ens.n_total]); res[which + f"_steps{rank}"] = ens.counters[:, 1].sum()
+        # speed-weighted shards (dist.ShardPlan), cut twice: shard(weights) then reshard(other weights)
+        ens, delta = _build(R, which, n)
+        ens.shard(weights=[1.0, 0.7], keep_full=True)
+        nloc = ens.n
+        ens.reshard([0.9, 1.0]).advance(delta)
+        g = ens.gather(nbins=32)
+        res[which + "_final_w"] = g["final"].cpu().numpy(); res[which + "_hist_w"] = g["hist"].cpu().numpy()
+        res[which + "_nlocal_w"] = np.array([nloc, ens.n])
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **res)
     dist.barrier()
     dist.destroy_process_group()
@@ -78,6 +86,11 @@ def test_two_rank_sharded_run_equals_one_rank_run(tmp_path):
                 assert int(r[which + "_stats"][0]) == g["stats"]["ok"] == n
                 assert abs(r[which + "_stats"][1] - g["stats"]["mean"]) <= 1e-12 * abs(g["stats"]["mean"])
             assert int(r0[which + "_steps0"]) + int(r1[which + "_steps1"]) == int(ens.counters[:, 1].sum())
+            for r in (r0, r1):
+                assert np.array_equal(r[which + "_final_w"], one), f"{which}: weighted shards, gathered result != 1-rank run"
+                assert np.array_equal(r[which + "_hist_w"], g["hist"].cpu().numpy())
+            assert r0[which + "_nlocal_w"][0] > r1[which + "_nlocal_w"][0] and r0[which + "_nlocal_w"][1] < r1[which + "_nlocal_w"][1]
+            assert r0[which + "_nlocal_w"].sum() + r1[which + "_nlocal_w"].sum() == 2 * n
             # the histogram kernel against numpy on the same final states
             if which == "particle":
                 m = ens.mass; p2 = np.sum(one[:, 4:7] ** 2, axis=1)
@@ -89,3 +102,24 @@ def test_two_rank_sharded_run_equals_one_rank_run(tmp_path):
             assert np.array_equal(ref, g["hist"].cpu().numpy()) and g["stats"]["outside"] == int(((q < g["edges"][0]) | (q > g["edges"][-1])).sum())
     finally:
         R.params.clear(); R.params.update(old)
+
+
+def test_unshard_kernel_against_shard_plan():
+    """rapt_b200_unshard_dev on its own: for round-robin and weighted plans (2 ... 64 ranks, ragged tails) the kernel puts
+    every rank's rows back where ShardPlan.indices() took them from."""
+    import torch
+    from rapt_b200 import engine, _lib, dist as rd
+    _lib.init(0)
+    rng = np.random.default_rng(5)
+    for n, w, weights in ((4097, 2, None), (4097, 2, [1.0, 0.7]), (100001, 8, 1 + 0.03 * np.arange(8)), (9000, 3, [1, 2, 3]),
+                          (12345, 64, np.linspace(1, 2, 64)), (5, 8, np.ones(8)), (8192, 8, np.ones(8))):
+        plan = rd.ShardPlan(n, w, weights)
+        want = rng.standard_normal((n, 7))
+        buf = np.zeros((w, max(max(plan.sizes()), 1), 7))
+        for r in range(w):
+            idx = plan.indices(r)
+            buf[r, :len(idx)] = want[idx]
+        out = torch.empty((n, 7), dtype=torch.float64, device="cuda:0")
+        period, off = plan.table()
+        engine.unshard_dev(torch.as_tensor(buf, device="cuda:0"), out, n, period, off)
+        assert np.array_equal(out.cpu().numpy(), want), (n, w)

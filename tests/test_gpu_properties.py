@@ -159,3 +159,38 @@ def test_abi_argument_checks_and_degenerate_inputs(eng):
     # guiding centres with a non-positive output step terminate too
     g = eng.gc_advance(fields.DoubleDipole(), np.array([[0.0, 5e7, 1e6, 1e5, 1e-23]]), 1e-7, 1e8, 9.1e-31, -1.6e-19, 0.0, 1.0, store_every=0)
     assert g["status"][0] < 0
+
+
+def test_launch_shapes_agree(eng):
+    """A launch that fills the GPU runs one 512-thread block per SM, a smaller one 128-thread blocks spread over the SMs
+    (kernels_tu.cu:block_threads) -- two launches of the same kernel.  131,072 tracers in one call must equal the same
+    tracers in eight calls of 16,384, bit for bit: Particle (Nystrom kernel) and GuidingCenter, with stored rows."""
+    from rapt_b200 import synth
+    n, chunk = 131072, 16384
+    st, ic = config2_state(eng, n)
+    f = H.gpu_field("EarthDipole", ())
+    kw = dict(store_every=5, max_rows=8, cyclotronresolution=20)
+    big = eng.particle_advance(f, st, ic["mass"], ic["charge"], 0.05, **kw)
+    for k in range(0, n, chunk):
+        sl = slice(k, k + chunk)
+        small = eng.particle_advance(f, st[sl], ic["mass"][sl], ic["charge"][sl], 0.05, **kw)
+        for key in ("state", "counters", "status", "nrows", "nstored", "tcur", "dt"):
+            assert np.array_equal(big[key][sl], small[key]), key
+        m = int(small["nstored"].max())
+        valid = np.arange(m)[None, :] < small["nstored"][:, None]           # rows past a tracer's nstored are not written
+        assert m >= 2 and np.array_equal(big["rows"][sl, :m][valid], small["rows"][:, :m][valid])
+    assert big["counters"][:, 1].sum() > 5 * n
+    ic3 = synth.config3_electrons(n)
+    f3 = H.gpu_field("DoubleDipole", ())
+    pos = np.column_stack([ic3["x"], ic3["y"], ic3["z"]])
+    ppar, mu = eng.gc_construct(f3, ic3["t0"], pos, ic3["v"], ic3["pa"], ic3["mass"])
+    st3 = np.column_stack([ic3["t0"], pos, ppar])
+    big = eng.gc_advance(f3, st3, mu, ic3["v"], ic3["mass"], ic3["charge"], 0.1, 0.5, store_every=2, max_rows=4)
+    for k in range(0, n, 4 * chunk):
+        sl = slice(k, k + 4 * chunk)
+        small = eng.gc_advance(f3, st3[sl], mu[sl], ic3["v"][sl], ic3["mass"][sl], ic3["charge"][sl], 0.1, 0.5, store_every=2, max_rows=4)
+        for key in ("state", "counters", "status", "nrows", "nstored", "tcur"):
+            assert np.array_equal(big[key][sl], small[key]), key
+        m = int(small["nstored"].max())
+        valid = np.arange(m)[None, :] < small["nstored"][:, None]
+        assert m >= 2 and np.array_equal(big["rows"][sl, :m][valid], small["rows"][:, :m][valid])
