@@ -316,10 +316,13 @@ def time_workload(args, workload, n_per_gpu, world, rank, dev, steps, warmup, wa
     attach()
     shard_history = None
     if rebalance:
-        # Speed-weighted shards: the GPUs of one box run the same shard up to a few per cent apart (profiles/r2_multi_gpu.md)
-        # and a step ends with the slowest.  Before the warm-up: time the kernel on every rank, give every rank a share of
-        # each 4096-member period proportional to its measured tracers per second, and repeat once (the second cut moves
-        # only the ends of the runs).  Not part of the timed region; the shard sizes are reported in per_rank.
+        # Time-weighted shards: equal shards of the same random ensemble take up to 5 % different kernel times (the end of a
+        # launch hangs on the few longest orbits each shard happens to hold: the per-rank times repeat to 0.3 ms on another
+        # box, profiles/r2_multi_gpu.md) and a step ends with the slowest rank.  Before the warm-up: time the kernel on every
+        # rank, give every rank a share of each 4096-member period proportional to its measured tracers per second, and
+        # repeat once (the second cut moves only the ends of the runs).  What an application does that advances an
+        # ensemble in several calls: the first call's times set the shards of the next.  Not part of the timed region; the
+        # calibration steps and the shard sizes are reported in per_rank.
         shard_history = []
         weights = np.ones(world)
         for _ in range(int(args.rebalance)):
@@ -394,7 +397,7 @@ def time_workload(args, workload, n_per_gpu, world, rank, dev, steps, warmup, wa
                launches=int(launches), wall=wall, per_rank=per_rank, n=n, n_total=n_total,
                kernel_ms_rank0=ms_kernel / steps,
                shards=("round-robin" if not rebalance else
-                       f"speed-weighted (rapt_b200/dist.py:ShardPlan, {int(args.rebalance)} calibration rounds before the warm-up)"))
+                       f"time-weighted (rapt_b200/dist.py:ShardPlan; {int(args.rebalance)} calibration rounds of 2 steps each before the warm-up, outside the timed region)"))
     if per_rank is not None:
         per_rank["shard_sizes"] = ens._plan.sizes()
         if shard_history:
@@ -497,8 +500,8 @@ def main():
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU,
                     help="tracers per GPU (--scaling weak) or in total (--scaling strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--rebalance", type=int, default=0,
-                    help="N > 1: calibration rounds of speed-weighted shards before the warm-up (0: round-robin shards)")
+    ap.add_argument("--rebalance", type=int, default=2,
+                    help="N > 1: calibration rounds of time-weighted shards before the warm-up (0: round-robin shards)")
     ap.add_argument("--delta", type=float, default=DELTA)
     ap.add_argument("--cpu-sample", type=int, default=8192, help="tracers of the C oracle-port sample")
     ap.add_argument("--ref-sample", type=int, default=0, help="tracers per step of the Python-reference sample (0: sized for ~150 s)")
@@ -571,15 +574,15 @@ def main():
                           want_e2e=not args.no_e2e)
         if rank == 0:
             flops = (gc_flops(args.workload, r["nstep"], r["ncalls"]) if is_gc
-                     else algorithmic_flops(r["nstep"], r["naccpt"], r["ncalls"])) / world
-            n = r["n"]
+                     else algorithmic_flops(r["nstep"], r["naccpt"], r["ncalls"])) * (r["n"] / r["n_total"])
+            n = r["n"]                    # rank 0's shard (its kernel time and its share of the flops make the roofline)
             io_bytes = n * ((10 * 8 + 5 * 8 + 8 + 7 * 4) if is_gc else (9 * 8 + 7 * 8 + 2 * 8 + 7 * 4))
             # the roofline is the KERNEL's: rank 0's kernel time per step, its share of the flops
             res = {
                 "metric": "particle-steps/s", "value": r["value"], "unit": "particle-steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD_NAME[args.workload], "particles_per_gpu": n, "particles_total": r["n_total"],
+                "config": {"workload": WORKLOAD_NAME[args.workload], "particles_per_gpu": r["n_total"] // world, "particles_total": r["n_total"],
                            "delta_s": args.delta, "arith": args.arith, "shards": r["shards"],
                            "l2": "512 MiB flush write between steps (inputs < L2)",
                            "particle_steps_per_bench_step": r["nstep"], "accepted": r["naccpt"], "output_rows": r["ncalls"],
@@ -591,8 +594,8 @@ def main():
                 "clocks": r["clocks"],
                 "gpu_launches": r["launches"],
                 "wall_s_timed_region": r["wall"],
-                "roofline": roofline(flops, r["kernel_ms_rank0"], r["nstep"] / world,
-                                     measured_traffic(args.workload, n, args.delta), io_bytes),
+                "roofline": roofline(flops, r["kernel_ms_rank0"], r["nstep"] * (r["n"] / r["n_total"]),
+                                     measured_traffic(args.workload, r["n_total"] // world, args.delta), io_bytes),
             }
             if r["per_rank"]:
                 res["per_rank"] = r["per_rank"]
