@@ -40,6 +40,7 @@ sys.path.insert(0, ROOT)
 N_PER_GPU = 1 << 20
 DELTA = 10.0
 PARAMS = dict(cyclotronresolution=20)
+WORK_ORDER = {"value": 1}          # --work-order previous: 2
 F_RHS = 38            # Lorentz 18 + EarthDipole 20 flop (E == 0 compiled out)
 F_STAGE = 6 * 158 + 20
 GC_DT = {"gc": 0.1, "belt": 0.05}          # params["GCtimestep"] of configs 3 and 5
@@ -154,7 +155,7 @@ def build_ensemble(workload, n_total, world, rank, weights=None, keep_full=False
 
 def run_advance(ens, workload, delta, arith):
     if workload == "particle":
-        ens.advance(delta, arith=arith, **PARAMS)
+        ens.advance(delta, arith=arith, sort_by_work=WORK_ORDER["value"], **PARAMS)
     else:
         ens.advance(delta, dt=GC_DT[workload], arith=arith)
 
@@ -502,6 +503,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--rebalance", type=int, default=2,
                     help="N > 1: calibration rounds of time-weighted shards before the warm-up (0: round-robin shards)")
+    ap.add_argument("--work-order", default="predicted", choices=["predicted", "previous"],
+                    help="particle workload: longest-first order from the initial state (predicted steps) or from the "
+                         "previous advance's step counts of the device-resident ensemble (sort_by_work = 2)")
     ap.add_argument("--delta", type=float, default=DELTA)
     ap.add_argument("--cpu-sample", type=int, default=8192, help="tracers of the C oracle-port sample")
     ap.add_argument("--ref-sample", type=int, default=0, help="tracers per step of the Python-reference sample (0: sized for ~150 s)")
@@ -510,6 +514,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the gc / belt / adaptive sub-records (extra.workloads)")
     args = ap.parse_args()
+    WORK_ORDER["value"] = 2 if args.work_order == "previous" else 1
     if args.impl == "reference":
         return run_reference(args)
 
@@ -583,7 +588,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD_NAME[args.workload], "particles_per_gpu": r["n_total"] // world, "particles_total": r["n_total"],
-                           "delta_s": args.delta, "arith": args.arith, "shards": r["shards"],
+                           "delta_s": args.delta, "arith": args.arith, "shards": r["shards"], "work_order": args.work_order,
                            "l2": "512 MiB flush write between steps (inputs < L2)",
                            "particle_steps_per_bench_step": r["nstep"], "accepted": r["naccpt"], "output_rows": r["ncalls"],
                            # members whose row loop ended on scipy's nsteps = 500 limit, as the reference's does for the
@@ -612,6 +617,19 @@ def main():
                             "gpu_launches": x["launches"], "solver_failures": x["failures"],
                             "roofline": roofline(fl, x["kernel_ms_rank0"], x["nstep"],
                                                  measured_traffic(w, x["n"], args.delta))}
+            if args.work_order == "predicted":
+                # the same ensemble in steady state of a multi-call run: every advance ordered by the previous advance's step
+                # counts (what ParticleEnsemble.advance does by default on device-resident state; the headline above is the
+                # cold call, ordered by the a-priori estimate)
+                WORK_ORDER["value"] = 2
+                x = time_workload(args, "particle", N_PER_GPU, 1, 0, dev, 3, 3, want_e2e=False)
+                WORK_ORDER["value"] = 1
+                fl = algorithmic_flops(x["nstep"], x["naccpt"], x["ncalls"])
+                extra["particle_work_order_previous"] = {
+                    "workload": WORKLOAD_NAME["particle"] + "; longest-first order from the previous advance's step counts "
+                                "(sort_by_work = 2), not from the a-priori estimate", "particles": x["n"], "delta_s": args.delta,
+                    "value": x["value"], "unit": "particle-steps/s", "ms_per_step": x["ms_per_step"], "steps": 3, "warmup": 3,
+                    "gpu_launches": x["launches"], "roofline": roofline(fl, x["kernel_ms_rank0"], x["nstep"])}
             a = time_adaptive(args, N_PER_GPU, dev, 1, 1)
             ms = a["st"]["ms_epochs"]
             extra["adaptive"] = {"workload": WORKLOAD_NAME["adaptive"], "particles": a["n"], "value": a["nstep"] / (ms * 1e-3),

@@ -674,7 +674,9 @@ int rapt_b200_particle_advance(const rapt_field_t *f, const rapt_params_t *p, in
     CK(drows.alloc(rb));
     CK(dnrows.alloc(n * sizeof(int))); CK(dnst.alloc(n * sizeof(int))); CK(dcnt.alloc(n * 4 * sizeof(int)));
     CK(dst.alloc(n * sizeof(int))); CK(dtcur.alloc(nb)); CK(ddt.alloc(nb));
-    int rc = rapt_b200_particle_advance_dev(f, p, n, dt_.as<double>(), dx.as<double>(), dy.as<double>(), dz.as<double>(),
+    rapt_params_t ph = *p;
+    if (ph.sort_by_work > 1) ph.sort_by_work = 1;          // no history in freshly allocated output buffers
+    int rc = rapt_b200_particle_advance_dev(f, &ph, n, dt_.as<double>(), dx.as<double>(), dy.as<double>(), dz.as<double>(),
                                             dpx.as<double>(), dpy.as<double>(), dpz.as<double>(), dm.as<double>(),
                                             dq.as<double>(), delta, store_every, max_rows,
                                             want_rows ? drows.as<double>() : nullptr, dnrows.as<int>(), dnst.as<int>(),

@@ -139,6 +139,13 @@ __global__ void k_particle_dt(const rapt::AdvArgs a, double *key, int *idx)
     double pB = dot3(px, py, pz, bx, by, bz), p2 = dot3(px, py, pz, px, py, pz);
     double sa = sqrt(fmax(1.0 - pB * pB / (p2 * B2), 1e-4));
     key[i] = dt / delta * fmin(1.0, sa / 0.9);
+    // sort_by_work == 2 (device-resident ensembles advanced in several calls): `counters` still holds the previous call's
+    // (nfcn, nstep, naccpt, nrejct) of this tracer; its step count replaces the estimate (same unit: 1 / steps).  Zero =
+    // no history.  Scheduling only.
+    if (a.p.sort_by_work == 2 && a.counters && !a.append) {
+        const int prev = a.counters[4 * i + 1];
+        if (prev > 0) key[i] = 1.0 / (double)prev;
+    }
     idx[i] = (int)i;
 }
 #define RAPT_KIND_SWITCH(CALL)                         \

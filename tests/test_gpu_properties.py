@@ -194,3 +194,23 @@ def test_launch_shapes_agree(eng):
         m = int(small["nstored"].max())
         valid = np.arange(m)[None, :] < small["nstored"][:, None]
         assert m >= 2 and np.array_equal(big["rows"][sl, :m][valid], small["rows"][:, :m][valid])
+
+
+def test_work_order_from_previous_call(eng):
+    """sort_by_work = 2 (device-resident ensembles): the previous call's step counts order the next call.  Scheduling only:
+    two consecutive advances are bit-identical to the same two advances with the predicted order, counters included; the
+    first call (no history in the counters buffer) runs with the predicted order."""
+    import rapt_b200 as R
+    from rapt_b200 import synth
+    n = 65536
+    ic = synth.config2_protons(n)
+    pos = np.column_stack([ic["x"], ic["y"], ic["z"]]); vel = np.column_stack([ic["vx"], ic["vy"], ic["vz"]])
+    res = []
+    for order in (1, 2):
+        ens = R.ParticleEnsemble(pos, vel, 0.0, ic["mass"], ic["charge"], R.fields.EarthDipole()).cuda("cuda:0")
+        ens.advance(0.25, cyclotronresolution=20, sort_by_work=order).advance(0.25, cyclotronresolution=20, sort_by_work=order)
+        ens.pull()
+        res.append((ens.state.copy(), ens.counters.copy(), ens.last_counters.copy(), ens.status.copy()))
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+    assert np.all(res[0][3] == 1) and res[0][2][:, 1].min() > 0
