@@ -157,7 +157,7 @@ def run_advance(ens, workload, delta, arith):
     if workload == "particle":
         ens.advance(delta, arith=arith, sort_by_work=WORK_ORDER["value"], **PARAMS)
     else:
-        ens.advance(delta, dt=GC_DT[workload], arith=arith)
+        ens.advance(delta, dt=GC_DT[workload], arith=arith, sort_by_work=WORK_ORDER["value"])
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -630,6 +630,15 @@ def main():
                                 "(sort_by_work = 2), not from the a-priori estimate", "particles": x["n"], "delta_s": args.delta,
                     "value": x["value"], "unit": "particle-steps/s", "ms_per_step": x["ms_per_step"], "steps": 3, "warmup": 3,
                     "gpu_launches": x["launches"], "roofline": roofline(fl, x["kernel_ms_rank0"], x["nstep"])}
+                for w in ("gc", "belt"):                  # guiding centres: no a-priori key, the cold call is unordered
+                    WORK_ORDER["value"] = 2
+                    x = time_workload(args, w, N_PER_GPU, 1, 0, dev, 2, 3, want_e2e=False)
+                    WORK_ORDER["value"] = 1
+                    extra[w + "_work_order_previous"] = {
+                        "workload": WORKLOAD_NAME[w] + "; longest-first order from the previous advance's step counts",
+                        "particles": x["n"], "delta_s": args.delta, "value": x["value"], "unit": "particle-steps/s",
+                        "ms_per_step": x["ms_per_step"], "steps": 2, "warmup": 3, "gpu_launches": x["launches"],
+                        "roofline": roofline(gc_flops(w, x["nstep"], x["ncalls"]), x["kernel_ms_rank0"], x["nstep"])}
             a = time_adaptive(args, N_PER_GPU, dev, 1, 1)
             ms = a["st"]["ms_epochs"]
             extra["adaptive"] = {"workload": WORKLOAD_NAME["adaptive"], "particles": a["n"], "value": a["nstep"] / (ms * 1e-3),

@@ -310,9 +310,21 @@ int check_field(const rapt_field_t *f)
     return RAPT_OK;
 }
 
+// work-order key of a tracer that was advanced before: 1 / (steps of the previous call), from the counters buffer the
+// caller left in place (rapt_params_t.sort_by_work = 2).  No history (0 steps): key 1, i.e. after every tracer that has one.
+__global__ void __launch_bounds__(256) k_key_previous(long long n, const int *__restrict__ counters, double *key, int *idx)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int prev = counters[4 * i + 1];
+    key[i] = prev > 0 ? 1.0 / (double)prev : 1.0;
+    idx[i] = (int)i;
+}
+
 // Longest-first schedule: sort particle indices by dt/delta ascending (fewest-rows last), so the lanes
 // that run dry at the end of the kernel are finishing the SHORTEST particles (SURVEY.md hard part H4).
-int build_order(const rapt_field_t *f, rapt::AdvArgs &a, bool strict, cudaStream_t s)
+// previous_only: the key is the previous call's step count alone (guiding centres: there is no a-priori estimate).
+int build_order(const rapt_field_t *f, rapt::AdvArgs &a, bool strict, cudaStream_t s, bool previous_only = false)
 {
     const size_t n = (size_t)a.nwork;
     if (g_sort.n < n) {
@@ -324,7 +336,10 @@ int build_order(const rapt_field_t *f, rapt::AdvArgs &a, bool strict, cudaStream
         CK(cudaMalloc(&g_sort.idx_out, n * sizeof(int)));
         g_sort.n = n;
     }
-    if (int rc = launch_any(f, strict, UK_PARTICLE_DT, &a, (long long)n, 0, s, g_sort.key_in, g_sort.idx_in)) return rc;
+    if (previous_only) {
+        k_key_previous<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((long long)n, a.counters, g_sort.key_in, g_sort.idx_in);
+        CK(cudaGetLastError());
+    } else if (int rc = launch_any(f, strict, UK_PARTICLE_DT, &a, (long long)n, 0, s, g_sort.key_in, g_sort.idx_in)) return rc;
     g_launches++;
     size_t need = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, need, g_sort.key_in, g_sort.key_out, g_sort.idx_in, g_sort.idx_out, (int)n, 0, 64, s);
@@ -722,6 +737,10 @@ int rapt_b200_gc_advance_dev(const rapt_field_t *f, const rapt_params_t *p, int 
     a.nstored = nstored; a.nrows = nrows; a.counters = counters; a.status = status; a.tcur = tcur;
     const bool strict = p->arith == 1;
     const int grid = grid_for(n, FLAVOUR(strict, gc_blocks_per_sm));
+    // longest-first from the previous call's step counts (sort_by_work = 2; there is no a-priori key for guiding centres)
+    if (p->sort_by_work == 2 && n > (long long)grid * 128) {
+        if (int rc = build_order(f, a, strict, s, true)) return rc;
+    }
     if (int rc = launch_any(f, strict, UK_GC, &a, n, grid, s)) return rc;
     g_launches++;
     return RAPT_OK;
@@ -749,7 +768,9 @@ int rapt_b200_gc_advance(const rapt_field_t *f, const rapt_params_t *p, int eom,
     CK(drows.alloc(rb));
     CK(dnrows.alloc(n * sizeof(int))); CK(dnst.alloc(n * sizeof(int))); CK(dcnt.alloc(n * 4 * sizeof(int)));
     CK(dst.alloc(n * sizeof(int))); CK(dtcur.alloc(nb));
-    int rc = rapt_b200_gc_advance_dev(f, p, eom, n, dt_.as<double>(), dx.as<double>(), dy.as<double>(), dz.as<double>(),
+    rapt_params_t ph = *p;
+    if (ph.sort_by_work > 1) ph.sort_by_work = 1;          // no history in freshly allocated output buffers
+    int rc = rapt_b200_gc_advance_dev(f, &ph, eom, n, dt_.as<double>(), dx.as<double>(), dy.as<double>(), dz.as<double>(),
                                       dpp.as<double>(), dmu.as<double>(), dv.as<double>(), dm.as<double>(), dq.as<double>(),
                                       ddt.as<double>(), delta, store_every, max_rows,
                                       want_rows ? drows.as<double>() : nullptr, dnrows.as<int>(), dnst.as<int>(),

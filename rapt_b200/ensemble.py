@@ -333,6 +333,7 @@ class GuidingCenterEnsemble(_Resident):
                 d.extras["dt"].copy_(torch.as_tensor(dt), non_blocking=False)
                 d.dt_uniform = uniform
             rows = self._rows_buffer(store_every, max_rows)
+            over.setdefault("sort_by_work", 2)     # longest-first from the previous call's step counts (see ParticleEnsemble)
             engine.gc_advance_dev(self.field, d.cols, d.extras["mu"], d.extras["v"], d.extras["mass"], d.extras["charge"],
                                   d.extras["dt"], float(delta), d.out, eom=eom, store_every=store_every, max_rows=max_rows,
                                   rows=rows, check_adiabaticity=self.check_adiabaticity, **over)

@@ -214,3 +214,16 @@ def test_work_order_from_previous_call(eng):
     for a, b in zip(*res):
         assert np.array_equal(a, b)
     assert np.all(res[0][3] == 1) and res[0][2][:, 1].min() > 0
+    # guiding centres: no a-priori key; with history the queue is sorted, without it the tracers are taken in member order
+    ic = synth.config3_electrons(n)
+    pos = np.column_stack([ic["x"], ic["y"], ic["z"]])
+    res = []
+    for order in (1, 2):
+        ens = R.GuidingCenterEnsemble(pos, ic["v"], pa=ic["pa"], mass=ic["mass"], charge=ic["charge"],
+                                      field=R.fields.DoubleDipole()).cuda("cuda:0")
+        ens.advance(0.5, dt=0.1, sort_by_work=order).advance(0.5, dt=0.1, sort_by_work=order)
+        ens.pull()
+        res.append((ens.state.copy(), ens.counters.copy(), ens.last_counters.copy(), ens.status.copy()))
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+    assert res[0][2][:, 1].min() > 0
