@@ -94,7 +94,7 @@ typedef struct rapt_params {
     int32_t dop853_reject_rule;      /* 0 = scipy 1.18.1 `_dop` (rejected step -> h/facc1); 1 = Hairer's Fortran */
     int32_t arith;                   /* 0 = fast (FMA contraction, reciprocal multiplies); 1 = strict
                                         (unfused, mirrors the CPU reference's operation order)    */
-    int32_t sort_by_work;            /* 1 = schedule particles longest-first (predicted steps from the initial state);
+    int32_t sort_by_work;            /* 1 = schedule tracers longest-first (predicted steps from the initial state);
                                         2 = _dev entry points only: the `counters` buffer still holds this tracer's counts
                                         from the previous call and its step count orders this call (0 there: as 1)     */
     int32_t reserved[3];

@@ -310,21 +310,31 @@ int check_field(const rapt_field_t *f)
     return RAPT_OK;
 }
 
-// work-order key of a tracer that was advanced before: 1 / (steps of the previous call), from the counters buffer the
-// caller left in place (rapt_params_t.sort_by_work = 2).  No history (0 steps): key 1, i.e. after every tracer that has one.
-__global__ void __launch_bounds__(256) k_key_previous(long long n, const int *__restrict__ counters, double *key, int *idx)
+// Work-order key of a guiding centre: 1 / (expected steps of this call).  A-priori estimate: DOPRI5 resolves the parallel
+// (bounce) motion, whose time scale is the transit time |r| / v of the tracer across its own distance from the origin of a
+// planet-centred field; ~23 steps per transit at the default tolerances on configs 3 and 5 (oracle counts, correlation 0.93 /
+// 0.96; list scheduling 2.2 % / 1.3 % above the ideal makespan against 8.5 % in member order: profiles/r2_work_order.md).
+// use_prev (rapt_params_t.sort_by_work = 2): the tracer's own step count of the previous call, left in the counters buffer
+// by the caller, replaces the estimate (0: no history).  Scheduling only.
+__global__ void __launch_bounds__(256) k_key_gc(long long n, const double *__restrict__ x, const double *__restrict__ y,
+                                               const double *__restrict__ z, const double *__restrict__ v,
+                                               const double *__restrict__ delta_arr, double delta,
+                                               const int *__restrict__ counters, int use_prev, double *key, int *idx)
 {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int prev = counters[4 * i + 1];
-    key[i] = prev > 0 ? 1.0 / (double)prev : 1.0;
+    const double r = sqrt(x[i] * x[i] + y[i] * y[i] + z[i] * z[i]);
+    double est = 23.0 * (delta_arr ? delta_arr[i] : delta) * v[i] / r;
+    if (!(est > 1.0) || est > 1e15) est = 1.0;                  // NaN, r = 0, v = 0: no estimate
+    if (use_prev) { const int prev = counters[4 * i + 1]; if (prev > 0) est = (double)prev; }
+    key[i] = 1.0 / est;
     idx[i] = (int)i;
 }
 
 // Longest-first schedule: sort particle indices by dt/delta ascending (fewest-rows last), so the lanes
 // that run dry at the end of the kernel are finishing the SHORTEST particles (SURVEY.md hard part H4).
-// previous_only: the key is the previous call's step count alone (guiding centres: there is no a-priori estimate).
-int build_order(const rapt_field_t *f, rapt::AdvArgs &a, bool strict, cudaStream_t s, bool previous_only = false)
+// gc: the guiding-centre key (k_key_gc) instead of the Particle one.
+int build_order(const rapt_field_t *f, rapt::AdvArgs &a, bool strict, cudaStream_t s, bool gc = false)
 {
     const size_t n = (size_t)a.nwork;
     if (g_sort.n < n) {
@@ -336,8 +346,9 @@ int build_order(const rapt_field_t *f, rapt::AdvArgs &a, bool strict, cudaStream
         CK(cudaMalloc(&g_sort.idx_out, n * sizeof(int)));
         g_sort.n = n;
     }
-    if (previous_only) {
-        k_key_previous<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((long long)n, a.counters, g_sort.key_in, g_sort.idx_in);
+    if (gc) {
+        k_key_gc<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((long long)n, a.s1, a.s2, a.s3, a.v, a.delta_arr, a.delta, a.counters,
+                                                             a.p.sort_by_work == 2 && !a.append, g_sort.key_in, g_sort.idx_in);
         CK(cudaGetLastError());
     } else if (int rc = launch_any(f, strict, UK_PARTICLE_DT, &a, (long long)n, 0, s, g_sort.key_in, g_sort.idx_in)) return rc;
     g_launches++;
@@ -737,8 +748,8 @@ int rapt_b200_gc_advance_dev(const rapt_field_t *f, const rapt_params_t *p, int 
     a.nstored = nstored; a.nrows = nrows; a.counters = counters; a.status = status; a.tcur = tcur;
     const bool strict = p->arith == 1;
     const int grid = grid_for(n, FLAVOUR(strict, gc_blocks_per_sm));
-    // longest-first from the previous call's step counts (sort_by_work = 2; there is no a-priori key for guiding centres)
-    if (p->sort_by_work == 2 && n > (long long)grid * 128) {
+    // longest-first: a-priori estimate (sort_by_work = 1) or the previous call's step counts (2): k_key_gc
+    if (p->sort_by_work && n > (long long)grid * 128) {
         if (int rc = build_order(f, a, strict, s, true)) return rc;
     }
     if (int rc = launch_any(f, strict, UK_GC, &a, n, grid, s)) return rc;

@@ -214,7 +214,7 @@ def test_work_order_from_previous_call(eng):
     for a, b in zip(*res):
         assert np.array_equal(a, b)
     assert np.all(res[0][3] == 1) and res[0][2][:, 1].min() > 0
-    # guiding centres: no a-priori key; with history the queue is sorted, without it the tracers are taken in member order
+    # guiding centres: a-priori key (transit time) on the first call, the previous call's step counts afterwards
     ic = synth.config3_electrons(n)
     pos = np.column_stack([ic["x"], ic["y"], ic["z"]])
     res = []
