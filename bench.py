@@ -328,16 +328,19 @@ def time_workload(args, workload, n_per_gpu, world, rank, dev, steps, warmup, wa
         weights = np.ones(world)
         for _ in range(int(args.rebalance)):
             one_step()
-            cev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-            one_step(cev)
+            cevs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(2)]
+            for cev in cevs:
+                one_step(cev)
             torch.cuda.synchronize()
-            mine = torch.tensor([cev[0].elapsed_time(cev[1]), float(ens.n)], dtype=torch.float64, device=dev)
+            mine = torch.tensor([min(cev[0].elapsed_time(cev[1]) for cev in cevs), float(ens.n)], dtype=torch.float64, device=dev)
             allm = torch.empty((world, 2), dtype=torch.float64, device=dev)
             dist.all_gather_into_tensor(allm.view(-1), mine)
             allm = allm.cpu().numpy()
             shard_history.append({"sizes": [int(v) for v in allm[:, 1]], "kernel_ms": [round(float(v), 3) for v in allm[:, 0]]})
+            if not (np.all(np.isfinite(allm)) and np.all(allm > 0)):
+                break                                     # no usable timing on some rank: keep the current cut
             speed = allm[:, 1] / allm[:, 0]
-            weights = speed / speed.mean()
+            weights = np.clip(speed / speed.mean(), 0.8, 1.25)     # one odd measurement must not empty a shard
             cur.clear()
             ens.reshard(weights)
             attach()
@@ -398,7 +401,7 @@ def time_workload(args, workload, n_per_gpu, world, rank, dev, steps, warmup, wa
                launches=int(launches), wall=wall, per_rank=per_rank, n=n, n_total=n_total,
                kernel_ms_rank0=ms_kernel / steps,
                shards=("round-robin" if not rebalance else
-                       f"time-weighted (rapt_b200/dist.py:ShardPlan; {int(args.rebalance)} calibration rounds of 2 steps each before the warm-up, outside the timed region)"))
+                       f"time-weighted (rapt_b200/dist.py:ShardPlan; {int(args.rebalance)} calibration rounds of 3 steps each before the warm-up, outside the timed region)"))
     if per_rank is not None:
         per_rank["shard_sizes"] = ens._plan.sizes()
         if shard_history:
