@@ -121,3 +121,38 @@ def test_shard_plan():
         rd.ShardPlan(10, 2, [1, 0])
     with pytest.raises(ValueError):
         rd.ShardPlan(10, 2, [1, 2, 3])
+
+
+def test_ensemble_shard_and_reshard_host_logic(monkeypatch):
+    """ParticleEnsemble.shard(weights) / reshard(): what each rank keeps (the device upload is stubbed out -- no GPU here).
+    Every member array is cut with the same ShardPlan indices, the cuts of all ranks partition the ensemble, a second cut
+    starts from the whole ensemble again, and reshard() without keep_full says so."""
+    import rapt_b200 as R
+    from rapt_b200 import synth, dist as rd, ensemble
+    n, world = 10007, 3
+    ic = synth.config2_protons(n)
+    pos = np.column_stack([ic["x"], ic["y"], ic["z"]]); vel = np.column_stack([ic["vx"], ic["vy"], ic["vz"]])
+    monkeypatch.setattr(ensemble.ParticleEnsemble, "cuda", lambda self, device="cuda:0": self)
+    full = R.ParticleEnsemble(pos, vel, 0.0, ic["mass"], ic["charge"], R.fields.EarthDipole())
+    seen = []
+    for rank in range(world):
+        monkeypatch.setattr(rd, "world_rank", lambda group=None, r=rank: (world, r))
+        ens = R.ParticleEnsemble(pos, vel, 0.0, ic["mass"], ic["charge"], R.fields.EarthDipole())
+        ens.shard(weights=[1.0, 2.0, 1.5], keep_full=True)
+        idx = rd.ShardPlan(n, world, [1.0, 2.0, 1.5]).indices(rank)
+        assert ens.n == len(idx) and ens.n_total == n and (ens.world, ens.rank) == (world, rank)
+        for name in ("state", "mass", "charge", "tcur", "counters", "status"):
+            assert np.array_equal(getattr(ens, name), getattr(full, name)[idx]), name
+        ens.reshard([1.0, 1.0, 1.0])                       # equal weights: runs of the period, not round-robin
+        idx2 = rd.ShardPlan(n, world, [1, 1, 1]).indices(rank)
+        assert ens.n == len(idx2) and np.array_equal(ens.state, full.state[idx2]) and not ens._plan.uniform
+        seen.append(idx2)
+        rr = R.ParticleEnsemble(pos, vel, 0.0, ic["mass"], ic["charge"], R.fields.EarthDipole()).shard()
+        assert rr._plan.uniform and np.array_equal(rr.state, full.state[rank::world])
+        with pytest.raises(RuntimeError):
+            rr.reshard([1, 1, 1])
+    assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(n))
+    # one process: nothing to cut, reshard is a no-op
+    monkeypatch.setattr(rd, "world_rank", lambda group=None: (1, 0))
+    one = R.ParticleEnsemble(pos, vel, 0.0, ic["mass"], ic["charge"], R.fields.EarthDipole()).shard(weights=[1.0], keep_full=True)
+    assert one.n == n and one.reshard([1.0]) is one
