@@ -400,7 +400,7 @@ def time_workload(args, workload, n_per_gpu, world, rank, dev, steps, warmup, wa
                failures=int(nall - nok), failed_members_rank0=[int(ens._plan.indices(rank)[int(i)]) for i in failed], clocks=clocks,
                launches=int(launches), wall=wall, per_rank=per_rank, n=n, n_total=n_total,
                kernel_ms_rank0=ms_kernel / steps,
-               shards=("round-robin" if not rebalance else
+               shards=("none (one GPU)" if world == 1 else "round-robin" if not rebalance else
                        f"time-weighted (rapt_b200/dist.py:ShardPlan; {int(args.rebalance)} calibration rounds of 3 steps each before the warm-up, outside the timed region)"))
     if per_rank is not None:
         per_rank["shard_sizes"] = ens._plan.sizes()
