@@ -8,6 +8,20 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import oracle as O
 from rapt_b200 import synth
 
+if len(sys.argv) > 1 and sys.argv[1] in ("gc", "belt"):
+    # guiding-centre ensembles (configs 3 and 5): python tools/work_order_counts.py gc|belt [n] [out.npz]
+    name = sys.argv[1]
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 131072
+    out = sys.argv[3] if len(sys.argv) > 3 else f"/tmp/wo/{name}_counts.npz"
+    gen, fld, dt = ((synth.config3_electrons, O.make_field("DoubleDipole"), 0.1) if name == "gc" else
+                    (synth.config5_belt, O.make_field("VarEarthDipole", 0.1, 10), 0.05))
+    ic = gen(n)
+    pos = np.column_stack([ic["x"], ic["y"], ic["z"]])
+    ppar, mu = O.gc_construct(fld, ic["t0"], pos, ic["v"], ic["pa"], ic["mass"])
+    st = np.column_stack([ic["t0"], pos, ppar])
+    o = O.gc_advance(fld, O.make_params(), st, mu, ic["v"], ic["mass"], ic["charge"], dt, 10.0, store_every=0, nthreads=os.cpu_count())
+    np.savez(out, counters=o["counters"], state=st, mu=mu, v=ic["v"], pa=ic["pa"], mass=ic["mass"], charge=ic["charge"])
+    sys.exit(0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 out = sys.argv[2] if len(sys.argv) > 2 else "/tmp/wo/cfg2_counts.npz"
 ic = synth.config2_protons(n)

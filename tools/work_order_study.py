@@ -64,7 +64,23 @@ def march(st, mass, q, delta, cres, nsub=400, c=1.0, p=1.0, adaptive=None):
     return steps, delta / dt_row
 
 
+def study_gc(paths):
+    """Guiding-centre keys (k_key_gc in capi.cu) against the oracle's counts: work_order_study.py gc <gc_counts.npz> ..."""
+    for path in paths:
+        d = np.load(path)
+        ns = d["counters"][:, 1].astype(float); st = d["state"]; v = d["v"]
+        n = len(ns); lanes = int(75776 * n / 1048576)
+        r = np.linalg.norm(st[:, 1:4], axis=1)
+        print(path, "steps per tracer: mean %.0f min %.0f max %.0f" % (ns.mean(), ns.min(), ns.max()),
+              " steps / (delta v / r): 1 %% %.1f median %.1f 99 %% %.1f" % tuple(np.quantile(ns / (10 * v / r), [0.01, 0.5, 0.99])))
+        for k, pr in {"member order": -np.arange(n).astype(float), "v/|r| (k_key_gc)": v / r, "true steps": ns}.items():
+            print("  %-20s corr %.4f  makespan/ideal %.4f" % (k, np.corrcoef(pr, ns)[0, 1], makespan(ns, -pr, lanes)))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "gc":
+        study_gc(sys.argv[2:] or ["/tmp/wo/gc_counts.npz", "/tmp/wo/belt_counts.npz"])
+        sys.exit(0)
     d = np.load(sys.argv[1] if len(sys.argv) > 1 else "/tmp/wo/cfg2_counts.npz")
     nmax = int(sys.argv[2]) if len(sys.argv) > 2 else len(d["mass"])
     st, mass, q = d["state"][:nmax], d["mass"][:nmax], d["charge"][:nmax]
