@@ -10,6 +10,66 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+# ---- independent restatements of the collection (plain torch.distributed calls, round-robin shards) that the product's
+# ---- gather_rows / reduce_diagnostics / ShardPlan are checked against
+def rd_shard_sizes(n_total, world):
+    return [len(range(r, n_total, world)) for r in range(world)]
+
+
+def unshard(gathered, n_total, world):
+    """Inverse of the round-robin sharding: `gathered[r]` holds rank r's rows (padded to the largest
+    shard); returns the (n_total, ...) array in global member order."""
+    sizes = rd_shard_sizes(n_total, world)
+    first = np.asarray(gathered[0])
+    out = np.empty((n_total,) + first.shape[1:], dtype=first.dtype)
+    for r in range(world):
+        out[r::world] = np.asarray(gathered[r])[:sizes[r]]
+    return out
+
+
+def all_gather_final(local, n_total, group=None):
+    """All-gather the per-rank final states (torch tensor (n_local, k), any device) and return the
+    global (n_total, k) tensor in member order on every rank."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n_max = max(rd_shard_sizes(n_total, world))
+    k = local.shape[1]
+    pad = torch.zeros((n_max, k), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    buf = torch.empty((world, n_max, k), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf.view(-1), pad.view(-1), group=group)
+    sizes = rd_shard_sizes(n_total, world)
+    out = torch.empty((n_total, k), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        out[r::world] = buf[r, :sizes[r]]
+    return out
+
+
+def all_reduce_histogram(values, bins, lo, hi, group=None):
+    """Histogram of a per-particle diagnostic over the whole ensemble (sum-all-reduce of local counts)."""
+    import torch
+    import torch.distributed as dist
+    h = torch.histc(values.to(torch.float64), bins=bins, min=lo, max=hi)
+    dist.all_reduce(h, group=group)
+    return h
+
+
+def all_reduce_stats(values, group=None):
+    """(count, sum, sum of squares, min, max) of a diagnostic over the whole ensemble."""
+    import torch
+    import torch.distributed as dist
+    v = values.to(torch.float64)
+    s = torch.stack([torch.tensor(float(v.numel()), dtype=torch.float64, device=v.device), v.sum(), (v * v).sum()])
+    mn = v.min().reshape(1); mx = v.max().reshape(1)
+    dist.all_reduce(s, group=group)
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    return dict(count=float(s[0]), mean=float(s[1] / s[0]), var=float(s[2] / s[0] - (s[1] / s[0]) ** 2),
+                min=float(mn[0]), max=float(mx[0]))
+
+
+
 def _worker(rank, world, port, n, out_dir):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
@@ -25,10 +85,10 @@ def _worker(rank, world, port, n, out_dir):
     o = O.particle_advance(O.make_field("EarthDipole"), O.make_params(cyclotronresolution=20), st[sl], ic["mass"][sl],
                            ic["charge"][sl], 0.05, store_every=0)
     local = torch.tensor(np.column_stack([o["state"], o["counters"][:, 1].astype(np.float64)]))
-    full = rd.all_gather_final(local, n)
+    full = all_gather_final(local, n)
     p = torch.tensor(np.linalg.norm(o["state"][:, 4:7], axis=1))
-    h = rd.all_reduce_histogram(torch.log10(p), 16, -21.0, -19.0)
-    stats = rd.all_reduce_stats(p)
+    h = all_reduce_histogram(torch.log10(p), 16, -21.0, -19.0)
+    stats = all_reduce_stats(p)
     # the product's collection path (rapt_b200/ensemble.py:gather): this rank's rows already sit in its slot of the
     # gather buffer (on the GPU the packing kernel writes them there), in-place all-gather, reduce of hist + sums
     n_max = max(rd.shard_sizes(n, world))
@@ -89,7 +149,7 @@ def test_shard_helpers():
             pad = np.full(max(sizes) if sizes else 0, -1); pad[:len(a)] = a
             parts.append(pad[:, None])
         if n:
-            assert np.array_equal(rd.unshard(parts, n, w)[:, 0], idx)
+            assert np.array_equal(unshard(parts, n, w)[:, 0], idx)
 
 
 def test_shard_plan():
